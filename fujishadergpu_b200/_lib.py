@@ -1,0 +1,110 @@
+"""ctypes binding of libfsg_b200.so (the C ABI declared in include/fsg_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, the caller
+gets an exception (ValueError for argument errors, as the reference raises; RuntimeError otherwise).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from .build import LIB_PATH
+
+FSG_OUT_F32, FSG_OUT_I16, FSG_OUT_U8 = 0, 1, 2
+_KIND = {"float32": FSG_OUT_F32, "int16": FSG_OUT_I16, "uint8": FSG_OUT_U8}
+NONE = float("nan")  # "None" for optional doubles
+
+
+class Encode(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("dn_min", C.c_int32), ("dn_max", C.c_int32), ("_pad", C.c_int32),
+                ("a_coef", C.c_double), ("b_coef", C.c_double)]
+
+
+class Window(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in
+                ("H_global", "W", "buf_row0", "buf_rows", "out_row0", "out_rows", "ld_in", "ld_out")]
+
+
+_P = C.c_void_p
+_D = C.c_double
+_I = C.c_int
+_L = C.c_int64
+_SIGNATURES = {
+    "fsg_last_error": (C.c_char_p, []),
+    "fsg_version": (_I, []),
+    "fsg_launch_count": (_L, []),
+    "fsg_reset_launch_count": (None, []),
+    "fsg_hillshade": (_I, [_P, _P, C.POINTER(Window), _D, _D, _D, _D, _D, _D, C.POINTER(Encode), _P]),
+    "fsg_slope": (_I, [_P, _P, C.POINTER(Window), _I, _D, _D, _D, C.POINTER(Encode), _P]),
+    "fsg_curvature": (_I, [_P, _P, C.POINTER(Window), _I, _D, _D, _D, C.POINTER(Encode), _P]),
+    "fsg_topousm_fast_workspace_bytes": (C.c_size_t, [_L, _L, C.POINTER(C.c_int32), _I, _D]),
+    "fsg_topousm_fast": (_I, [_P, _P, _L, _L, _L, _L, C.POINTER(C.c_int32), C.POINTER(C.c_float), _I,
+                              _D, _D, C.POINTER(Encode), _P, C.c_size_t, _P]),
+    "fsg_topousm_large_part": (_I, [_P, _P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _L, _L, _L, _D, _P]),
+    "fsg_openness": (_I, [_P, _P, C.POINTER(Window), _I, _I, _I, _D, _D, _D, _D, _D, C.POINTER(Encode), _P]),
+    "fsg_decimate_workspace_bytes": (C.c_size_t, [_L, _L, _I]),
+    "fsg_decimate": (_I, [_P, _P, _L, _L, _L, _I, _P, C.c_size_t, _P]),
+    "fsg_upsample": (_I, [_P, _P, _L, _L, _L, _L, _P, C.c_size_t, _P]),
+    "fsg_openness_samples": (_I, [_P, _P, C.POINTER(Window), _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                  C.POINTER(C.c_int32), C.POINTER(C.c_float), _D, _D, C.POINTER(Encode), _P]),
+    "fsg_encode_f32": (_I, [_P, _P, _L, C.POINTER(Encode), _P]),
+    "fsg_scale_f32": (_I, [_P, _P, _L, _D, _P]),
+    "fsg_stretch_f32": (_I, [_P, _P, _L, _D, _D, _P]),
+    "fsg_order_stats_workspace_bytes": (C.c_size_t, []),
+    "fsg_order_stats": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, _L, _I, _I,
+                             _P, _P, C.c_size_t, _P]),
+    "fsg_synth_dem": (_I, [_P, _L, _L, _L, _L, _L, C.c_uint64, _I, _P]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class FsgError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    """Names include/fsg_b200.h declares (used by the CPU-side symbol test)."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise FsgError(
+                    f"{LIB_PATH} is missing: build it with `python -m fujishadergpu_b200.build` "
+                    "(there is no CPU or CuPy fallback for the hot path)")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc == 0:
+        return
+    msg = load().fsg_last_error().decode("utf-8", "replace")
+    if rc == -1:
+        raise ValueError(msg)
+    raise FsgError(f"{what or 'libfsg_b200'} failed (code {rc}): {msg}")
+
+
+def make_encode(output_dtype: str = "float32", qp: dict | None = None) -> Encode:
+    kind = _KIND[str(output_dtype)]
+    if kind == FSG_OUT_F32 or qp is None:
+        return Encode(FSG_OUT_F32, 0, 0, 0, 1.0, 0.0)
+    return Encode(kind, int(qp["dn_min"]), int(qp["dn_max"]), 0, float(qp["a_coef"]), float(qp["b_coef"]))
+
+
+def opt(v) -> float:
+    """Optional double -> NaN sentinel."""
+    return NONE if v is None else float(v)

@@ -1,0 +1,115 @@
+"""Host-side radius / weight resolution and the device helpers the block functions share
+(reference: algorithms/_nan_utils.py).  Only the pieces on the hot path are provided; the image
+arithmetic itself lives in the CUDA library."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from .. import kernels as _k
+from .. import _device as _dev
+from .common.spatial_mode import auto_spatial_profile, auto_spatial_radii, auto_spatial_weights
+
+_ALGO_SCORE = {
+    "topousm_fast": 1.15, "hillshade": 1.0, "slope": 1.0, "specular": 1.4, "atmospheric_scattering": 1.05,
+    "curvature": 1.1, "ambient_occlusion": 1.5, "openness": 1.4, "multi_light_uncertainty": 1.25,
+}
+
+
+def _radius_to_downsample_factor(radius: float, *, block_shape: Optional[Tuple[int, int]] = None,
+                                 pixel_size: float = 1.0, algorithm_name: str = "default",
+                                 base_radius: float = 24.0, max_factor: int = 16) -> int:
+    """reference :555-601 -- power-of-two decimation from the radius; independent of block_shape."""
+    r = max(1.0, float(radius))
+    px = max(1e-3, float(pixel_size) if pixel_size else 1.0)
+    gain = float(_ALGO_SCORE.get(str(algorithm_name), 1.0))
+    score = (r / max(1.0, base_radius)) * gain * 1.0 * (max(1.0, 1.0 / px) ** 0.35)
+    if score <= 1.0:
+        return 1
+    return int(max(1, min(2 ** int(np.floor(np.log2(score))), max_factor)))
+
+
+def _weight_count_matches(weights, expected: int) -> bool:
+    if weights is None or isinstance(weights, (str, bytes)):
+        return False
+    try:
+        return len(weights) == expected
+    except TypeError:
+        return False
+
+
+def _clean_normalized_weights(weights) -> Optional[List[float]]:
+    """reference :142-154 -- clip to >= 0, L1-normalise; None when nothing positive is left."""
+    vals: List[float] = []
+    for w in weights:
+        try:
+            x = float(w)
+        except (TypeError, ValueError):
+            return None
+        vals.append(x if np.isfinite(x) and x > 0 else 0.0)
+    tot = float(sum(vals))
+    if tot <= 0:
+        return None
+    return [v / tot for v in vals]
+
+
+def _normalize_spatial_radii(radii, pixel_size: float) -> List[int]:
+    """reference :77-98 -- ints > 0, order kept, duplicates dropped; auto ladder when empty."""
+    if radii is None:
+        return auto_spatial_radii(None)
+    seen, kept = set(), []
+    for r in radii:
+        try:
+            v = int(round(float(r)))
+        except (TypeError, ValueError):
+            continue
+        if v > 0 and v not in seen:
+            seen.add(v)
+            kept.append(v)
+    return kept if kept else auto_spatial_radii(None)
+
+
+def _resolve_spatial_radii_weights(radii, weights, pixel_size: float, short_side_px: Optional[float] = None):
+    """reference :101-130."""
+    if radii is None:
+        rr, ww = auto_spatial_profile(short_side_px)
+        if _weight_count_matches(weights, len(rr)):
+            user = _clean_normalized_weights(weights)
+            if user is not None:
+                return rr, user
+        return rr, ww
+    rr = _normalize_spatial_radii(radii, pixel_size)
+    if _weight_count_matches(weights, len(rr)):
+        user = _clean_normalized_weights(weights)
+        if user is not None:
+            return rr, user
+    return rr, auto_spatial_weights(len(rr))
+
+
+def _downsample_nan_aware(block, factor: int):
+    """reference :604-668 -- device array in, device array out."""
+    if factor <= 1:
+        return block
+    return _dev.like_input(_k.decimate(block, int(factor)), block)
+
+
+def _upsample_to_shape(block, target_shape):
+    """reference :671-698."""
+    return _dev.like_input(_k.upsample(block, target_shape), block)
+
+
+def _bilinear_sample_coarse(coarse, r0: int, r1: int, c0: int, c1: int, full_h: int, full_w: int):
+    """reference :255-281 (through the fused large-part kernel with w_large = 0 on a zero block)."""
+    import torch
+    t = _dev.as_f32_2d(coarse)
+    zero = torch.zeros((int(r1 - r0), int(c1 - c0)), dtype=torch.float32, device=t.device)
+    up = _k.topousm_large_part(zero, t, w_large=0.0, off_r=int(r0), off_c=int(c0), full_h=int(full_h), full_w=int(full_w))
+    return _dev.like_input(-up, coarse)
+
+
+__all__ = [
+    "_radius_to_downsample_factor", "_resolve_spatial_radii_weights", "_normalize_spatial_radii",
+    "_clean_normalized_weights", "_weight_count_matches", "_downsample_nan_aware", "_upsample_to_shape",
+    "_bilinear_sample_coarse",
+]

@@ -1,0 +1,105 @@
+// Shared device/host helpers for libfsg_b200 (sm_100a).
+// Compiled with -fmad=false: every f32 product/sum below is an individually rounded IEEE op,
+// like the NumPy/CuPy elementwise expressions it mirrors.  Where a fused multiply-add is wanted
+// (f64 helpers) it is written explicitly with fma().
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/fsg_b200.h"
+
+namespace fsg {
+
+// ---- host-side error plumbing ------------------------------------------------------------
+char* last_error_buf();
+void count_launch(int n = 1);
+int fail(int code, const char* fmt, ...);
+
+#define FSG_CUDA_OK(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      return fsg::fail(FSG_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define FSG_LAUNCH_OK()                                                                \
+  do {                                                                                 \
+    fsg::count_launch();                                                               \
+    cudaError_t _e = cudaPeekAtLastError();                                            \
+    if (_e != cudaSuccess)                                                             \
+      return fsg::fail(FSG_E_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+inline bool is_none(double v) { return v != v; }
+
+// Step sizes as the reference resolves them (algorithms/_nan_utils.py:64-71,
+// _impl_curvature.py:23-28): `signed_steps` keeps the geotransform sign.
+inline void resolve_steps(double pixel_size, double psx, double psy, bool signed_steps, double* sy, double* sx) {
+  double y = is_none(psy) ? pixel_size : psy;
+  double x = is_none(psx) ? pixel_size : psx;
+  if (!signed_steps) { y = fabs(y); x = fabs(x); }
+  if (fabs(y) < 1e-9) y = (pixel_size != 0.0) ? pixel_size : 1.0;
+  if (fabs(x) < 1e-9) x = (pixel_size != 0.0) ? pixel_size : 1.0;
+  *sy = y; *sx = x;
+}
+
+// Gaussian taps exactly as scipy.ndimage builds them (radius int(4*sigma+0.5), normalised f64).
+// Returns radius; w[0..radius] = centre..outermost (symmetric).
+int gauss_half_taps(double sigma, double* w, int max_radius);
+
+// ---- device helpers ----------------------------------------------------------------------
+struct EncodeDev {
+  int kind;
+  float a, b, lo, hi;
+};
+inline EncodeDev make_encode(const fsg_encode* e) {
+  EncodeDev d;
+  d.kind = e ? e->kind : FSG_OUT_F32;
+  d.a = e ? (float)e->a_coef : 1.f;
+  d.b = e ? (float)e->b_coef : 0.f;
+  d.lo = e ? (float)e->dn_min : 0.f;
+  d.hi = e ? (float)e->dn_max : 0.f;
+  return d;
+}
+inline size_t out_elem_size(int kind) { return kind == FSG_OUT_U8 ? 1 : (kind == FSG_OUT_I16 ? 2 : 4); }
+
+#ifdef __CUDACC__
+// DN = clip(rint(a*v + b), lo, hi); non-finite -> 0  (core/dask_processor.py:1004-1008)
+__device__ __forceinline__ float encode_dn(float v, const EncodeDev& e) {
+  float dn = rintf(e.a * v + e.b);
+  dn = fminf(fmaxf(dn, e.lo), e.hi);
+  return isfinite(v) ? dn : 0.f;
+}
+__device__ __forceinline__ void store_out(void* out, int64_t idx, float v, const EncodeDev& e) {
+  if (e.kind == FSG_OUT_F32) {
+    ((float*)out)[idx] = v;
+  } else if (e.kind == FSG_OUT_U8) {
+    ((uint8_t*)out)[idx] = (uint8_t)(int)encode_dn(v, e);
+  } else {
+    ((int16_t*)out)[idx] = (int16_t)(int)encode_dn(v, e);
+  }
+}
+
+// scipy 'reflect' (edge-inclusive mirror, d c b a | a b c d | d c b a), any distance.
+__device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
+  if (n == 1) return 0;
+  int64_t p = 2 * n;
+  i %= p;
+  if (i < 0) i += p;
+  return i < n ? i : p - 1 - i;
+}
+__device__ __forceinline__ int64_t clamp_index(int64_t i, int64_t n) { return i < 0 ? 0 : (i >= n ? n - 1 : i); }
+
+// Correctly rounded f64 quotient s/n for a small positive integer n given inv = 1/n (rounded):
+// one Newton correction of the rounded product (Markstein).
+__device__ __forceinline__ double div_by_count(double s, double n, double inv) {
+  double q = s * inv;
+  double r = fma(-q, n, s);
+  return fma(r, inv, q);
+}
+#endif
+
+}  // namespace fsg

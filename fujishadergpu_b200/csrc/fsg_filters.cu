@@ -1,0 +1,207 @@
+// Generic NaN-aware separable box / Gaussian passes (see fsg_filters.cuh for the contract).
+#include "fsg_filters.cuh"
+
+namespace fsg {
+
+constexpr int A0_CHUNK = 128;  // rows per thread in the axis-0 running-sum pass
+constexpr int A1_CW = 256;     // output columns per CTA in the axis-1 pass
+
+// ---------------------------------------------------------------- box, axis 0 (running sums)
+__global__ void __launch_bounds__(128) box_axis0_kernel(Grid g, int size, float* __restrict__ tv, float* __restrict__ tw) {
+  int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= g.w) return;
+  int64_t y0 = (int64_t)blockIdx.y * A0_CHUNK;
+  int64_t y1 = y0 + A0_CHUNK < g.h ? y0 + A0_CHUNK : g.h;
+  const int lo = size / 2, hi = size - 1 - lo;
+  const double n = (double)size, inv = 1.0 / n;
+  const float nf = (float)size;
+  double s = 0.0;
+  int cnt = 0;
+  for (int k = -lo; k <= hi; ++k) {
+    float v = g.src[reflect_index(y0 + k, g.h) * g.ld + x];
+    bool ok = v == v;
+    s += ok ? (double)v : 0.0;
+    cnt += ok;
+  }
+  for (int64_t y = y0; y < y1; ++y) {
+    tv[y * g.w + x] = (float)div_by_count(s, n, inv);
+    tw[y * g.w + x] = (float)cnt / nf;
+    float vin = g.src[reflect_index(y + hi + 1, g.h) * g.ld + x];
+    float vout = g.src[reflect_index(y - lo, g.h) * g.ld + x];
+    bool oin = vin == vin, oout = vout == vout;
+    s += (oin ? (double)vin : 0.0) - (oout ? (double)vout : 0.0);
+    cnt += (int)oin - (int)oout;
+  }
+}
+
+// ---------------------------------------------------------------- box, axis 1 (smem tiles)
+template <int RT>
+__global__ void __launch_bounds__(256) box_axis1_kernel(const float* __restrict__ tv, const float* __restrict__ tw,
+                                                        int64_t h, int64_t w, int size, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int span = A1_CW + size - 1;
+  const int P = span | 1;
+  float* sv_p = sm;
+  float* sw_p = sm + (size_t)RT * P;
+  float* so_p = sw_p + (size_t)RT * P;  // RT x (A1_CW+1)
+  const int64_t x0 = (int64_t)blockIdx.x * A1_CW;
+  const int64_t y0 = (int64_t)blockIdx.y * RT;
+  const int lo = size / 2;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < RT * span; idx += 256) {
+    int r = idx / span, c = idx - r * span;
+    int64_t gy = y0 + r;
+    float a = 0.f, b = 0.f;
+    if (gy < h) {
+      int64_t gx = reflect_index(x0 - lo + c, w);
+      a = tv[gy * w + gx];
+      b = tw[gy * w + gx];
+    }
+    sv_p[r * P + c] = a;
+    sw_p[r * P + c] = b;
+  }
+  __syncthreads();
+  constexpr int NSEG = 256 / RT;
+  constexpr int SEGLEN = A1_CW / NSEG;
+  const int r = tid % RT, gseg = tid / RT;
+  const int j0 = gseg * SEGLEN;
+  if (y0 + r < h && x0 + j0 < w) {
+    const double n = (double)size, inv = 1.0 / n;
+    const float* pv = sv_p + r * P + j0;
+    const float* pw = sw_p + r * P + j0;
+    double sv = 0.0, sw = 0.0;
+    for (int k = 0; k < size; ++k) {
+      sv += (double)pv[k];
+      sw += (double)pw[k];
+    }
+    for (int jj = 0; jj < SEGLEN; ++jj) {
+      float num = (float)div_by_count(sv, n, inv);
+      float den = (float)div_by_count(sw, n, inv);
+      so_p[r * (A1_CW + 1) + j0 + jj] = den > 0.f ? num / den : 0.f;
+      sv += (double)pv[jj + size] - (double)pv[jj];
+      sw += (double)pw[jj + size] - (double)pw[jj];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < RT * A1_CW; idx += 256) {
+    int rr = idx / A1_CW, c = idx - rr * A1_CW;
+    if (y0 + rr < h && x0 + c < w) out[(y0 + rr) * w + x0 + c] = so_p[rr * (A1_CW + 1) + c];
+  }
+}
+
+// ---------------------------------------------------------------- gaussian passes (direct)
+__global__ void gauss_taps_kernel(double sigma, int radius, double* w) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s2 = sigma * sigma, tot = 0.0;
+  for (int x = -radius; x <= radius; ++x) tot += exp(-0.5 / s2 * (double)x * (double)x);
+  for (int x = 0; x <= radius; ++x) w[x] = exp(-0.5 / s2 * (double)x * (double)x) / tot;
+}
+
+__global__ void __launch_bounds__(256) gauss_axis0_kernel(Grid g, const double* __restrict__ taps, int radius,
+                                                          float* __restrict__ tv, float* __restrict__ tw,
+                                                          const int* run_flag) {
+  if (run_flag && *run_flag == 0) return;
+  int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t y = (int64_t)blockIdx.y + (int64_t)blockIdx.z * 32768;
+  if (x >= g.w || y >= g.h) return;
+  auto at = [&](int64_t yy, double* ok) {
+    float v = g.src[clamp_index(yy, g.h) * g.ld + x];
+    bool good = v == v;
+    *ok = good ? 1.0 : 0.0;
+    return good ? (double)v : 0.0;
+  };
+  double o0;
+  double v0 = at(y, &o0);
+  double sv = v0 * taps[0], sw = o0 * taps[0];
+  for (int j = radius; j >= 1; --j) {
+    double oa, ob;
+    double va = at(y - j, &oa), vb = at(y + j, &ob);
+    sv += (va + vb) * taps[j];
+    sw += (oa + ob) * taps[j];
+  }
+  tv[y * g.w + x] = (float)sv;
+  tw[y * g.w + x] = (float)sw;
+}
+
+__global__ void __launch_bounds__(256) gauss_axis1_kernel(const float* __restrict__ tv, const float* __restrict__ tw,
+                                                          int64_t h, int64_t w, const double* __restrict__ taps,
+                                                          int radius, int combine, float* out, const int* run_flag,
+                                                          int* still_nan) {
+  if (run_flag && *run_flag == 0) return;
+  int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t y = (int64_t)blockIdx.y + (int64_t)blockIdx.z * 32768;
+  if (x >= w || y >= h) return;
+  if (combine == COMBINE_VOIDFILL) {
+    float cur = out[y * w + x];
+    if (cur == cur) return;  // only void cells are candidates
+  }
+  const float* rv = tv + y * w;
+  const float* rw = tw + y * w;
+  double sv = (double)rv[x] * taps[0], sw = (double)rw[x] * taps[0];
+  for (int j = radius; j >= 1; --j) {
+    int64_t xa = clamp_index(x - j, w), xb = clamp_index(x + j, w);
+    sv += ((double)rv[xa] + (double)rv[xb]) * taps[j];
+    sw += ((double)rw[xa] + (double)rw[xb]) * taps[j];
+  }
+  float fv = (float)sv, fw = (float)sw;
+  if (combine == COMBINE_MEAN) {
+    out[y * w + x] = fw > 0.f ? fv / fw : 0.f;
+  } else {
+    if (fw > 0.5f) out[y * w + x] = fv / fmaxf(fw, 1e-6f);
+    else if (still_nan) *still_nan = 1;
+  }
+}
+
+// ---------------------------------------------------------------- launchers
+int launch_box_axis0(const Grid& g, int size, float* tv, float* tw, cudaStream_t s) {
+  dim3 grid((unsigned)((g.w + 127) / 128), (unsigned)((g.h + A0_CHUNK - 1) / A0_CHUNK));
+  box_axis0_kernel<<<grid, 128, 0, s>>>(g, size, tv, tw);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+template <int RT>
+static int launch_a1(const float* tv, const float* tw, int64_t h, int64_t w, int size, float* out, cudaStream_t s,
+                     size_t smem) {
+  FSG_CUDA_OK(cudaFuncSetAttribute(box_axis1_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((w + A1_CW - 1) / A1_CW), (unsigned)((h + RT - 1) / RT));
+  box_axis1_kernel<RT><<<grid, 256, smem, s>>>(tv, tw, h, w, size, out);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int launch_box_axis1(const float* tv, const float* tw, int64_t h, int64_t w, int size, float* out, cudaStream_t s) {
+  auto need = [&](int rt) {
+    size_t P = (size_t)((A1_CW + size - 1) | 1);
+    return (size_t)rt * P * 8 + (size_t)rt * (A1_CW + 1) * 4;
+  };
+  const size_t cap = 220 * 1024;
+  if (need(32) <= cap) return launch_a1<32>(tv, tw, h, w, size, out, s, need(32));
+  if (need(8) <= cap) return launch_a1<8>(tv, tw, h, w, size, out, s, need(8));
+  if (need(1) <= cap) return launch_a1<1>(tv, tw, h, w, size, out, s, need(1));
+  return fail(FSG_E_UNSUPPORTED, "box filter of %d taps exceeds the shared-memory tile budget", size);
+}
+
+int launch_gauss_taps(double sigma, int radius, double* taps_dev, cudaStream_t s) {
+  gauss_taps_kernel<<<1, 32, 0, s>>>(sigma, radius, taps_dev);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int launch_gauss_axis0(const Grid& g, const double* taps_dev, int radius, float* tv, float* tw, const int* run_flag,
+                       cudaStream_t s) {
+  dim3 grid((unsigned)((g.w + 255) / 256), (unsigned)(g.h < 32768 ? g.h : 32768), (unsigned)((g.h + 32767) / 32768));
+  gauss_axis0_kernel<<<grid, 256, 0, s>>>(g, taps_dev, radius, tv, tw, run_flag);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int launch_gauss_axis1(const float* tv, const float* tw, int64_t h, int64_t w, const double* taps_dev, int radius,
+                       int combine, float* out, const int* run_flag, int* still_nan, cudaStream_t s) {
+  dim3 grid((unsigned)((w + 255) / 256), (unsigned)(h < 32768 ? h : 32768), (unsigned)((h + 32767) / 32768));
+  gauss_axis1_kernel<<<grid, 256, 0, s>>>(tv, tw, h, w, taps_dev, radius, combine, out, run_flag, still_nan);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+}  // namespace fsg

@@ -1,0 +1,38 @@
+// Generic NaN-aware separable filters on f32 grids (used on the decimated pyramid levels, for the
+// sigma=1 Gaussian of local mode, for the coarse enclosed-void fill, and as the general fallback).
+//
+// Arithmetic contract (== scipy.ndimage on f32 input, which cupyx.scipy.ndimage mirrors):
+//   * each axis pass accumulates in f64 and rounds ONCE to f32; axis 0 first;
+//   * box ('reflect'): exact window sum / size, correctly rounded;
+//   * gaussian ('nearest'): centre*w0 + sum_{j=R..1} (x[-j]+x[+j])*w[j]  (scipy's symmetric order);
+//   * NaN-aware form of handle_nan_with_uniform/_gaussian (algorithms/_nan_utils.py:18-47):
+//       mean = U(filled)/U(valid) where U(valid) > 0 else 0.
+//     Evaluated per pixel; on a NaN-free grid U(valid) == 1.0f exactly, so it coincides bit for bit
+//     with the reference's plain branch and no block-level `.any()` sync is needed.
+#pragma once
+#include "fsg_common.cuh"
+
+namespace fsg {
+
+struct Grid {
+  const float* src;  // input grid (may hold NaN)
+  int64_t h, w, ld;
+};
+
+// pass A (axis 0).  tv/tw: f32 planes h x w (ld = w).
+int launch_box_axis0(const Grid& g, int size, float* tv, float* tw, cudaStream_t s);
+int launch_gauss_axis0(const Grid& g, const double* taps_dev, int radius, float* tv, float* tw, const int* run_flag,
+                       cudaStream_t s);
+
+// pass B (axis 1) + combine.  mode 0: mean = tw>0 ? tv/tw : 0 -> out
+//                            mode 1 (void fill, _nan_utils.py:655-667): where isnan(orig) & (sw > 0.5):
+//                                    orig = sv / max(sw, 1e-6) (in place); sets *still_nan if NaN remains
+enum { COMBINE_MEAN = 0, COMBINE_VOIDFILL = 1 };
+int launch_box_axis1(const float* tv, const float* tw, int64_t h, int64_t w, int size, float* out, cudaStream_t s);
+int launch_gauss_axis1(const float* tv, const float* tw, int64_t h, int64_t w, const double* taps_dev, int radius,
+                       int combine, float* out, const int* run_flag, int* still_nan, cudaStream_t s);
+
+// taps for sigma (device side, f64): w[0..radius]
+int launch_gauss_taps(double sigma, int radius, double* taps_dev, cudaStream_t s);
+
+}  // namespace fsg

@@ -1,0 +1,292 @@
+// Gradient family: hillshade / slope / curvature as ONE fused pass per algorithm.
+//
+// Reference arithmetic (every f32 op individually rounded, no FMA):
+//   handle_nan_for_gradient  algorithms/_nan_utils.py:50-74   (NaN gap fill + np.gradient edge_order=2)
+//   compute_hillshade_block  algorithms/_impl_hillshade.py:20-54
+//   compute_slope_block      algorithms/_impl_slope.py:19-35
+//   compute_curvature_block  algorithms/_impl_curvature.py:19-57
+//
+// Layout: a CTA of 256 threads owns a 64x32 output tile.  The gap-filled, z-scaled DEM tile plus a
+// 2-px (hillshade/slope) or 3-px (curvature) halo is staged once in shared memory; curvature also
+// stages the first derivatives on tile+2.  Global traffic: one read of the DEM (+halo re-reads that
+// hit L2) and one write of the result -- 8 B/px (f32 out), 5 B/px (u8 out).
+#include "fsg_common.cuh"
+
+namespace fsg {
+
+constexpr int GT_W = 64;
+constexpr int GT_H = 32;
+constexpr int G_THREADS = 256;
+
+struct AxisCoef {  // np.gradient(edge_order=2) coefficients for one axis, already f32
+  float two_h;     // f32(2*h)           interior: (f[i+1]-f[i-1]) / two_h
+  float a0, b0, c0;  // first sample:   a0*f0 + b0*f1 + c0*f2
+  float a1, b1, c1;  // last sample:    a1*f[n-3] + b1*f[n-2] + c1*f[n-1]
+};
+
+static AxisCoef make_axis(double h) {
+  AxisCoef c;
+  c.two_h = (float)(2.0 * h);
+  c.a0 = (float)(-1.5 / h); c.b0 = (float)(2.0 / h); c.c0 = (float)(-0.5 / h);
+  c.a1 = (float)(0.5 / h);  c.b1 = (float)(-2.0 / h); c.c1 = (float)(1.5 / h);
+  return c;
+}
+
+struct GradParams {
+  const float* dem;
+  void* out;
+  int64_t H, W, buf_row0, buf_rows, out_row0, out_rows, ld_in, ld_out;
+  float zscale;
+  AxisCoef y1, x1;  // first derivatives (|step|)
+  AxisCoef y2, x2;  // second derivatives (signed step; curvature only)
+  float lx, ly, lz, sgx, sgy;  // hillshade light vector / orientation signs
+  int sub;                     // slope unit or curvature type
+  double gw[5];                // sigma=1 Gaussian half taps (centre..outer)
+  EncodeDev enc;
+};
+
+// NaN-aware sigma=1 Gaussian at one pixel (handle_nan_with_gaussian, mode='nearest'): separable,
+// axis 0 first, f64 accumulation in scipy's symmetric order, f32 between the passes.
+__device__ float gap_fill(const GradParams& p, int64_t gy, int64_t gx) {
+  float colv[9], colw[9];
+#pragma unroll 1
+  for (int k = 0; k < 9; ++k) {
+    int64_t x = clamp_index(gx + k - 4, p.W);
+    auto at = [&](int64_t y, float* ok) {
+      y = clamp_index(y, p.H) - p.buf_row0;
+      y = y < 0 ? 0 : (y >= p.buf_rows ? p.buf_rows - 1 : y);
+      float v = p.dem[y * p.ld_in + x];
+      bool nan = v != v;
+      *ok = nan ? 0.f : 1.f;
+      return nan ? 0.f : v;
+    };
+    float o0;
+    float v0 = at(gy, &o0);
+    double sv = (double)v0 * p.gw[0];
+    double sw = (double)o0 * p.gw[0];
+#pragma unroll
+    for (int j = 4; j >= 1; --j) {
+      float oa, ob;
+      float va = at(gy - j, &oa);
+      float vb = at(gy + j, &ob);
+      sv += ((double)va + (double)vb) * p.gw[j];
+      sw += ((double)oa + (double)ob) * p.gw[j];
+    }
+    colv[k] = (float)sv;
+    colw[k] = (float)sw;
+  }
+  double sv = (double)colv[4] * p.gw[0];
+  double sw = (double)colw[4] * p.gw[0];
+#pragma unroll
+  for (int j = 4; j >= 1; --j) {
+    sv += ((double)colv[4 - j] + (double)colv[4 + j]) * p.gw[j];
+    sw += ((double)colw[4 - j] + (double)colw[4 + j]) * p.gw[j];
+  }
+  float fv = (float)sv, fw = (float)sw;
+  return fw > 0.f ? fv / fw : 0.f;
+}
+
+// derivative along one axis of a shared-memory plane; `g` is the global index along the axis,
+// `n` the raster extent, `s` the element stride along that axis.
+__device__ __forceinline__ float deriv(const float* f, int s, int64_t g, int64_t n, const AxisCoef& c) {
+  if (g == 0) return (c.a0 * f[0] + c.b0 * f[s]) + c.c0 * f[2 * s];
+  if (g == n - 1) return (c.a1 * f[-2 * s] + c.b1 * f[-s]) + c.c1 * f[0];
+  return (f[s] - f[-s]) / c.two_h;
+}
+
+template <int CLASS>  // 0 hillshade, 1 slope, 2 curvature
+__global__ void __launch_bounds__(G_THREADS) grad_kernel(GradParams p) {
+  constexpr int HALO = (CLASS == 2) ? 3 : 2;
+  constexpr int FW = GT_W + 2 * HALO + 1;  // +1: odd stride, fewer bank conflicts
+  constexpr int FH = GT_H + 2 * HALO;
+  constexpr int DW = GT_W + 4 + 1;
+  constexpr int DH = GT_H + 4;
+  __shared__ float F[FH * FW];
+  __shared__ unsigned char M[GT_H * GT_W];
+  __shared__ float DY[(CLASS == 2) ? DH * DW : 1];
+  __shared__ float DX[(CLASS == 2) ? DH * DW : 1];
+
+  const int64_t ty0 = p.out_row0 + (int64_t)blockIdx.y * GT_H;  // global row of tile origin
+  const int64_t tx0 = (int64_t)blockIdx.x * GT_W;
+  const int tid = threadIdx.x;
+
+  // ---- stage gap-filled, scaled DEM ----
+  for (int i = tid; i < FH * (GT_W + 2 * HALO); i += G_THREADS) {
+    int fy = i / (GT_W + 2 * HALO), fx = i - fy * (GT_W + 2 * HALO);
+    int64_t gy = ty0 - HALO + fy, gx = tx0 - HALO + fx;
+    float v = 0.f;
+    bool inside = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+    bool nan = false;
+    if (inside) {
+      int64_t by = gy - p.buf_row0;
+      if (by >= 0 && by < p.buf_rows) {
+        v = p.dem[by * p.ld_in + gx];
+        nan = v != v;
+        if (nan) v = gap_fill(p, gy, gx);
+        v = v * p.zscale;
+      }
+    }
+    F[fy * FW + fx] = v;
+    int cy = fy - HALO, cx = fx - HALO;
+    if (cy >= 0 && cy < GT_H && cx >= 0 && cx < GT_W) M[cy * GT_W + cx] = nan ? 1 : 0;
+  }
+  __syncthreads();
+
+  if (CLASS == 2) {
+    for (int i = tid; i < DH * (GT_W + 4); i += G_THREADS) {
+      int dyi = i / (GT_W + 4), dxi = i - dyi * (GT_W + 4);
+      int64_t gy = ty0 - 2 + dyi, gx = tx0 - 2 + dxi;
+      float vy = 0.f, vx = 0.f;
+      if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+        const float* f = &F[(dyi + 1) * FW + (dxi + 1)];
+        vy = deriv(f, FW, gy, p.H, p.y1);
+        vx = deriv(f, 1, gx, p.W, p.x1);
+      }
+      DY[dyi * DW + dxi] = vy;
+      DX[dyi * DW + dxi] = vx;
+    }
+    __syncthreads();
+  }
+
+  for (int i = tid; i < GT_H * GT_W; i += G_THREADS) {
+    int cy = i / GT_W, cx = i - cy * GT_W;
+    int64_t gy = ty0 + cy, gx = tx0 + cx;
+    if (gy >= p.out_row0 + p.out_rows || gx >= p.W) continue;
+    float res;
+    if (M[i]) {
+      res = nanf("");
+    } else if (CLASS == 0) {
+      const float* f = &F[(cy + HALO) * FW + (cx + HALO)];
+      float dy = deriv(f, FW, gy, p.H, p.y1);
+      float dx = deriv(f, 1, gx, p.W, p.x1);
+      float e = dx * p.sgx, n = dy * p.sgy;
+      float norm = sqrtf((e * e + n * n) + 1.0f);
+      float hs = (((-e) * p.lx + (-n) * p.ly) + p.lz) / norm;
+      res = fminf(fmaxf(hs, 0.f), 1.f);
+    } else if (CLASS == 1) {
+      const float* f = &F[(cy + HALO) * FW + (cx + HALO)];
+      float dy = deriv(f, FW, gy, p.H, p.y1);
+      float dx = deriv(f, 1, gx, p.W, p.x1);
+      float s = atanf(sqrtf(dx * dx + dy * dy));
+      if (p.sub == FSG_SLOPE_DEGREE) res = s * (180.0f / 3.14159274101257324f);  // npy_rad2degf
+      else if (p.sub == FSG_SLOPE_PERCENT) res = tanf(s) * 100.f;
+      else res = s;
+    } else {
+      const float* gyp = &DY[(cy + 2) * DW + (cx + 2)];
+      const float* gxp = &DX[(cy + 2) * DW + (cx + 2)];
+      float dy = gyp[0], dx = gxp[0];
+      float dyy = deriv(gyp, DW, gy, p.H, p.y2);
+      float dyx = deriv(gyp, 1, gx, p.W, p.x2);
+      float dxy = deriv(gxp, DW, gy, p.H, p.y2);
+      float dxx = deriv(gxp, 1, gx, p.W, p.x2);
+      float k;
+      if (p.sub == FSG_CURV_MEAN) {
+        float pp = dx, q = dy, r = dxx, t = dyy;
+        float s = (dxy + dyx) / 2.f;
+        float den = powf((1.f + pp * pp) + q * q, 1.5f);
+        float num = ((1.f + q * q) * r - ((2.f * pp) * q) * s) + (1.f + pp * pp) * t;
+        k = (-num) / (2.f * den + 1e-10f);
+      } else if (p.sub == FSG_CURV_GAUSSIAN) {
+        float b = (1.f + dx * dx) + dy * dy;
+        k = (dxx * dyy - dxy * dxy) / (b * b);
+      } else if (p.sub == FSG_CURV_PLANFORM) {
+        float num = ((dy * dy) * dxx - ((2.f * dx) * dy) * dxy) + (dx * dx) * dyy;
+        k = (-num) / (powf(dx * dx + dy * dy, 1.5f) + 1e-10f);
+      } else {
+        float num = ((dx * dx) * dxx + ((2.f * dx) * dy) * dxy) + (dy * dy) * dyy;
+        float g2 = dx * dx + dy * dy;
+        k = (-num) / (g2 * powf((1.f + dx * dx) + dy * dy, 1.5f) + 1e-10f);
+      }
+      float t = tanhf(k * 100.f);
+      res = powf((t + 1.f) / 2.f, (float)(1 / 2.2));
+    }
+    store_out(p.out, (gy - p.out_row0) * p.ld_out + gx, res, p.enc);
+  }
+}
+
+static int check_window(const fsg_window* w, int need_halo, const char* who) {
+  if (!w) return fail(FSG_E_INVALID, "%s: window is NULL", who);
+  if (w->H_global < 3 || w->W < 3)
+    return fail(FSG_E_INVALID,
+                "%s: Shape of array too small to calculate a numerical gradient, at least (edge_order + 1) elements are required.", who);
+  if (w->out_rows < 0 || w->out_row0 < 0 || w->out_row0 + w->out_rows > w->H_global)
+    return fail(FSG_E_INVALID, "%s: output rows [%lld,+%lld) outside raster of %lld rows", who,
+                (long long)w->out_row0, (long long)w->out_rows, (long long)w->H_global);
+  int64_t lo = w->out_row0 - need_halo; if (lo < 0) lo = 0;
+  int64_t hi = w->out_row0 + w->out_rows + need_halo; if (hi > w->H_global) hi = w->H_global;
+  if (w->buf_row0 > lo || w->buf_row0 + w->buf_rows < hi)
+    return fail(FSG_E_INVALID, "%s: buffer rows [%lld,%lld) do not cover the %d-row halo [%lld,%lld)", who,
+                (long long)w->buf_row0, (long long)(w->buf_row0 + w->buf_rows), need_halo, (long long)lo, (long long)hi);
+  if (w->ld_in < w->W || w->ld_out < w->W) return fail(FSG_E_INVALID, "%s: row stride smaller than width", who);
+  return FSG_OK;
+}
+
+static int run_grad(int cls, const float* dem, void* out, const fsg_window* win, GradParams& p,
+                    const fsg_encode* enc, void* stream, const char* who) {
+  int halo = (cls == 2) ? 3 : 2;
+  int rc = check_window(win, halo, who);
+  if (rc) return rc;
+  if (!dem || !out) return fail(FSG_E_INVALID, "%s: NULL buffer", who);
+  p.dem = dem; p.out = out;
+  p.H = win->H_global; p.W = win->W; p.buf_row0 = win->buf_row0; p.buf_rows = win->buf_rows;
+  p.out_row0 = win->out_row0; p.out_rows = win->out_rows; p.ld_in = win->ld_in; p.ld_out = win->ld_out;
+  p.enc = make_encode(enc);
+  if (gauss_half_taps(1.0, p.gw, 4) != 4) return fail(FSG_E_INVALID, "%s: gaussian taps", who);
+  if (p.out_rows == 0) return FSG_OK;
+  dim3 grid((unsigned)((p.W + GT_W - 1) / GT_W), (unsigned)((p.out_rows + GT_H - 1) / GT_H));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cls == 0) grad_kernel<0><<<grid, G_THREADS, 0, s>>>(p);
+  else if (cls == 1) grad_kernel<1><<<grid, G_THREADS, 0, s>>>(p);
+  else grad_kernel<2><<<grid, G_THREADS, 0, s>>>(p);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+}  // namespace fsg
+
+extern "C" {
+
+int fsg_hillshade(const float* dem, void* out, const fsg_window* win, double azimuth, double altitude,
+                  double z_factor, double pixel_size, double psx, double psy, const fsg_encode* enc, void* stream) {
+  using namespace fsg;
+  GradParams p{};
+  double sy, sx;
+  resolve_steps(pixel_size, psx, psy, false, &sy, &sx);
+  p.y1 = make_axis(sy); p.x1 = make_axis(sx); p.y2 = p.y1; p.x2 = p.x1;
+  p.zscale = (float)(is_none(z_factor) ? 1.0 : z_factor);
+  const double d2r = 3.14159265358979323846 / 180.0;
+  double alt = altitude * d2r, az = azimuth * d2r;
+  p.lx = (float)(sin(az) * cos(alt)); p.ly = (float)(cos(az) * cos(alt)); p.lz = (float)sin(alt);
+  p.sgx = (is_none(psx) || psx >= 0.0) ? 1.f : -1.f;
+  p.sgy = (is_none(psy) || psy >= 0.0) ? 1.f : -1.f;
+  return run_grad(0, dem, out, win, p, enc, stream, "fsg_hillshade");
+}
+
+int fsg_slope(const float* dem, void* out, const fsg_window* win, int unit, double pixel_size, double psx,
+              double psy, const fsg_encode* enc, void* stream) {
+  using namespace fsg;
+  if (unit < 0 || unit > 2) return fail(FSG_E_INVALID, "fsg_slope: unknown unit %d", unit);
+  GradParams p{};
+  double sy, sx;
+  resolve_steps(pixel_size, psx, psy, false, &sy, &sx);
+  p.y1 = make_axis(sy); p.x1 = make_axis(sx); p.y2 = p.y1; p.x2 = p.x1;
+  p.zscale = 1.f; p.sub = unit;
+  return run_grad(1, dem, out, win, p, enc, stream, "fsg_slope");
+}
+
+int fsg_curvature(const float* dem, void* out, const fsg_window* win, int curvature_type, double pixel_size,
+                  double psx, double psy, const fsg_encode* enc, void* stream) {
+  using namespace fsg;
+  if (curvature_type < 0 || curvature_type > 3) return fail(FSG_E_INVALID, "fsg_curvature: unknown type %d", curvature_type);
+  GradParams p{};
+  // first derivatives use |step| (handle_nan_for_gradient), second derivatives the signed step
+  double sy2, sx2;
+  resolve_steps(pixel_size, psx, psy, true, &sy2, &sx2);
+  p.y1 = make_axis(fabs(sy2) < 1e-9 ? 1.0 : fabs(sy2));
+  p.x1 = make_axis(fabs(sx2) < 1e-9 ? 1.0 : fabs(sx2));
+  p.y2 = make_axis(sy2); p.x2 = make_axis(sx2);
+  p.zscale = 1.f; p.sub = curvature_type;
+  return run_grad(2, dem, out, win, p, enc, stream, "fsg_curvature");
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// Topographic openness (Yokoyama et al. 2002) -- compute_openness_vectorized
+// (algorithms/_impl_openness.py:31-132) as one fused gather kernel.
+//
+// Per pixel: D azimuths x <=10 ray samples; sample offset (round(r cos a), round(r sin a)) with
+// Python's half-even round; sample value = NaN->0 raster, edge-replicated; sample validity = inside
+// the raster and not NaN (and the centre not NaN).  Per azimuth the reference keeps
+// max/min over samples of arctan(dz/dist); arctan is monotone, so the kernel keeps the extreme of the
+// f32 quotient dz/dist (same individually rounded ops) and applies arctan once per azimuth.
+// Then: zenith/nadir angle, mean over azimuths with >=1 valid sample, /(pi/2), clip, gamma,
+// optional display stretch (tile/dask_bridge.py:173-187), NaN restore, optional integer encoding.
+//
+// Traffic: the 80 gathers of a CTA tile are 80 shifted copies of the tile, served by L1/L2; DRAM sees
+// the DEM about once when CTAs sweep the raster in row-major order (a +-256-row band of a 32768-wide
+// raster is 67 MB < 126 MB L2).  Algorithmic bytes: 8 B/px.
+#include "fsg_common.cuh"
+
+namespace fsg {
+
+constexpr int OP_MAX_SAMPLES = 64 * 10;
+
+struct OpenParams {
+  const float* dem;
+  void* out;
+  int64_t H, W, buf_row0, buf_rows, out_row0, out_rows, ld_in, ld_out;
+  int n_dirs;
+  int negative;
+  int stretch;
+  float stretch_lo, stretch_scale;
+  EncodeDev enc;
+};
+
+struct OpenSample {
+  short ox, oy;
+  float dist;  // f32(max(hypot(ox*sx, oy*sy), 1e-9))
+};
+
+// Passed BY VALUE as a kernel parameter (read through the constant bank, broadcast to the warp):
+// no global/constant symbol is written, so concurrent calls from several host threads are safe.
+struct OpenTable {
+  int dir_start[65];
+  OpenSample s[OP_MAX_SAMPLES];
+};
+
+__global__ void __launch_bounds__(256) openness_kernel(OpenParams p, const __grid_constant__ OpenTable tab) {
+  const int64_t x = (int64_t)blockIdx.x * 64 + (threadIdx.x & 63);
+  const int64_t y = p.out_row0 + (int64_t)blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= p.W || y >= p.out_row0 + p.out_rows) return;
+  const float* base = p.dem - p.buf_row0 * p.ld_in;  // address of global row 0
+  const float c = base[y * p.ld_in + x];
+  float res;
+  if (c != c) {
+    res = nanf("");
+  } else {
+    const float half_pi = (float)(3.14159265358979323846 / 2);
+    float asum = 0.f, acnt = 0.f;
+    for (int d = 0; d < p.n_dirs; ++d) {
+      float ext = 0.f;
+      bool seen = false;
+      for (int k = tab.dir_start[d]; k < tab.dir_start[d + 1]; ++k) {
+        const OpenSample sm = tab.s[k];
+        int64_t sy = y + sm.oy, sx = x + sm.ox;
+        if (sy < 0 || sy >= p.H || sx < 0 || sx >= p.W) continue;  // padded validity = False
+        float v = base[sy * p.ld_in + sx];
+        if (v != v) continue;
+        float t = (v - c) / sm.dist;
+        if (!seen) ext = t;
+        else ext = p.negative ? fminf(ext, t) : fmaxf(ext, t);
+        seen = true;
+      }
+      if (seen) {
+        // np.maximum(ext, angle) starting from -pi/2 (f32): atan never drops below it
+        float a = atanf(ext);
+        a = p.negative ? fminf(half_pi, a) : fmaxf(-half_pi, a);
+        float dang = p.negative ? half_pi + a : half_pi - a;
+        asum = asum + dang;
+        acnt = acnt + 1.f;
+      }
+    }
+    float o = asum / fmaxf(acnt, 1.f);
+    o = o / half_pi;
+    o = fminf(fmaxf(o, 0.f), 1.f);
+    res = powf(o, (float)(1 / 2.2));
+    if (p.stretch) res = fmaxf((res - p.stretch_lo) / p.stretch_scale, 0.f);
+  }
+  store_out(p.out, (y - p.out_row0) * p.ld_out + x, res, p.enc);
+}
+
+static double py_round(double v) { return nearbyint(v); }  // half-to-even, like Python's round()
+
+static int run_openness(const float* dem, void* out, const fsg_window* win, int negative, int n_dirs,
+                        const OpenTable& tab, int D, double stretch_lo, double stretch_scale, const fsg_encode* enc,
+                        void* stream) {
+  if (!dem || !out || !win) return fail(FSG_E_INVALID, "fsg_openness: NULL argument");
+  if (win->H_global < 1 || win->W < 1) return fail(FSG_E_INVALID, "fsg_openness: empty raster");
+  if (win->out_row0 < 0 || win->out_rows < 0 || win->out_row0 + win->out_rows > win->H_global)
+    return fail(FSG_E_INVALID, "fsg_openness: output rows outside the raster");
+  int64_t lo = win->out_row0 - D; if (lo < 0) lo = 0;
+  int64_t hi = win->out_row0 + win->out_rows + D; if (hi > win->H_global) hi = win->H_global;
+  if (win->buf_row0 > lo || win->buf_row0 + win->buf_rows < hi)
+    return fail(FSG_E_INVALID, "fsg_openness: buffer rows do not cover the %d-row halo", D);
+  OpenParams p{};
+  p.dem = dem; p.out = out; p.H = win->H_global; p.W = win->W; p.buf_row0 = win->buf_row0; p.buf_rows = win->buf_rows;
+  p.out_row0 = win->out_row0; p.out_rows = win->out_rows; p.ld_in = win->ld_in; p.ld_out = win->ld_out;
+  p.n_dirs = n_dirs; p.negative = negative ? 1 : 0;
+  p.stretch = (!is_none(stretch_scale) && !is_none(stretch_lo) && stretch_scale > 1e-12) ? 1 : 0;
+  p.stretch_lo = (float)stretch_lo; p.stretch_scale = (float)stretch_scale;
+  p.enc = make_encode(enc);
+  if (p.out_rows == 0) return FSG_OK;
+  dim3 grid((unsigned)((p.W + 63) / 64), (unsigned)((p.out_rows + 3) / 4));
+  openness_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, tab);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+}  // namespace fsg
+
+extern "C" {
+
+// Explicit ray-sample table (the Python host layer builds it with NumPy exactly as the reference
+// does, so the integer offsets cannot drift with the libm in use).
+int fsg_openness_samples(const float* dem, void* out, const fsg_window* win, int negative, int num_directions,
+                         const int32_t* dir_start_host, const int32_t* ox_host, const int32_t* oy_host,
+                         const float* dist_host, double stretch_lo, double stretch_scale, const fsg_encode* enc,
+                         void* stream) {
+  using namespace fsg;
+  if (num_directions < 1 || num_directions > 64) return fail(FSG_E_INVALID, "fsg_openness: num_directions must be 1..64");
+  if (!dir_start_host || !ox_host || !oy_host || !dist_host) return fail(FSG_E_INVALID, "fsg_openness: NULL sample table");
+  int ns = dir_start_host[num_directions];
+  if (ns < 0 || ns > OP_MAX_SAMPLES) return fail(FSG_E_INVALID, "fsg_openness: too many ray samples (%d)", ns);
+  OpenTable tab{};
+  int D = 0;
+  for (int d = 0; d <= 64; ++d) tab.dir_start[d] = d <= num_directions ? dir_start_host[d] : ns;
+  for (int k = 0; k < ns; ++k) {
+    tab.s[k].ox = (short)ox_host[k]; tab.s[k].oy = (short)oy_host[k]; tab.s[k].dist = dist_host[k];
+    int a = abs(ox_host[k]) > abs(oy_host[k]) ? abs(ox_host[k]) : abs(oy_host[k]);
+    if (a > D) D = a;
+  }
+  return run_openness(dem, out, win, negative, num_directions, tab, D, stretch_lo, stretch_scale, enc, stream);
+}
+
+int fsg_openness(const float* dem, void* out, const fsg_window* win, int negative, int num_directions,
+                 int max_distance, double pixel_size, double psx, double psy, double stretch_lo,
+                 double stretch_scale, const fsg_encode* enc, void* stream) {
+  using namespace fsg;
+  if (num_directions < 1 || num_directions > 64) return fail(FSG_E_INVALID, "fsg_openness: num_directions must be 1..64");
+  if (max_distance < 0 || max_distance > 32000) return fail(FSG_E_INVALID, "fsg_openness: max_distance out of range");
+  // distances: np.unique((np.linspace(0.1, 1.0, 10) * max_distance).astype(int)), > 0  (:67-68)
+  int dist[10], nd = 0;
+  for (int i = 0; i < 10; ++i) {
+    double step = (1.0 - 0.1) / 9.0;
+    double f = (i == 9) ? 1.0 : (double)i * step + 0.1;
+    int v = (int)(f * (double)max_distance);
+    if (v <= 0) continue;
+    if (nd == 0 || v != dist[nd - 1]) dist[nd++] = v;
+  }
+  int D = nd ? dist[nd - 1] : 0;
+  double sx = is_none(psx) ? pixel_size : fabs(psx);
+  double sy = is_none(psy) ? pixel_size : fabs(psy);
+  if (sx < 1e-9) sx = pixel_size != 0.0 ? pixel_size : 1.0;
+  if (sy < 1e-9) sy = pixel_size != 0.0 ? pixel_size : 1.0;
+  OpenTable tab{};
+  int ns = 0;
+  const double two_pi = 2.0 * 3.14159265358979323846;
+  for (int d = 0; d < num_directions; ++d) {
+    tab.dir_start[d] = ns;
+    double ang = (double)d * (two_pi / (double)num_directions);  // np.linspace(0, 2*pi, D, endpoint=False)
+    double cx = cos(ang), cy = sin(ang);
+    for (int k = 0; k < nd; ++k) {
+      int ox = (int)py_round((double)dist[k] * cx);
+      int oy = (int)py_round((double)dist[k] * cy);
+      if (ox == 0 && oy == 0) continue;
+      double pd = hypot((double)ox * sx, (double)oy * sy);
+      if (pd < 1e-9) pd = 1e-9;
+      tab.s[ns].ox = (short)ox; tab.s[ns].oy = (short)oy; tab.s[ns].dist = (float)pd;
+      ++ns;
+    }
+  }
+  for (int d = num_directions; d <= 64; ++d) tab.dir_start[d] = ns;
+  return run_openness(dem, out, win, negative, num_directions, tab, D, stretch_lo, stretch_scale, enc, stream);
+}
+
+}  // extern "C"

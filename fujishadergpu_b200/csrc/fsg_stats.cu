@@ -1,0 +1,217 @@
+// Exact percentile of a pooled sample (np.percentile, method='linear') without sorting:
+// 3-level radix select on the order-preserving integer image of the f32 values.
+//
+// Reference: topousm_fast_stat_func (algorithms/_normalization.py:22-32): percentile(|x[~isnan]|, 99)
+//            robust_unsigned_stretch_stat_func (algorithms/_global_stats.py:181-203): p1 / p99 of finite x
+// NumPy evaluates the virtual index (n-1)*q/100 in the ARRAY dtype (f32 here), so the host layer first
+// asks for the sample count (rank < 0), derives k with NumPy's own scalar arithmetic, then asks for the
+// order statistics a[k], a[k+1]; the two-point interpolation is likewise done host-side in f32.
+#include "fsg_common.cuh"
+
+namespace fsg {
+
+constexpr int MAX_CHUNKS = 16;
+
+struct Chunks {
+  const float* ptr[MAX_CHUNKS];
+  int64_t rows[MAX_CHUNKS], cols[MAX_CHUNKS], ld[MAX_CHUNKS];
+  int64_t start[MAX_CHUNKS + 1];  // prefix of rows*cols
+  int n;
+};
+
+struct SelState {
+  unsigned long long n;       // contributing samples
+  unsigned long long rank;    // remaining rank inside the current prefix bucket
+  unsigned int prefix;        // key bits fixed so far
+  unsigned int mask;          // which bits are fixed
+  unsigned int key_k;         // key of a[k]
+  unsigned long long cnt_le;  // #keys <= key_k
+  unsigned int key_next;      // min key > key_k
+  double q;
+  double out[4];              // a[k], a[k+1], gamma, n
+};
+
+__device__ __forceinline__ bool sample_key(float v, int take_abs, int finite_only, unsigned int* key) {
+  if (finite_only ? !isfinite(v) : (v != v)) return false;
+  unsigned int b = __float_as_uint(v);
+  if (take_abs) b &= 0x7fffffffu;
+  else b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  *key = b;
+  return true;
+}
+__device__ __forceinline__ float key_value(unsigned int key, int take_abs) {
+  if (take_abs) return __uint_as_float(key);
+  unsigned int b = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+  return __uint_as_float(b);
+}
+
+__device__ __forceinline__ float fetch(const Chunks& c, int64_t i) {
+  int k = 0;
+  while (k + 1 < c.n && i >= c.start[k + 1]) ++k;
+  int64_t j = i - c.start[k];
+  int64_t r = j / c.cols[k], x = j - r * c.cols[k];
+  return c.ptr[k][r * c.ld[k] + x];
+}
+
+// level: 0 -> bits 31..21 (2048 bins), 1 -> bits 20..10 (2048), 2 -> bits 9..0 (1024)
+__global__ void __launch_bounds__(256) hist_kernel(Chunks c, int level, int take_abs, int finite_only,
+                                                   const SelState* st, unsigned int* hist, unsigned long long* count) {
+  __shared__ unsigned int sh[2048];
+  for (int i = threadIdx.x; i < 2048; i += 256) sh[i] = 0;
+  __syncthreads();
+  const unsigned int prefix = level ? st->prefix : 0u, mask = level ? st->mask : 0u;
+  const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
+  const unsigned int bins_mask = level == 2 ? 1023u : 2047u;
+  const int64_t total = c.start[c.n];
+  unsigned long long local = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    unsigned int key;
+    if (!sample_key(fetch(c, i), take_abs, finite_only, &key)) continue;
+    ++local;
+    if ((key & mask) == prefix) atomicAdd(&sh[(key >> shift) & bins_mask], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += 256)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+  if (level == 0) {
+    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+  }
+}
+
+__global__ void pick_kernel(int level, SelState* st, unsigned int* hist, const unsigned long long* count) {
+  if (threadIdx.x != 0) return;
+  if (level == 0) {
+    st->n = *count;
+    if (st->n == 0) { st->rank = 0; st->prefix = 0; st->mask = 0; return; }
+    if (st->rank >= st->n) st->rank = st->n - 1;
+    st->out[2] = (double)st->rank;
+    st->prefix = 0; st->mask = 0;
+  }
+  if (st->n == 0) return;
+  const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
+  const int bins = level == 2 ? 1024 : 2048;
+  unsigned long long r = st->rank;
+  int b = 0;
+  for (; b < bins; ++b) {
+    unsigned int h = hist[b];
+    if (r < h) break;
+    r -= h;
+  }
+  if (b >= bins) b = bins - 1;
+  st->rank = r;
+  st->prefix |= ((unsigned int)b) << shift;
+  st->mask |= ((unsigned int)(bins - 1)) << shift;
+  for (int i = 0; i < 2048; ++i) hist[i] = 0;
+  if (level == 2) st->key_k = st->prefix;
+}
+
+__global__ void __launch_bounds__(256) next_kernel(Chunks c, int take_abs, int finite_only, SelState* st) {
+  if (st->n == 0) return;
+  const unsigned int kk = st->key_k;
+  const int64_t total = c.start[c.n];
+  unsigned long long le = 0;
+  unsigned int mn = 0xffffffffu;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    unsigned int key;
+    if (!sample_key(fetch(c, i), take_abs, finite_only, &key)) continue;
+    if (key <= kk) ++le;
+    else if (key < mn) mn = key;
+  }
+  for (int o = 16; o; o >>= 1) {
+    le += __shfl_down_sync(0xffffffffu, le, o);
+    unsigned int other = __shfl_down_sync(0xffffffffu, mn, o);
+    mn = other < mn ? other : mn;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (le) atomicAdd(&st->cnt_le, le);
+    atomicMin(&st->key_next, mn);
+  }
+}
+
+__global__ void finish_kernel(SelState* st, int take_abs, double* result, unsigned long long abs_rank_plus1_hint) {
+  if (threadIdx.x != 0) return;
+  (void)abs_rank_plus1_hint;
+  if (st->n == 0) {
+    result[0] = nan(""); result[1] = nan(""); result[2] = 0.0; result[3] = 0.0;
+    return;
+  }
+  unsigned long long k = (unsigned long long)st->out[2];
+  float ak = key_value(st->key_k, take_abs);
+  float ak1 = ak;
+  if (k + 1 < st->n && st->cnt_le < k + 2) ak1 = key_value(st->key_next, take_abs);
+  result[0] = (double)ak;
+  result[1] = (double)ak1;
+  result[2] = st->out[2];
+  result[3] = (double)st->n;
+}
+
+__global__ void count_only_kernel(const unsigned long long* count, double* result) {
+  if (threadIdx.x == 0) { result[0] = nan(""); result[1] = nan(""); result[2] = 0.0; result[3] = (double)*count; }
+}
+
+__global__ void init_state_kernel(SelState* st, unsigned int* hist, unsigned long long* count, long long rank) {
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
+  if (threadIdx.x == 0) {
+    memset(st, 0, sizeof(SelState));
+    st->rank = rank < 0 ? 0ull : (unsigned long long)rank;
+    st->key_next = 0xffffffffu;
+    *count = 0;
+  }
+}
+
+}  // namespace fsg
+
+extern "C" {
+
+size_t fsg_order_stats_workspace_bytes(void) { return 2048 * 4 + 256 + sizeof(fsg::SelState) + 256; }
+
+int fsg_order_stats(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                    const int64_t* ld_host, int n_chunks, int64_t rank, int take_abs, int finite_only,
+                    double* result_dev, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace fsg;
+  if (n_chunks < 1 || n_chunks > MAX_CHUNKS) return fail(FSG_E_INVALID, "fsg_order_stats: 1..%d chunks supported", MAX_CHUNKS);
+  if (!workspace || workspace_bytes < fsg_order_stats_workspace_bytes() || !result_dev)
+    return fail(FSG_E_WORKSPACE, "fsg_order_stats: workspace too small");
+  Chunks c{};
+  c.n = n_chunks;
+  int64_t tot = 0;
+  for (int i = 0; i < n_chunks; ++i) {
+    if (!chunks_host[i] || rows_host[i] < 0 || cols_host[i] < 0 || ld_host[i] < cols_host[i])
+      return fail(FSG_E_INVALID, "fsg_order_stats: bad chunk %d", i);
+    c.ptr[i] = chunks_host[i]; c.rows[i] = rows_host[i]; c.cols[i] = cols_host[i]; c.ld[i] = ld_host[i];
+    c.start[i] = tot;
+    tot += rows_host[i] * cols_host[i];
+  }
+  c.start[n_chunks] = tot;
+  unsigned char* base = (unsigned char*)workspace;
+  unsigned int* hist = (unsigned int*)base;
+  unsigned long long* count = (unsigned long long*)(base + 2048 * 4);
+  SelState* st = (SelState*)(base + 2048 * 4 + 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  int blocks = (int)((tot + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  init_state_kernel<<<1, 256, 0, s>>>(st, hist, count, (long long)rank);
+  FSG_LAUNCH_OK();
+  if (rank < 0) {  // count only
+    hist_kernel<<<blocks, 256, 0, s>>>(c, 0, take_abs, finite_only, st, hist, count);
+    FSG_LAUNCH_OK();
+    count_only_kernel<<<1, 32, 0, s>>>(count, result_dev);
+    FSG_LAUNCH_OK();
+    return FSG_OK;
+  }
+  for (int level = 0; level < 3; ++level) {
+    hist_kernel<<<blocks, 256, 0, s>>>(c, level, take_abs, finite_only, st, hist, count);
+    FSG_LAUNCH_OK();
+    pick_kernel<<<1, 32, 0, s>>>(level, st, hist, count);
+    FSG_LAUNCH_OK();
+  }
+  next_kernel<<<blocks, 256, 0, s>>>(c, take_abs, finite_only, st);
+  FSG_LAUNCH_OK();
+  finish_kernel<<<1, 32, 0, s>>>(st, take_abs, result_dev, 0ull);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+}  // extern "C"

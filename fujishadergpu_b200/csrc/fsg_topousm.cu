@@ -1,0 +1,841 @@
+// topousm_fast: multiscale unsharp mask  out = sum_i w_i * (dem - mean_i(dem))
+//
+// Reference: compute_topousm_fast_efficient_block (algorithms/_impl_topousm_fast.py:49-100) with
+//   _radius_to_downsample_factor (algorithms/_nan_utils.py:555-601)
+//   _downsample_nan_aware        (:604-668)   -> pyramid_kernel (+ enclosed-void fill)
+//   handle_nan_with_uniform/_gaussian (:18-47) on the decimated grids -> fsg_filters.cu
+//   _upsample_to_shape           (:671-698)   -> align-corners bilinear taps inside the fused kernel
+//   apply_global_normalization   (algorithms/_global_stats.py:123-153) + integer encoding -> epilogue
+//
+// Pipeline (all on the caller's stream, no host sync, no allocation):
+//   1. pyramid_kernel : ONE read of the DEM produces every needed f x f valid-mean level
+//                       (f32 sums in NumPy's reduction order -> bit-identical coarse grids).
+//   2. per coarse term: box / sigma=1 Gaussian mean on its (small) level.
+//   3. fused_kernel   : streams column strips of the DEM through a shared-memory row ring; for
+//                       every full-resolution radius the vertical pass keeps exact f64 running
+//                       window sums per column, the horizontal pass slides f64 sums along rows
+//                       (results rounded to f32 exactly where scipy rounds: after each axis);
+//                       coarse means are sampled with scipy's zoom arithmetic; terms are combined
+//                       in list order in f32; normalise; NaN restore; optional u8/i16 encoding.
+//      Algorithmic traffic: 4 B/px read + 4 B/px (f32) or 1 B/px (u8) written.
+#include "fsg_filters.cuh"
+
+namespace fsg {
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+constexpr int MAX_TERMS = 16;
+constexpr int MAX_FUSED_R = 41;  // ds==1 for r<=41 at pixel_size>=1 (and fewer for finer pixels)
+constexpr int MAX_LEVELS = 4;    // decimation factors 2,4,8,16
+
+enum TermKind { TERM_BOX_FUSED = 0, TERM_COARSE = 1, TERM_PLANE = 2 };
+
+struct HostTerm {
+  int kind;
+  int radius;     // user radius
+  int ds;         // decimation factor
+  int size;       // box taps on its grid (0: sigma=1 gaussian)
+  int level;      // index into levels[] for coarse terms
+  size_t grid_off;  // workspace offset of the mean grid (coarse) / plane
+};
+
+struct HostLevel {
+  int f;
+  int64_t h, w;
+  size_t off;  // workspace offset of the coarse grid
+};
+
+struct HostPlan {
+  int n_terms;
+  HostTerm terms[MAX_TERMS];
+  int n_levels;
+  HostLevel levels[MAX_LEVELS];
+  size_t off_tv, off_tw;   // scratch planes (max over users)
+  size_t off_taps;         // f64 taps scratch
+  size_t off_flags;        // ints: [0..3] level has void cell, [4..7] level still has NaN after fill
+  size_t total;
+  int taps_cap;
+  int fused_R;             // max fused radius
+};
+
+static int decimation_factor(double radius, double pixel_size) {
+  // algorithms/_nan_utils.py:555-601 with algorithm_name="topousm_fast"
+  double r = radius < 1.0 ? 1.0 : radius;
+  double px = pixel_size != 0.0 ? pixel_size : 1.0;
+  if (px < 1e-3) px = 1e-3;
+  double res = 1.0 / px;
+  if (res < 1.0) res = 1.0;
+  double score = (r / 24.0) * 1.15 * 1.0 * pow(res, 0.35);
+  if (score <= 1.0) return 1;
+  int f = 1 << (int)floor(log2(score));
+  if (f < 1) f = 1;
+  if (f > 16) f = 16;
+  return f;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int make_plan(int64_t H, int64_t W, const int32_t* radii, int n, double pixel_size, HostPlan* p) {
+  if (n <= 0) return fail(FSG_E_INVALID, "At least one radius value is required");
+  if (n > MAX_TERMS) return fail(FSG_E_UNSUPPORTED, "at most %d radii are supported, got %d", MAX_TERMS, n);
+  if (H < 1 || W < 1) return fail(FSG_E_INVALID, "empty raster %lld x %lld", (long long)H, (long long)W);
+  memset(p, 0, sizeof(*p));
+  p->n_terms = n;
+  size_t off = 0;
+  size_t scratch = 0;  // elements needed in tv/tw
+  int taps_cap = 8;
+  int n_fused = 0;
+  for (int i = 0; i < n; ++i) {
+    HostTerm& t = p->terms[i];
+    t.radius = radii[i];
+    t.ds = decimation_factor((double)radii[i], pixel_size);
+    if (t.ds > 1) {
+      int rs = (int)nearbyint((double)radii[i] / (double)t.ds);  // Python round(): half to even
+      if (rs < 1) rs = 1;
+      t.kind = TERM_COARSE;
+      t.size = rs <= 1 ? 0 : 2 * rs + 1;
+      int lv = -1;
+      for (int k = 0; k < p->n_levels; ++k)
+        if (p->levels[k].f == t.ds) lv = k;
+      if (lv < 0) {
+        lv = p->n_levels++;
+        p->levels[lv].f = t.ds;
+        p->levels[lv].h = (H + t.ds - 1) / t.ds;
+        p->levels[lv].w = (W + t.ds - 1) / t.ds;
+      }
+      t.level = lv;
+    } else if (radii[i] <= 1) {
+      t.kind = TERM_PLANE;
+      t.size = 0;
+    } else if (radii[i] <= MAX_FUSED_R && n_fused < 8) {
+      t.kind = TERM_BOX_FUSED;
+      t.size = 2 * radii[i] + 1;
+      ++n_fused;
+      if (radii[i] > p->fused_R) p->fused_R = radii[i];
+    } else {
+      t.kind = TERM_PLANE;  // general fallback (never hit by the reference's decimation rule)
+      t.size = 2 * radii[i] + 1;
+    }
+  }
+  for (int k = 0; k < p->n_levels; ++k) {
+    HostLevel& l = p->levels[k];
+    l.off = off;
+    off = align_up(off + (size_t)l.h * l.w * 4, 256);
+    if ((size_t)l.h * l.w > scratch) scratch = (size_t)l.h * l.w;
+    double sigma = (double)(l.h < l.w ? l.h : l.w) / 64.0;
+    if (sigma < 1.0) sigma = 1.0;
+    int r = (int)(4.0 * sigma + 0.5);
+    if (r + 1 > taps_cap) taps_cap = r + 1;
+  }
+  for (int i = 0; i < n; ++i) {
+    HostTerm& t = p->terms[i];
+    if (t.kind == TERM_COARSE) {
+      const HostLevel& l = p->levels[t.level];
+      t.grid_off = off;
+      off = align_up(off + (size_t)l.h * l.w * 4, 256);
+    } else if (t.kind == TERM_PLANE) {
+      t.grid_off = off;
+      off = align_up(off + (size_t)H * W * 4, 256);
+      if ((size_t)H * W > scratch) scratch = (size_t)H * W;
+    }
+  }
+  p->off_tv = off; off = align_up(off + scratch * 4, 256);
+  p->off_tw = off; off = align_up(off + scratch * 4, 256);
+  p->off_taps = off; off = align_up(off + (size_t)taps_cap * 8, 256);
+  p->off_flags = off; off = align_up(off + 64, 256);
+  p->taps_cap = taps_cap;
+  p->total = off;
+  return FSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// 1. pyramid: f x f mean of finite members, NumPy reduction order
+// ------------------------------------------------------------------------------------------
+constexpr int PY_ROWS = 16;
+constexpr int PY_COLS = 512;
+constexpr int PY_STRIDE = PY_COLS + PY_COLS / 16;  // +1 pad per 16 columns
+
+struct PyramidParams {
+  const float* dem;
+  int64_t H, W, ld;
+  int n_levels;
+  int f[MAX_LEVELS];
+  float* grid[MAX_LEVELS];
+  int64_t gw[MAX_LEVELS];
+  int64_t gh[MAX_LEVELS];
+  int* flags;  // flags[k] = level k has a void (all-NaN) cell
+};
+
+__device__ __forceinline__ int py_idx(int row, int col) { return row * PY_STRIDE + col + (col >> 4); }
+
+// One cell: `sum(axis=(1,3), dtype=float32)` of NumPy = per cell row a pairwise row sum
+// (n<8: sequential; n>=8: 8 lanes then ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))), rows added in order.
+template <int F>
+__device__ __forceinline__ void cell_reduce(const float* sm, int row0, int col0, float* tot, float* cnt) {
+  float T = 0.f, Cn = 0.f;
+#pragma unroll 1
+  for (int i = 0; i < F; ++i) {
+    float rs, rc;
+    if (F < 8) {
+      float v = sm[py_idx(row0 + i, col0)];
+      bool ok = isfinite(v);
+      rs = ok ? v : 0.f;
+      rc = ok ? 1.f : 0.f;
+#pragma unroll
+      for (int j = 1; j < F; ++j) {
+        v = sm[py_idx(row0 + i, col0 + j)];
+        ok = isfinite(v);
+        rs = rs + (ok ? v : 0.f);
+        rc = rc + (ok ? 1.f : 0.f);
+      }
+    } else {
+      float r[8], c[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float v = sm[py_idx(row0 + i, col0 + k)];
+        bool ok = isfinite(v);
+        r[k] = ok ? v : 0.f;
+        c[k] = ok ? 1.f : 0.f;
+      }
+#pragma unroll
+      for (int j = 8; j < F; j += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float v = sm[py_idx(row0 + i, col0 + j + k)];
+          bool ok = isfinite(v);
+          r[k] = r[k] + (ok ? v : 0.f);
+          c[k] = c[k] + (ok ? 1.f : 0.f);
+        }
+      }
+      rs = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+      rc = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+    }
+    if (i == 0) { T = rs; Cn = rc; } else { T = T + rs; Cn = Cn + rc; }
+  }
+  *tot = T;
+  *cnt = Cn;
+}
+
+__global__ void __launch_bounds__(256) pyramid_kernel(PyramidParams p) {
+  __shared__ float sm[PY_ROWS * PY_STRIDE];
+  const int64_t x0 = (int64_t)blockIdx.x * PY_COLS;
+  const int64_t y0 = (int64_t)blockIdx.y * PY_ROWS;
+  const int tid = threadIdx.x;
+  const float qnan = nanf("");
+  // coalesced load, ragged edge -> NaN (the reference NaN-pads before reshaping)
+  for (int i = tid; i < PY_ROWS * (PY_COLS / 4); i += 256) {
+    int r = i / (PY_COLS / 4), c4 = (i - r * (PY_COLS / 4)) * 4;
+    int64_t gy = y0 + r, gx = x0 + c4;
+    float v[4] = {qnan, qnan, qnan, qnan};
+    if (gy < p.H) {
+      const float* src = p.dem + gy * p.ld + gx;
+      if (gx + 3 < p.W && ((((uintptr_t)src) & 15) == 0)) {
+        float4 q = *reinterpret_cast<const float4*>(src);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (gx + k < p.W) v[k] = src[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sm[py_idx(r, c4 + k)] = v[k];
+  }
+  __syncthreads();
+  for (int lv = 0; lv < p.n_levels; ++lv) {
+    const int f = p.f[lv];
+    const int cells_x = PY_COLS / f, cells_y = PY_ROWS / f;
+    for (int i = tid; i < cells_x * cells_y; i += 256) {
+      int cy = i / cells_x, cx = i - cy * cells_x;
+      int64_t oy = y0 / f + cy, ox = x0 / f + cx;
+      if (oy >= p.gh[lv] || ox >= p.gw[lv]) continue;
+      float tot, cnt;
+      if (f == 2) cell_reduce<2>(sm, cy * 2, cx * 2, &tot, &cnt);
+      else if (f == 4) cell_reduce<4>(sm, cy * 4, cx * 4, &tot, &cnt);
+      else if (f == 8) cell_reduce<8>(sm, cy * 8, cx * 8, &tot, &cnt);
+      else cell_reduce<16>(sm, cy * 16, cx * 16, &tot, &cnt);
+      float out;
+      if (cnt > 0.f) out = tot / fmaxf(cnt, 1.f);
+      else { out = qnan; p.flags[lv] = 1; }
+      p.grid[lv][oy * p.gw[lv] + ox] = out;
+    }
+  }
+}
+
+// flags[4+lv] = grid still holds NaN (set by void fill when it leaves a cell; or copy of flags[lv]
+// when... see host code) -- helper to zero the flag block
+__global__ void zero_flags_kernel(int* flags) {
+  if (threadIdx.x < 16) flags[threadIdx.x] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. fused full-resolution kernel
+// ------------------------------------------------------------------------------------------
+constexpr int FK_THREADS = 352;             // 11 warps
+constexpr int FK_NB = 32;                   // rows per batch
+constexpr int FK_TW = 256;                  // output columns per strip
+constexpr int FK_NSEG = FK_THREADS / FK_NB; // 11 column segments in the horizontal phase
+constexpr int FK_SEG = (FK_TW + FK_NSEG - 1) / FK_NSEG;  // 24
+constexpr int FK_MAXF = 8;
+
+struct DevTerm {
+  int kind;
+  int r;             // fused radius
+  float weight;
+  const float* grid; // coarse mean grid / plane
+  int64_t gh, gw;    // coarse dims
+  double rscale, cscale;  // (gh-1)/(H-1), (gw-1)/(W-1)
+};
+
+struct FusedParams {
+  const float* dem;
+  void* out;
+  int64_t H, W, ld_in, ld_out;
+  int n_terms;
+  DevTerm terms[MAX_TERMS];
+  int R;           // halo (max fused radius, 0 if none)
+  int band_rows;   // rows per CTA band (multiple of FK_NB)
+  int norm_mode;   // 0 none, 1 divide by norm_scale, 2 zeros
+  float norm_scale;
+  EncodeDev enc;
+};
+
+__global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int R = p.R;
+  const int SW = FK_TW + 2 * R;          // strip width incl. halo
+  const int SWp = SW | 1;                // odd row stride (bank-conflict-free row-parallel access)
+  const int NRING = FK_NB + 2 * R + 1;   // rows resident in the ring
+  float* ring = reinterpret_cast<float*>(smraw);                 // NRING x SWp
+  float* vplane = ring + (size_t)NRING * SWp;                    // FK_NB x SWp  (also output staging)
+  unsigned char* cplane = reinterpret_cast<unsigned char*>(vplane + (size_t)FK_NB * SWp);  // FK_NB x SWp
+  __shared__ int s_nan;
+
+  const int tid = threadIdx.x;
+  const int64_t x0 = (int64_t)blockIdx.x * FK_TW;       // first output column of the strip
+  const int64_t cs0 = x0 - R;                            // global column of strip slot 0
+  const int64_t yb0 = (int64_t)blockIdx.y * p.band_rows;
+  const int64_t yb1 = (yb0 + p.band_rows < p.H) ? yb0 + p.band_rows : p.H;
+  const int64_t H = p.H, W = p.W;
+
+  // column owned in the vertical phase
+  const int vc = tid;                                    // strip slot
+  const int64_t vgx = cs0 + vc;
+  const bool vcol_ok = vc < SW && vgx >= 0 && vgx < W;
+
+  // per-thread running window state for the fused radii
+  double rs[FK_MAXF];
+  int rc[FK_MAXF];
+  int fr[FK_MAXF];
+  int nf = 0;
+  for (int t = 0; t < p.n_terms; ++t)
+    if (p.terms[t].kind == TERM_BOX_FUSED) fr[nf++] = p.terms[t].r;
+
+  // horizontal-phase mapping: lane <-> row, warp-group <-> column segment
+  const int hi = tid % FK_NB;
+  const int hg = tid / FK_NB;
+  const int hj0 = hg * FK_SEG;
+  int hjn = (hj0 + FK_SEG <= FK_TW) ? FK_SEG : (FK_TW - hj0 > 0 ? FK_TW - hj0 : 0);
+  if (x0 + hj0 + hjn > p.W) hjn = (p.W - x0 - hj0 > 0) ? (int)(p.W - x0 - hj0) : 0;  // never slide past the raster
+
+  unsigned nan_hist = 0;  // bit b: batch loaded b steps ago contained NaN (uniform)
+  int64_t loaded_hi = -1; // highest actual row resident (exclusive upper bound - 1)
+
+  auto ring_at = [&](int64_t row, int slot) -> float& { return ring[(size_t)(row % NRING) * SWp + slot]; };
+
+  for (int64_t y = yb0; y < yb1; y += FK_NB) {
+    // ---- (1) make rows [y-R, y+NB+R] (clipped to the raster) resident ----
+    int64_t need_lo = y - R < 0 ? 0 : y - R;
+    int64_t need_hi = y + FK_NB + R >= H ? H - 1 : y + FK_NB + R;
+    int64_t from = (y == yb0) ? need_lo : loaded_hi + 1;
+    __syncthreads();  // everyone is done with the rows about to be overwritten
+    int my_nan = 0;
+    for (int64_t row = from; row <= need_hi; ++row) {
+      for (int c = tid; c < SW; c += FK_THREADS) {
+        int64_t gx = cs0 + c;
+        if (gx >= 0 && gx < W) {
+          float v = p.dem[row * p.ld_in + gx];
+          my_nan |= (v != v);
+          ring_at(row, c) = v;
+        }
+      }
+    }
+    loaded_hi = need_hi;
+    int any = __syncthreads_or(my_nan);
+    nan_hist = (y == yb0) ? (any ? 0xffffffffu : 0u) : ((nan_hist << 1) | (any ? 1u : 0u));
+    // ring spans NB+2R+1 rows <= 4 batches (+1 for safety)
+    const bool nanmode = (nan_hist & 0x3fu) != 0;
+
+    // ---- (2) (re)initialise the running sums at the first batch of the band ----
+    if (y == yb0 && vcol_ok) {
+      for (int k = 0; k < nf; ++k) {
+        double s = 0.0;
+        int c = 0;
+        for (int d = -fr[k]; d <= fr[k]; ++d) {
+          float v = ring_at(reflect_index(y + d, H), vc);
+          bool ok = v == v;
+          s += ok ? (double)v : 0.0;
+          c += ok;
+        }
+        rs[k] = s;
+        rc[k] = c;
+      }
+    }
+
+    // ---- (3) terms in list order ----
+    float acc[FK_SEG];
+    int fk = 0;
+    bool first = true;
+    const int64_t orow = y + hi;  // output row of this thread in the horizontal phase
+    const bool hrow_ok = orow < yb1;
+    for (int t = 0; t < p.n_terms; ++t) {
+      const DevTerm& T = p.terms[t];
+      if (T.kind == TERM_BOX_FUSED) {
+        const int r = T.r;
+        const double n = (double)(2 * r + 1), inv = 1.0 / n;
+        const float nf32 = (float)(2 * r + 1);
+        // vertical phase: thread = column
+        if (vcol_ok && vc >= R - r && vc < R + FK_TW + r) {
+          double s = rs[fk];
+          int c = rc[fk];
+          for (int i = 0; i < FK_NB; ++i) {
+            int64_t row = y + i;
+            if (row >= yb1) break;
+            vplane[i * SWp + vc] = (float)div_by_count(s, n, inv);
+            float vin = ring_at(reflect_index(row + r + 1, H), vc);
+            float vout = ring_at(reflect_index(row - r, H), vc);
+            if (nanmode) {
+              cplane[i * SWp + vc] = (unsigned char)c;
+              bool oin = vin == vin, oout = vout == vout;
+              s += (oin ? (double)vin : 0.0) - (oout ? (double)vout : 0.0);
+              c += (int)oin - (int)oout;
+            } else {
+              s += (double)vin - (double)vout;
+            }
+          }
+          rs[fk] = s;
+          rc[fk] = c;
+        }
+        __syncthreads();
+        // horizontal phase: thread = (row, column segment)
+        if (hrow_ok && hjn > 0) {
+          const float* vrow = vplane + hi * SWp;
+          const unsigned char* crow = cplane + hi * SWp;
+          const float* xrow = ring + (size_t)(orow % NRING) * SWp;
+          auto slot = [&](int64_t j) -> int {  // strip slot of global column x0+j (reflected)
+            int64_t gx = x0 + j;
+            if (gx < 0 || gx >= W) gx = reflect_index(gx, W);
+            return (int)(gx - cs0);
+          };
+          double sv = 0.0, sw = 0.0;
+          for (int d = -r; d <= r; ++d) {
+            int sidx = slot(hj0 + d);
+            sv += (double)vrow[sidx];
+            if (nanmode) sw += (double)((float)crow[sidx] / nf32);
+          }
+#pragma unroll
+          for (int jj = 0; jj < FK_SEG; ++jj) {
+            if (jj < hjn) {
+              int64_t j = hj0 + jj;
+              float mean = (float)div_by_count(sv, n, inv);
+              if (nanmode) {
+                float den = (float)div_by_count(sw, n, inv);
+                mean = den > 0.f ? mean / den : 0.f;
+              }
+              float x = xrow[R + j];
+              float term = T.weight * (x - mean);
+              acc[jj] = first ? term : acc[jj] + term;
+              if (jj + 1 < hjn) {
+                int sin_ = slot(j + r + 1), sout = slot(j - r);
+                sv += (double)vrow[sin_] - (double)vrow[sout];
+                if (nanmode) sw += (double)((float)crow[sin_] / nf32) - (double)((float)crow[sout] / nf32);
+              }
+            }
+          }
+        }
+        __syncthreads();
+        ++fk;
+      } else if (T.kind == TERM_COARSE) {
+        if (hrow_ok && hjn > 0) {
+          const float* xrow = ring + (size_t)(orow % NRING) * SWp;
+          // scipy zoom(order=1): coordinate = index * (n_in-1)/(n_out-1); weights [1-t, t]; 'nearest' edge
+          double ri = (double)orow * T.rscale;
+          int64_t r0 = (int64_t)floor(ri);
+          if (r0 > T.gh - 1) r0 = T.gh - 1;
+          double tr = ri - (double)r0;
+          int64_t r1 = r0 + 1 < T.gh ? r0 + 1 : T.gh - 1;
+          double wr0 = 1.0 - tr, wr1 = tr;
+          const float* g0 = T.grid + r0 * T.gw;
+          const float* g1 = T.grid + r1 * T.gw;
+          double ci = (double)(x0 + hj0) * T.cscale;
+          int64_t c0 = (int64_t)floor(ci);
+          if (c0 > T.gw - 1) c0 = T.gw - 1;
+          double next_int = (double)(c0 + 1);
+          int64_t c1 = c0 + 1 < T.gw ? c0 + 1 : T.gw - 1;
+          double p00 = (double)g0[c0] * wr0, p01 = (double)g0[c1] * wr0;
+          double p10 = (double)g1[c0] * wr1, p11 = (double)g1[c1] * wr1;
+#pragma unroll
+          for (int jj = 0; jj < FK_SEG; ++jj) {
+            if (jj < hjn) {
+              int64_t gx = x0 + hj0 + jj;
+              if (gx < W) {
+                ci = (double)gx * T.cscale;
+                while (ci >= next_int && c0 < T.gw - 1) {
+                  ++c0;
+                  next_int += 1.0;
+                  c1 = c0 + 1 < T.gw ? c0 + 1 : T.gw - 1;
+                  p00 = (double)g0[c0] * wr0; p01 = (double)g0[c1] * wr0;
+                  p10 = (double)g1[c0] * wr1; p11 = (double)g1[c1] * wr1;
+                }
+                double tc = ci - (double)c0;
+                double wc0 = 1.0 - tc;
+                double v = p00 * wc0;
+                v += p01 * tc;
+                v += p10 * wc0;
+                v += p11 * tc;
+                float mean = (float)v;
+                float x = xrow[R + hj0 + jj];
+                float term = T.weight * (x - mean);
+                acc[jj] = first ? term : acc[jj] + term;
+              }
+            }
+          }
+        }
+      } else {  // TERM_PLANE: precomputed full-resolution mean
+        if (hrow_ok && hjn > 0) {
+          const float* xrow = ring + (size_t)(orow % NRING) * SWp;
+          const float* prow = T.grid + orow * W;
+#pragma unroll
+          for (int jj = 0; jj < FK_SEG; ++jj) {
+            if (jj < hjn) {
+              int64_t gx = x0 + hj0 + jj;
+              if (gx < W) {
+                float x = xrow[R + hj0 + jj];
+                float term = T.weight * (x - prow[gx]);
+                acc[jj] = first ? term : acc[jj] + term;
+              }
+            }
+          }
+        }
+      }
+      first = false;
+    }
+
+    // ---- (4) epilogue: normalise, stage, coalesced store ----
+    float* stage = vplane;  // FK_NB x (FK_TW+1)
+    if (hrow_ok && hjn > 0) {
+#pragma unroll
+      for (int jj = 0; jj < FK_SEG; ++jj) {
+        if (jj < hjn) {
+          float v = acc[jj];
+          if (p.norm_mode == 1) v = v / p.norm_scale;
+          else if (p.norm_mode == 2) v = (v != v) ? v : 0.f;
+          stage[hi * (FK_TW + 1) + hj0 + jj] = v;
+        }
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < FK_NB * FK_TW; idx += FK_THREADS) {
+      int rr = idx / FK_TW, c = idx - rr * FK_TW;
+      int64_t gy = y + rr, gx = x0 + c;
+      if (gy < yb1 && gx < W) store_out(p.out, gy * p.ld_out + gx, stage[rr * (FK_TW + 1) + c], p.enc);
+    }
+  }
+}
+
+static size_t fused_smem_bytes(int R) {
+  size_t SWp = (size_t)((FK_TW + 2 * R) | 1);
+  size_t nring = FK_NB + 2 * R + 1;
+  size_t vp = (size_t)FK_NB * SWp;
+  size_t stage = (size_t)FK_NB * (FK_TW + 1);
+  if (stage > vp) vp = stage;
+  return nring * SWp * 4 + vp * 4 + align_up((size_t)FK_NB * SWp, 16);
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+static int mean_on_grid(const Grid& g, int size, float* out, float* tv, float* tw, double* taps, cudaStream_t s) {
+  int rc;
+  if (size == 0) {  // sigma = 1 gaussian, 'nearest'
+    if ((rc = launch_gauss_taps(1.0, 4, taps, s))) return rc;
+    if ((rc = launch_gauss_axis0(g, taps, 4, tv, tw, nullptr, s))) return rc;
+    return launch_gauss_axis1(tv, tw, g.h, g.w, taps, 4, COMBINE_MEAN, out, nullptr, nullptr, s);
+  }
+  if ((rc = launch_box_axis0(g, size, tv, tw, s))) return rc;
+  return launch_box_axis1(tv, tw, g.h, g.w, size, out, s);
+}
+
+static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_t ld_in, int64_t ld_out,
+                       const int32_t* radii, const float* weights, int n, double pixel_size, double norm_scale,
+                       const fsg_encode* enc, void* ws, size_t ws_bytes, cudaStream_t s) {
+  HostPlan plan;
+  int rc = make_plan(H, W, radii, n, pixel_size, &plan);
+  if (rc) return rc;
+  if (!dem || !out) return fail(FSG_E_INVALID, "fsg_topousm_fast: NULL buffer");
+  if (ld_in < W || ld_out < W) return fail(FSG_E_INVALID, "fsg_topousm_fast: row stride smaller than width");
+  if (plan.total > 0 && (!ws || ws_bytes < plan.total))
+    return fail(FSG_E_WORKSPACE, "fsg_topousm_fast: workspace of %zu bytes needed, %zu given", plan.total, ws_bytes);
+  unsigned char* base = (unsigned char*)ws;
+  float* tv = (float*)(base + plan.off_tv);
+  float* tw = (float*)(base + plan.off_tw);
+  double* taps = (double*)(base + plan.off_taps);
+  int* flags = (int*)(base + plan.off_flags);
+
+  if (plan.n_levels > 0) {
+    zero_flags_kernel<<<1, 32, 0, s>>>(flags);
+    FSG_LAUNCH_OK();
+    PyramidParams pp{};
+    pp.dem = dem; pp.H = H; pp.W = W; pp.ld = ld_in; pp.n_levels = plan.n_levels; pp.flags = flags;
+    for (int k = 0; k < plan.n_levels; ++k) {
+      pp.f[k] = plan.levels[k].f;
+      pp.grid[k] = (float*)(base + plan.levels[k].off);
+      pp.gw[k] = plan.levels[k].w;
+      pp.gh[k] = plan.levels[k].h;
+    }
+    dim3 grid((unsigned)((W + PY_COLS - 1) / PY_COLS), (unsigned)((H + PY_ROWS - 1) / PY_ROWS));
+    pyramid_kernel<<<grid, 256, 0, s>>>(pp);
+    FSG_LAUNCH_OK();
+    // enclosed-void fill (runs only when the level has an all-NaN cell; device-side flag)
+    for (int k = 0; k < plan.n_levels; ++k) {
+      const HostLevel& l = plan.levels[k];
+      double sigma = (double)(l.h < l.w ? l.h : l.w) / 64.0;
+      if (sigma < 1.0) sigma = 1.0;
+      int radius = (int)(4.0 * sigma + 0.5);
+      float* grid_k = (float*)(base + l.off);
+      Grid g{grid_k, l.h, l.w, l.w};
+      if ((rc = launch_gauss_taps(sigma, radius, taps, s))) return rc;
+      if ((rc = launch_gauss_axis0(g, taps, radius, tv, tw, flags + k, s))) return rc;
+      if ((rc = launch_gauss_axis1(tv, tw, l.h, l.w, taps, radius, COMBINE_VOIDFILL, grid_k, flags + k, flags + 4 + k, s)))
+        return rc;
+    }
+  }
+
+  FusedParams fp{};
+  fp.dem = dem; fp.out = out; fp.H = H; fp.W = W; fp.ld_in = ld_in; fp.ld_out = ld_out;
+  fp.n_terms = n; fp.R = plan.fused_R;
+  fp.enc = make_encode(enc);
+  if (is_none(norm_scale)) fp.norm_mode = 0;
+  else if (norm_scale > 0.0) { fp.norm_mode = 1; fp.norm_scale = (float)norm_scale; }
+  else fp.norm_mode = 2;
+  for (int i = 0; i < n; ++i) {
+    const HostTerm& t = plan.terms[i];
+    DevTerm& d = fp.terms[i];
+    d.kind = t.kind; d.r = t.radius; d.weight = weights[i];
+    if (t.kind == TERM_COARSE) {
+      const HostLevel& l = plan.levels[t.level];
+      float* mean = (float*)(base + t.grid_off);
+      Grid g{(const float*)(base + l.off), l.h, l.w, l.w};
+      if ((rc = mean_on_grid(g, t.size, mean, tv, tw, taps, s))) return rc;
+      d.grid = mean; d.gh = l.h; d.gw = l.w;
+      // scipy.ndimage.zoom: zoom = (n_in - 1) / (n_out - 1)  (1.0 when n_out == 1)
+      d.rscale = H > 1 ? (double)(l.h - 1) / (double)(H - 1) : 1.0;
+      d.cscale = W > 1 ? (double)(l.w - 1) / (double)(W - 1) : 1.0;
+    } else if (t.kind == TERM_PLANE) {
+      float* mean = (float*)(base + t.grid_off);
+      Grid g{dem, H, W, ld_in};
+      if ((rc = mean_on_grid(g, t.size, mean, tv, tw, taps, s))) return rc;
+      d.grid = mean; d.gh = H; d.gw = W;
+    }
+  }
+  // bands: enough CTAs to fill the machine, few enough that the (2R+1)-row warm-up stays small
+  int64_t strips = (W + FK_TW - 1) / FK_TW;
+  int64_t want_bands = (H + 1023) / 2048;
+  if (want_bands < 1) want_bands = 1;
+  const int64_t min_rows = 8 * (int64_t)(2 * plan.fused_R + 1);
+  while (strips * want_bands < 148 * 6 && (H + 2 * want_bands - 1) / (2 * want_bands) >= min_rows) want_bands *= 2;
+  int64_t band_rows = (H + want_bands - 1) / want_bands;
+  band_rows = (band_rows + FK_NB - 1) / FK_NB * FK_NB;
+  if (band_rows > (1 << 30)) band_rows = 1 << 30;
+  fp.band_rows = (int)band_rows;
+  int64_t bands = (H + band_rows - 1) / band_rows;
+  if (bands > 65535) return fail(FSG_E_UNSUPPORTED, "fsg_topousm_fast: raster too tall");
+  size_t smem = fused_smem_bytes(plan.fused_R);
+  FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)strips, (unsigned)bands);
+  fused_kernel<<<grid, FK_THREADS, smem, s>>>(fp);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// stand-alone helpers (exposed for parity tests and for the reference's other call sites)
+// ------------------------------------------------------------------------------------------
+// _upsample_to_shape (algorithms/_nan_utils.py:671-698): zoom(order=1) with align-corners mapping.
+// NaN-aware branch when *has_nan != 0: zoom of filled & valid, num/max(den,1e-6) where den>1e-3.
+__global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t h,
+                                                       int64_t w, int64_t H, int64_t W, double rscale, double cscale,
+                                                       const int* has_nan) {
+  int64_t x = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  int64_t y = (int64_t)blockIdx.y + (int64_t)blockIdx.z * 32768;
+  if (x >= W || y >= H) return;
+  double ri = (double)y * rscale, ci = (double)x * cscale;
+  int64_t r0 = (int64_t)floor(ri), c0 = (int64_t)floor(ci);
+  if (r0 > h - 1) r0 = h - 1;
+  if (c0 > w - 1) c0 = w - 1;
+  double tr = ri - (double)r0, tc = ci - (double)c0;
+  int64_t r1 = r0 + 1 < h ? r0 + 1 : h - 1, c1 = c0 + 1 < w ? c0 + 1 : w - 1;
+  float a00 = in[r0 * w + c0], a01 = in[r0 * w + c1], a10 = in[r1 * w + c0], a11 = in[r1 * w + c1];
+  double wr0 = 1.0 - tr, wr1 = tr, wc0 = 1.0 - tc, wc1 = tc;
+  if (!*has_nan) {
+    double v = ((double)a00 * wr0) * wc0;
+    v += ((double)a01 * wr0) * wc1;
+    v += ((double)a10 * wr1) * wc0;
+    v += ((double)a11 * wr1) * wc1;
+    out[y * W + x] = (float)v;
+  } else {
+    auto val = [](float a) { return a != a ? 0.0 : (double)a; };
+    auto ok = [](float a) { return a != a ? 0.0 : 1.0; };
+    double n = (val(a00) * wr0) * wc0; n += (val(a01) * wr0) * wc1; n += (val(a10) * wr1) * wc0; n += (val(a11) * wr1) * wc1;
+    double d = (ok(a00) * wr0) * wc0; d += (ok(a01) * wr0) * wc1; d += (ok(a10) * wr1) * wc0; d += (ok(a11) * wr1) * wc1;
+    float nf = (float)n, df = (float)d;
+    out[y * W + x] = df > 1e-3f ? nf / fmaxf(df, 1e-6f) : nanf("");
+  }
+}
+
+__global__ void any_nan_kernel(const float* __restrict__ in, int64_t n, int* flag) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t step = (int64_t)gridDim.x * blockDim.x;
+  int f = 0;
+  for (; i < n; i += step) f |= (in[i] != in[i]);
+  if (__syncthreads_or(f) && threadIdx.x == 0) *flag = 1;
+}
+
+// _bilinear_sample_coarse (algorithms/_nan_utils.py:255-281) fused with W_large*block - up
+// (algorithms/_impl_topousm_fast.py:158-186): f32 coordinates, map_coordinates(order=1, 'nearest').
+__global__ void __launch_bounds__(256) large_part_kernel(const float* __restrict__ block, float* __restrict__ out, int64_t h,
+                                                         int64_t w, int64_t ld_in, int64_t ld_out,
+                                                         const float* __restrict__ field, int64_t ch, int64_t cw,
+                                                         int64_t ld_f, int64_t off_r, int64_t off_c, float sr, float sc,
+                                                         float w_large) {
+  int64_t x = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  int64_t y = (int64_t)blockIdx.y + (int64_t)blockIdx.z * 32768;
+  if (x >= w || y >= h) return;
+  // (arange(r0, r1, f32) + 0.5f) * f32(ch/full_h) - 0.5f, all f32
+  float rr = ((float)(off_r + y) + 0.5f) * sr - 0.5f;
+  float cc = ((float)(off_c + x) + 0.5f) * sc - 0.5f;
+  // map_coordinates order=1, mode='nearest': coordinates are used in f64
+  double dr = (double)rr, dc = (double)cc;
+  auto tap = [&](double coord, int64_t n, int64_t* i0, int64_t* i1, double* t) {
+    double fl = floor(coord);
+    *t = coord - fl;
+    int64_t a = (int64_t)fl, b = a + 1;
+    *i0 = a < 0 ? 0 : (a > n - 1 ? n - 1 : a);
+    *i1 = b < 0 ? 0 : (b > n - 1 ? n - 1 : b);
+  };
+  int64_t r0, r1, c0, c1;
+  double tr, tc;
+  tap(dr, ch, &r0, &r1, &tr);
+  tap(dc, cw, &c0, &c1, &tc);
+  double v = ((double)field[r0 * ld_f + c0] * (1.0 - tr)) * (1.0 - tc);
+  v += ((double)field[r0 * ld_f + c1] * (1.0 - tr)) * tc;
+  v += ((double)field[r1 * ld_f + c0] * tr) * (1.0 - tc);
+  v += ((double)field[r1 * ld_f + c1] * tr) * tc;
+  float up = (float)v;
+  out[y * ld_out + x] = w_large * block[y * ld_in + x] - up;
+}
+
+static int run_decimate(const float* in, float* out, int64_t H, int64_t W, int64_t ld_in, int f, void* ws,
+                        size_t ws_bytes, cudaStream_t s) {
+  if (f != 2 && f != 4 && f != 8 && f != 16) return fail(FSG_E_INVALID, "fsg_decimate: factor must be 2, 4, 8 or 16");
+  if (!in || !out || H < 1 || W < 1 || ld_in < W) return fail(FSG_E_INVALID, "fsg_decimate: bad argument");
+  int64_t h = (H + f - 1) / f, w = (W + f - 1) / f;
+  double sigma = (double)(h < w ? h : w) / 64.0;
+  if (sigma < 1.0) sigma = 1.0;
+  int radius = (int)(4.0 * sigma + 0.5);
+  size_t plane = align_up((size_t)h * w * 4, 256);
+  size_t need = 2 * plane + align_up((size_t)(radius + 1) * 8, 256) + 256;
+  if (!ws || ws_bytes < need) return fail(FSG_E_WORKSPACE, "fsg_decimate: workspace of %zu bytes needed", need);
+  unsigned char* base = (unsigned char*)ws;
+  float* tv = (float*)base;
+  float* tw = (float*)(base + plane);
+  double* taps = (double*)(base + 2 * plane);
+  int* flags = (int*)(base + 2 * plane + align_up((size_t)(radius + 1) * 8, 256));
+  zero_flags_kernel<<<1, 32, 0, s>>>(flags);
+  FSG_LAUNCH_OK();
+  PyramidParams pp{};
+  pp.dem = in; pp.H = H; pp.W = W; pp.ld = ld_in; pp.n_levels = 1; pp.flags = flags;
+  pp.f[0] = f; pp.grid[0] = out; pp.gw[0] = w; pp.gh[0] = h;
+  dim3 grid((unsigned)((W + PY_COLS - 1) / PY_COLS), (unsigned)((H + PY_ROWS - 1) / PY_ROWS));
+  pyramid_kernel<<<grid, 256, 0, s>>>(pp);
+  FSG_LAUNCH_OK();
+  Grid g{out, h, w, w};
+  int rc;
+  if ((rc = launch_gauss_taps(sigma, radius, taps, s))) return rc;
+  if ((rc = launch_gauss_axis0(g, taps, radius, tv, tw, flags, s))) return rc;
+  return launch_gauss_axis1(tv, tw, h, w, taps, radius, COMBINE_VOIDFILL, out, flags, flags + 4, s);
+}
+
+}  // namespace fsg
+
+extern "C" {
+
+size_t fsg_topousm_fast_workspace_bytes(int64_t H, int64_t W, const int32_t* radii_host, int n_radii, double pixel_size) {
+  fsg::HostPlan plan;
+  if (fsg::make_plan(H, W, radii_host, n_radii, pixel_size, &plan)) return 0;
+  return plan.total;
+}
+
+int fsg_topousm_fast(const float* dem, void* out, int64_t H, int64_t W, int64_t ld_in, int64_t ld_out,
+                     const int32_t* radii_host, const float* weights_host, int n_radii, double pixel_size,
+                     double norm_scale, const fsg_encode* enc, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!radii_host || !weights_host) return fsg::fail(FSG_E_INVALID, "fsg_topousm_fast: radii/weights are NULL");
+  return fsg::run_topousm(dem, out, H, W, ld_in, ld_out, radii_host, weights_host, n_radii, pixel_size, norm_scale,
+                          enc, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+
+size_t fsg_decimate_workspace_bytes(int64_t H, int64_t W, int factor) {
+  if (factor < 2 || H < 1 || W < 1) return 0;
+  int64_t h = (H + factor - 1) / factor, w = (W + factor - 1) / factor;
+  double sigma = (double)(h < w ? h : w) / 64.0;
+  if (sigma < 1.0) sigma = 1.0;
+  int radius = (int)(4.0 * sigma + 0.5);
+  return 2 * fsg::align_up((size_t)h * w * 4, 256) + fsg::align_up((size_t)(radius + 1) * 8, 256) + 256;
+}
+
+int fsg_decimate(const float* in, float* out, int64_t H, int64_t W, int64_t ld_in, int factor, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  return fsg::run_decimate(in, out, H, W, ld_in, factor, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+/* workspace: >= 256 bytes (NaN flag) */
+int fsg_upsample(const float* in, float* out, int64_t h, int64_t w, int64_t H, int64_t W, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  using namespace fsg;
+  if (!in || !out || h < 1 || w < 1 || H < 1 || W < 1) return fail(FSG_E_INVALID, "fsg_upsample: bad argument");
+  if (!workspace || workspace_bytes < 256) return fail(FSG_E_WORKSPACE, "fsg_upsample: 256-byte workspace needed");
+  cudaStream_t s = (cudaStream_t)stream;
+  int* flag = (int*)workspace;
+  zero_flags_kernel<<<1, 32, 0, s>>>(flag);
+  FSG_LAUNCH_OK();
+  int64_t n = h * w;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  any_nan_kernel<<<blocks, 256, 0, s>>>(in, n, flag);
+  FSG_LAUNCH_OK();
+  double rs = H > 1 ? (double)(h - 1) / (double)(H - 1) : 1.0;
+  double cs = W > 1 ? (double)(w - 1) / (double)(W - 1) : 1.0;
+  dim3 grid((unsigned)((W + 255) / 256), (unsigned)(H < 32768 ? H : 32768), (unsigned)((H + 32767) / 32768));
+  upsample_kernel<<<grid, 256, 0, s>>>(in, out, h, w, H, W, rs, cs, flag);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_topousm_large_part(const float* block, float* out, int64_t h, int64_t w, int64_t ld_in, int64_t ld_out,
+                           const float* field, int64_t ch, int64_t cw, int64_t ld_field, int64_t off_r, int64_t off_c,
+                           int64_t full_h, int64_t full_w, double w_large, void* stream) {
+  using namespace fsg;
+  if (!block || !out || !field || h < 1 || w < 1 || ch < 1 || cw < 1 || full_h < 1 || full_w < 1)
+    return fail(FSG_E_INVALID, "fsg_topousm_large_part: bad argument");
+  float sr = (float)((double)ch / (double)full_h), sc = (float)((double)cw / (double)full_w);
+  dim3 grid((unsigned)((w + 255) / 256), (unsigned)(h < 32768 ? h : 32768), (unsigned)((h + 32767) / 32768));
+  large_part_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(block, out, h, w, ld_in, ld_out, field, ch, cw, ld_field,
+                                                           off_r, off_c, sr, sc, (float)w_large);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+}  // extern "C"

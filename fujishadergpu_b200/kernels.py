@@ -1,0 +1,306 @@
+"""Functional Python face of the C ABI (include/fsg_b200.h): one function per entry point, taking
+device arrays and returning device arrays.  No arithmetic happens here -- only argument marshalling,
+output / workspace allocation (through torch's caching allocator) and error translation."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _device as dev
+from . import _lib
+from ._lib import Encode, Window, check, make_encode, opt
+
+_SLOPE_UNITS = {"degree": 0, "percent": 1, "radian": 2}
+_CURV_TYPES = {"mean": 0, "gaussian": 1, "planform": 2, "profile": 3}
+
+
+def _ptr(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr())
+
+
+def _window(t: torch.Tensor, out: torch.Tensor, *, h_global=None, buf_row0=0, out_row0=None, out_rows=None) -> Window:
+    H = int(t.shape[0]) if h_global is None else int(h_global)
+    o0 = int(buf_row0) if out_row0 is None else int(out_row0)
+    n = int(out.shape[0]) if out_rows is None else int(out_rows)
+    return Window(H, int(t.shape[1]), int(buf_row0), int(t.shape[0]), o0, n, int(t.stride(0)), int(out.stride(0)))
+
+
+def _band_args(t, band):
+    """band = None (whole raster) or dict(h_global, buf_row0, out_row0, out_rows) for a row-band shard."""
+    if band is None:
+        return dict(h_global=int(t.shape[0]), buf_row0=0, out_row0=0, out_rows=int(t.shape[0]))
+    return dict(h_global=int(band["h_global"]), buf_row0=int(band["buf_row0"]),
+                out_row0=int(band["out_row0"]), out_rows=int(band["out_rows"]))
+
+
+def hillshade(dem, *, azimuth=315, altitude=45, z_factor=1.0, pixel_size=1.0, pixel_scale_x=None,
+              pixel_scale_y=None, output_dtype="float32", qp=None, band=None) -> torch.Tensor:
+    t = dev.as_f32_2d(dem)
+    b = _band_args(t, band)
+    out = dev.empty_out(t, (b["out_rows"], t.shape[1]), output_dtype)
+    win = _window(t, out, **b)
+    enc = make_encode(output_dtype, qp)
+    z = 1.0 if z_factor is None else float(z_factor)
+    check(_lib.load().fsg_hillshade(_ptr(t), _ptr(out), C.byref(win), float(azimuth), float(altitude), z,
+                                    float(pixel_size), opt(pixel_scale_x), opt(pixel_scale_y), C.byref(enc),
+                                    C.c_void_p(dev.stream_ptr(t))), "fsg_hillshade")
+    return out
+
+
+def slope(dem, *, unit="degree", pixel_size=1.0, pixel_scale_x=None, pixel_scale_y=None,
+          output_dtype="float32", qp=None, band=None) -> torch.Tensor:
+    t = dev.as_f32_2d(dem)
+    b = _band_args(t, band)
+    out = dev.empty_out(t, (b["out_rows"], t.shape[1]), output_dtype)
+    win = _window(t, out, **b)
+    enc = make_encode(output_dtype, qp)
+    # the reference treats any unit other than degree/percent as radian (_impl_slope.py:28-33)
+    u = _SLOPE_UNITS.get(str(unit), 2)
+    check(_lib.load().fsg_slope(_ptr(t), _ptr(out), C.byref(win), u, float(pixel_size), opt(pixel_scale_x),
+                                opt(pixel_scale_y), C.byref(enc), C.c_void_p(dev.stream_ptr(t))), "fsg_slope")
+    return out
+
+
+def curvature(dem, *, curvature_type="mean", pixel_size=1.0, pixel_scale_x=None, pixel_scale_y=None,
+              output_dtype="float32", qp=None, band=None) -> torch.Tensor:
+    t = dev.as_f32_2d(dem)
+    b = _band_args(t, band)
+    out = dev.empty_out(t, (b["out_rows"], t.shape[1]), output_dtype)
+    win = _window(t, out, **b)
+    enc = make_encode(output_dtype, qp)
+    # anything but mean/gaussian/planform falls to the profile branch (_impl_curvature.py:48)
+    ct = _CURV_TYPES.get(str(curvature_type), 3)
+    check(_lib.load().fsg_curvature(_ptr(t), _ptr(out), C.byref(win), ct, float(pixel_size), opt(pixel_scale_x),
+                                    opt(pixel_scale_y), C.byref(enc), C.c_void_p(dev.stream_ptr(t))), "fsg_curvature")
+    return out
+
+
+def _radii_weights(radii: Sequence, weights: Optional[Sequence]):
+    rr = np.asarray([int(r) for r in radii], dtype=np.int32)
+    if weights is None:
+        # np.array([1/n]*n, dtype=float32)  (_impl_topousm_fast.py:58-59)
+        ww = np.asarray([1.0 / len(rr)] * len(rr), dtype=np.float32)
+    else:
+        ww = np.asarray(weights.cpu() if isinstance(weights, torch.Tensor) else weights, dtype=np.float32).reshape(-1)
+        if len(ww) != len(rr):
+            raise ValueError(f"Length of weights ({len(ww)}) must match length of radii ({len(rr)})")
+    return np.ascontiguousarray(rr), np.ascontiguousarray(ww)
+
+
+def topousm_fast_workspace_bytes(shape, radii, pixel_size=1.0) -> int:
+    rr = np.ascontiguousarray(np.asarray([int(r) for r in radii], dtype=np.int32))
+    return int(_lib.load().fsg_topousm_fast_workspace_bytes(
+        int(shape[0]), int(shape[1]), rr.ctypes.data_as(C.POINTER(C.c_int32)), len(rr), float(pixel_size)))
+
+
+def topousm_fast(dem, *, radii, weights=None, pixel_size=1.0, norm_scale=None, output_dtype="float32",
+                 qp=None, workspace: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Whole pipeline for one block == whole raster.  norm_scale=None -> raw block output."""
+    t = dev.as_f32_2d(dem)
+    if radii is None or len(radii) == 0:
+        raise ValueError("At least one radius value is required")
+    rr, ww = _radii_weights(radii, weights)
+    lib = _lib.load()
+    need = topousm_fast_workspace_bytes(t.shape, rr, pixel_size)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(max(need, 256), dtype=torch.uint8, device=t.device)
+    if out is None:
+        out = dev.empty_out(t, t.shape, output_dtype)
+    enc = make_encode(output_dtype, qp)
+    check(lib.fsg_topousm_fast(_ptr(t), _ptr(out), int(t.shape[0]), int(t.shape[1]), int(t.stride(0)),
+                               int(out.stride(0)), rr.ctypes.data_as(C.POINTER(C.c_int32)),
+                               ww.ctypes.data_as(C.POINTER(C.c_float)), len(rr), float(pixel_size), opt(norm_scale),
+                               C.byref(enc), _ptr(workspace), workspace.numel() * workspace.element_size(),
+                               C.c_void_p(dev.stream_ptr(t))), "fsg_topousm_fast")
+    return out
+
+
+def topousm_large_part(block, field, *, w_large, off_r, off_c, full_h, full_w) -> torch.Tensor:
+    t = dev.as_f32_2d(block)
+    f = dev.as_f32_2d(field)
+    out = dev.empty_out(t, t.shape, "float32")
+    check(_lib.load().fsg_topousm_large_part(_ptr(t), _ptr(out), int(t.shape[0]), int(t.shape[1]), int(t.stride(0)),
+                                             int(out.stride(0)), _ptr(f), int(f.shape[0]), int(f.shape[1]),
+                                             int(f.stride(0)), int(off_r), int(off_c), int(full_h), int(full_w),
+                                             float(w_large), C.c_void_p(dev.stream_ptr(t))), "fsg_topousm_large_part")
+    return out
+
+
+def openness_table(num_directions: int, max_distance: int, pixel_size=1.0, pixel_scale_x=None, pixel_scale_y=None):
+    """Ray-sample table built with NumPy exactly as algorithms/_impl_openness.py:58-68,96-109 does
+    (host integers and Python floats only -- no image arithmetic)."""
+    angles = np.linspace(0, 2 * np.pi, num_directions, endpoint=False)
+    dirs = np.stack([np.cos(angles), np.sin(angles)], axis=1)
+    distances = np.unique((np.linspace(0.1, 1.0, 10) * max_distance).astype(int))
+    distances = distances[distances > 0]
+    sx = abs(float(pixel_scale_x)) if pixel_scale_x is not None else float(pixel_size)
+    sy = abs(float(pixel_scale_y)) if pixel_scale_y is not None else float(pixel_size)
+    if sx < 1e-9:
+        sx = float(pixel_size) if pixel_size else 1.0
+    if sy < 1e-9:
+        sy = float(pixel_size) if pixel_size else 1.0
+    start, ox, oy, dist = [0], [], [], []
+    for d in range(num_directions):
+        for r in distances:
+            ax = int(round(float(r) * float(dirs[d][0])))
+            ay = int(round(float(r) * float(dirs[d][1])))
+            if ax == 0 and ay == 0:
+                continue
+            ox.append(ax)
+            oy.append(ay)
+            dist.append(max(float(np.hypot(float(ax) * sx, float(ay) * sy)), 1e-9))
+        start.append(len(ox))
+    return (np.asarray(start, np.int32), np.asarray(ox, np.int32), np.asarray(oy, np.int32),
+            np.asarray(dist, np.float32))
+
+
+def openness(dem, *, openness_type="positive", num_directions=16, max_distance=50, pixel_size=1.0,
+             pixel_scale_x=None, pixel_scale_y=None, stretch=None, output_dtype="float32", qp=None,
+             band=None) -> torch.Tensor:
+    t = dev.as_f32_2d(dem)
+    b = _band_args(t, band)
+    out = dev.empty_out(t, (b["out_rows"], t.shape[1]), output_dtype)
+    win = _window(t, out, **b)
+    enc = make_encode(output_dtype, qp)
+    start, ox, oy, dist = openness_table(int(num_directions), int(max_distance), pixel_size, pixel_scale_x, pixel_scale_y)
+    lo, sc = (float("nan"), float("nan"))
+    if isinstance(stretch, (tuple, list)) and len(stretch) >= 2 and float(stretch[1]) > 1e-12:
+        lo, sc = float(stretch[0]), float(stretch[1])
+    if len(ox) == 0:  # keep pointers valid
+        ox = np.zeros(1, np.int32); oy = np.zeros(1, np.int32); dist = np.ones(1, np.float32)
+    i32 = C.POINTER(C.c_int32)
+    check(_lib.load().fsg_openness_samples(
+        _ptr(t), _ptr(out), C.byref(win), 0 if openness_type == "positive" else 1, int(num_directions),
+        start.ctypes.data_as(i32), ox.ctypes.data_as(i32), oy.ctypes.data_as(i32),
+        dist.ctypes.data_as(C.POINTER(C.c_float)), lo, sc, C.byref(enc), C.c_void_p(dev.stream_ptr(t))),
+        "fsg_openness")
+    return out
+
+
+def decimate(dem, factor: int) -> torch.Tensor:
+    t = dev.as_f32_2d(dem)
+    f = int(factor)
+    if f <= 1:
+        return t
+    H, W = int(t.shape[0]), int(t.shape[1])
+    lib = _lib.load()
+    need = int(lib.fsg_decimate_workspace_bytes(H, W, f))
+    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=t.device)
+    out = dev.empty_out(t, ((H + f - 1) // f, (W + f - 1) // f), "float32")
+    check(lib.fsg_decimate(_ptr(t), _ptr(out), H, W, int(t.stride(0)), f, _ptr(ws), need,
+                           C.c_void_p(dev.stream_ptr(t))), "fsg_decimate")
+    return out
+
+
+def upsample(coarse, shape) -> torch.Tensor:
+    t = dev.as_f32_2d(coarse).contiguous()
+    H, W = int(shape[0]), int(shape[1])
+    if (int(t.shape[0]), int(t.shape[1])) == (H, W):
+        return t
+    out = dev.empty_out(t, (H, W), "float32")
+    ws = torch.empty(256, dtype=torch.uint8, device=t.device)
+    check(_lib.load().fsg_upsample(_ptr(t), _ptr(out), int(t.shape[0]), int(t.shape[1]), H, W, _ptr(ws), 256,
+                                   C.c_void_p(dev.stream_ptr(t))), "fsg_upsample")
+    return out
+
+
+def encode(arr, qp: dict, output_dtype: str) -> torch.Tensor:
+    t = dev.as_tensor(arr)
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    t = t.contiguous()
+    out = dev.empty_out(t, t.shape, output_dtype)
+    enc = make_encode(output_dtype, qp)
+    check(_lib.load().fsg_encode_f32(_ptr(t), _ptr(out), t.numel(), C.byref(enc), C.c_void_p(dev.stream_ptr(t))),
+          "fsg_encode_f32")
+    return out
+
+
+def scale(arr, scale_value: float) -> torch.Tensor:
+    t = dev.as_tensor(arr).to(torch.float32).contiguous()
+    out = torch.empty_like(t)
+    check(_lib.load().fsg_scale_f32(_ptr(t), _ptr(out), t.numel(), float(scale_value), C.c_void_p(dev.stream_ptr(t))),
+          "fsg_scale_f32")
+    return out
+
+
+def stretch(arr, lo: float, scale_value: float) -> torch.Tensor:
+    t = dev.as_tensor(arr).to(torch.float32).contiguous()
+    out = torch.empty_like(t)
+    check(_lib.load().fsg_stretch_f32(_ptr(t), _ptr(out), t.numel(), float(lo), float(scale_value),
+                                      C.c_void_p(dev.stream_ptr(t))), "fsg_stretch_f32")
+    return out
+
+
+def _pooled_views(chunks):
+    views = [dev.as_tensor(c) for c in chunks]
+    views = [v if v.ndim == 2 else v.reshape(1, -1) for v in views]
+    views = [v if (v.dtype == torch.float32 and v.stride(1) == 1) else v.to(torch.float32).contiguous() for v in views]
+    if len(views) > 16:  # the C entry point pools up to 16 chunks
+        views = [torch.cat([v.reshape(-1) for v in views]).reshape(1, -1)]
+    return views
+
+
+def order_stats(chunks: Sequence, rank: int, *, take_abs: bool, finite_only: bool):
+    """(a[rank], a[rank+1], n) over the pooled non-NaN (or finite) samples of the 2-D device views in
+    `chunks`; rank < 0 only counts.  One host sync per call (stats are host scalars by contract)."""
+    views = _pooled_views(chunks)
+    n = len(views)
+    if n == 0:
+        return float("nan"), float("nan"), 0
+    lib = _lib.load()
+    ptrs = (C.c_void_p * n)(*[v.data_ptr() for v in views])
+    rows = (C.c_int64 * n)(*[int(v.shape[0]) for v in views])
+    cols = (C.c_int64 * n)(*[int(v.shape[1]) for v in views])
+    lds = (C.c_int64 * n)(*[int(v.stride(0)) if v.shape[0] > 1 else int(v.shape[1]) for v in views])
+    d = views[0].device
+    result = torch.empty(4, dtype=torch.float64, device=d)
+    wsb = int(lib.fsg_order_stats_workspace_bytes())
+    ws = torch.empty(wsb, dtype=torch.uint8, device=d)
+    check(lib.fsg_order_stats(ptrs, rows, cols, lds, n, int(rank), 1 if take_abs else 0, 1 if finite_only else 0,
+                              _ptr(result), _ptr(ws), wsb, C.c_void_p(dev.stream_ptr(views[0]))), "fsg_order_stats")
+    res = result.cpu().tolist()
+    return float(res[0]), float(res[1]), int(res[3])
+
+
+def percentile(chunks: Sequence, q: float, *, take_abs=False, finite_only=False) -> float:
+    """np.percentile(sample, q) for an f32 sample (method 'linear'); NaN when the sample is empty.
+    Index and interpolation arithmetic are NumPy's own f32 scalar ops
+    (numpy/lib/_function_base_impl.py: percentile -> _quantile -> _lerp)."""
+    views = _pooled_views(chunks)
+    _, _, n = order_stats(views, -1, take_abs=take_abs, finite_only=finite_only)
+    if n == 0:
+        return float("nan")
+    q32 = np.true_divide(q, np.float32(100))
+    vi = (n - 1) * q32                      # f32 scalar, like numpy's get_virtual_index
+    prev = int(np.floor(vi))
+    prev = min(max(prev, 0), n - 1)
+    gamma = np.asanyarray(vi - np.floor(vi), dtype=np.asanyarray(vi).dtype)[()]
+    lo, hi, _ = order_stats(views, prev, take_abs=take_abs, finite_only=finite_only)
+    a, b = np.float32(lo), np.float32(hi)
+    diff = b - a
+    out = a + diff * gamma
+    if gamma >= 0.5:
+        out = b - diff * (1 - gamma)
+    return float(out)
+
+
+def synth_dem(shape, *, seed=20261017, nodata=False, device="cuda", row0=0, h_global=None, out=None) -> torch.Tensor:
+    rows, W = int(shape[0]), int(shape[1])
+    H = rows if h_global is None else int(h_global)
+    if out is None:
+        out = torch.empty((rows, W), dtype=torch.float32, device=device)
+    check(_lib.load().fsg_synth_dem(_ptr(out), H, W, int(row0), rows, int(out.stride(0)), int(seed),
+                                    1 if nodata else 0, C.c_void_p(dev.stream_ptr(out))), "fsg_synth_dem")
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.load().fsg_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.load().fsg_reset_launch_count()

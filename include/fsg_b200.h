@@ -1,0 +1,176 @@
+/* fsg_b200.h -- C ABI of libfsg_b200.so: B200 (sm_100a) kernels for the per-block
+ * terrain-shading hot path of geoign/FujiShaderGPU v1.0.1.
+ *
+ * Every entry point replaces one CuPy "block function" of the reference (paths below are
+ * relative to FujiShaderGPU/ in the reference tree).  Conventions:
+ *   - plain pointers and sizes only; rasters are row-major float32, NaN = NoData;
+ *     `ld_*` are row strides in ELEMENTS of the respective buffer;
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - the caller owns every buffer (input, output, workspace); the library never calls
+ *     cudaMalloc/cudaFree/cudaDeviceSynchronize, and enqueues all work on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - return value 0 = ok, <0 = error (FSG_E_*); fsg_last_error() gives a thread-local text;
+ *   - re-entrant: no mutable global state (the tile backend calls from up to 6 threads).
+ *   - "None" for an optional double parameter is passed as NaN.
+ *
+ * Row windows: functions taking (H_global, row0, rows) operate on a horizontal band of a
+ * larger raster: `dem` points at global row `buf_row0` and holds `buf_rows` rows; outputs are
+ * produced for global rows [out_row0, out_row0+out_rows) into `out` (whose row 0 is global
+ * row out_row0).  Raster-edge rules (one-sided differences, reflect / edge replicate) are
+ * applied at the GLOBAL edges only, so row-band shards reproduce the single-block result.
+ */
+#ifndef FSG_B200_H
+#define FSG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSG_OK 0
+#define FSG_E_INVALID (-1)   /* bad argument (maps to ValueError on the Python side) */
+#define FSG_E_CUDA (-2)      /* CUDA runtime error, see fsg_last_error() */
+#define FSG_E_WORKSPACE (-3) /* workspace too small */
+#define FSG_E_UNSUPPORTED (-4)
+
+/* output encodings (io/output_encoding.py:130-190, core/dask_processor.py:997-1008) */
+#define FSG_OUT_F32 0
+#define FSG_OUT_I16 1
+#define FSG_OUT_U8 2
+
+/* slope units (algorithms/_impl_slope.py:28-33) */
+#define FSG_SLOPE_DEGREE 0
+#define FSG_SLOPE_PERCENT 1
+#define FSG_SLOPE_RADIAN 2
+
+/* curvature types (algorithms/_impl_curvature.py:34-52) */
+#define FSG_CURV_MEAN 0
+#define FSG_CURV_GAUSSIAN 1
+#define FSG_CURV_PLANFORM 2
+#define FSG_CURV_PROFILE 3
+
+/* Integer encoding applied in the kernel epilogue: DN = clip(rint(f32(a)*v + f32(b)), dn_min,
+ * dn_max), non-finite -> 0.  kind = FSG_OUT_F32 disables it. */
+typedef struct fsg_encode {
+  int32_t kind;
+  int32_t dn_min;
+  int32_t dn_max;
+  int32_t _pad;
+  double a_coef;
+  double b_coef;
+} fsg_encode;
+
+/* Raster window descriptor shared by the stencil entry points. */
+typedef struct fsg_window {
+  int64_t H_global;  /* rows of the whole raster (edge rules)            */
+  int64_t W;         /* columns (always the full width)                  */
+  int64_t buf_row0;  /* global row of dem[0]                             */
+  int64_t buf_rows;  /* rows available in dem                            */
+  int64_t out_row0;  /* first global row to produce                      */
+  int64_t out_rows;  /* number of rows to produce                        */
+  int64_t ld_in;     /* dem row stride (elements)                        */
+  int64_t ld_out;    /* out row stride (elements of the output dtype)    */
+} fsg_window;
+
+const char* fsg_last_error(void);
+int fsg_version(void);
+/* number of kernels this thread has launched through the library since fsg_reset_launch_count */
+int64_t fsg_launch_count(void);
+void fsg_reset_launch_count(void);
+
+/* ---- gradient family -------------------------------------------------------------------
+ * replaces compute_hillshade_block   (algorithms/_impl_hillshade.py:20-54)
+ *          compute_slope_block       (algorithms/_impl_slope.py:19-35)
+ *          compute_curvature_block   (algorithms/_impl_curvature.py:19-57)
+ * incl. handle_nan_for_gradient     (algorithms/_nan_utils.py:50-74): NaN gap fill with the
+ * NaN-aware sigma=1 Gaussian, np.gradient(edge_order=2), NaN restore.  Band halo: 2 rows
+ * (hillshade/slope) or 3 rows (curvature) each side, +4 rows when the band may contain NaN. */
+int fsg_hillshade(const float* dem, void* out, const fsg_window* win,
+                  double azimuth, double altitude, double z_factor,
+                  double pixel_size, double pixel_scale_x, double pixel_scale_y,
+                  const fsg_encode* enc, void* stream);
+int fsg_slope(const float* dem, void* out, const fsg_window* win, int unit,
+              double pixel_size, double pixel_scale_x, double pixel_scale_y,
+              const fsg_encode* enc, void* stream);
+int fsg_curvature(const float* dem, void* out, const fsg_window* win, int curvature_type,
+                  double pixel_size, double pixel_scale_x, double pixel_scale_y,
+                  const fsg_encode* enc, void* stream);
+
+/* ---- topousm_fast -----------------------------------------------------------------------
+ * replaces compute_topousm_fast_efficient_block (algorithms/_impl_topousm_fast.py:49-100)
+ * + apply_global_normalization/topousm_fast_norm_func (algorithms/_global_stats.py:123-153,
+ * _normalization.py:35-41) + the integer encoding, in one pipeline:
+ *   pyramid  : _downsample_nan_aware   (algorithms/_nan_utils.py:604-668)
+ *   coarse   : handle_nan_with_uniform / _gaussian on the decimated grids (:18-47)
+ *   fused    : full-res box means (reflect), align-corners bilinear taps of the coarse means
+ *              (_upsample_to_shape, :671-698), ordered f32 weighted sum, /scale, NaN restore.
+ * radii/weights are the already-resolved lists (host side keeps the reference's scale
+ * construction).  norm_scale <= 0 or NaN: no normalisation (raw block output).
+ * Whole-raster semantics: the block IS the raster [0,H) x [0,W). */
+size_t fsg_topousm_fast_workspace_bytes(int64_t H, int64_t W, const int32_t* radii_host, int n_radii,
+                                        double pixel_size);
+int fsg_topousm_fast(const float* dem, void* out, int64_t H, int64_t W, int64_t ld_in, int64_t ld_out,
+                     const int32_t* radii_host, const float* weights_host, int n_radii,
+                     double pixel_size, double norm_scale, const fsg_encode* enc,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- overview large-radius part (algorithms/_impl_topousm_fast.py:158-186,
+ *      algorithms/_nan_utils.py:255-281): out = f32(w_large)*block - bilinear(field) */
+int fsg_topousm_large_part(const float* block, float* out, int64_t h, int64_t w, int64_t ld_in, int64_t ld_out,
+                           const float* field, int64_t ch, int64_t cw, int64_t ld_field,
+                           int64_t off_r, int64_t off_c, int64_t full_h, int64_t full_w,
+                           double w_large, void* stream);
+
+/* ---- openness (algorithms/_impl_openness.py:31-132) -------------------------------------- */
+int fsg_openness(const float* dem, void* out, const fsg_window* win, int negative,
+                 int num_directions, int max_distance,
+                 double pixel_size, double pixel_scale_x, double pixel_scale_y,
+                 double stretch_lo, double stretch_scale, /* NaN/<=1e-12 scale: no stretch */
+                 const fsg_encode* enc, void* stream);
+
+/* Same kernel with an explicit ray-sample table: samples of azimuth d are
+ * [dir_start[d], dir_start[d+1]); offsets in pixels, dist = f32(max(hypot(ox*|sx|, oy*|sy|), 1e-9)).
+ * The Python host layer builds the table with NumPy exactly as the reference does (:58-68, :96-109). */
+int fsg_openness_samples(const float* dem, void* out, const fsg_window* win, int negative, int num_directions,
+                         const int32_t* dir_start_host, const int32_t* ox_host, const int32_t* oy_host,
+                         const float* dist_host, double stretch_lo, double stretch_scale,
+                         const fsg_encode* enc, void* stream);
+
+/* ---- helpers ------------------------------------------------------------------------------
+ * fsg_decimate      : _downsample_nan_aware incl. enclosed-void fill (needs workspace)
+ * fsg_upsample      : _upsample_to_shape (plain and NaN-aware branch)
+ * fsg_encode_f32    : _quantize_block_cp / quantize_array
+ * fsg_scale_f32     : out = in / f32(scale) with NaN kept (topousm_fast_norm_func)
+ * fsg_stretch_f32   : max((x - lo)/scale, 0)   (tile/dask_bridge.py:173-187)
+ * fsg_order_stats   : exact order statistics for percentile(|x|, 99) (topousm_fast_stat_func,
+ *                     _normalization.py:22-32) and p1/p99 (robust_unsigned_stretch_stat_func) */
+size_t fsg_decimate_workspace_bytes(int64_t H, int64_t W, int factor);
+int fsg_decimate(const float* in, float* out, int64_t H, int64_t W, int64_t ld_in, int factor,
+                 void* workspace, size_t workspace_bytes, void* stream);
+int fsg_upsample(const float* in, float* out, int64_t h, int64_t w, int64_t H, int64_t W,
+                 void* workspace /* >= 256 bytes */, size_t workspace_bytes, void* stream);
+int fsg_encode_f32(const float* in, void* out, int64_t n, const fsg_encode* enc, void* stream);
+int fsg_scale_f32(const float* in, float* out, int64_t n, double scale, void* stream);
+int fsg_stretch_f32(const float* in, float* out, int64_t n, double lo, double scale, void* stream);
+
+size_t fsg_order_stats_workspace_bytes(void);
+/* Pooled order statistics over up to 16 2-D chunks (|x| first when take_abs != 0; samples are the
+ * non-NaN, or with finite_only the finite, values).  rank < 0: count only.  Otherwise exact radix
+ * selection of the rank-th smallest sample.  result_dev (4 doubles): a[rank], a[min(rank+1,n-1)],
+ * rank used, n.  NumPy computes the percentile's virtual index in f32 for f32 input, so the host
+ * layer derives `rank` and interpolates with NumPy scalars (kernels.percentile). */
+int fsg_order_stats(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                    const int64_t* ld_host, int n_chunks, int64_t rank, int take_abs, int finite_only,
+                    double* result_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+/* synthetic DEM generator used by bench/tests: eight sinusoid octaves +
+ * hash noise, optional NoData wedge/ellipses; rows [row0,row0+rows) of an H x W raster. */
+int fsg_synth_dem(float* out, int64_t H, int64_t W, int64_t row0, int64_t rows, int64_t ld,
+                  uint64_t seed, int nodata, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSG_B200_H */

@@ -1,0 +1,226 @@
+"""Parity of the CUDA path (through the C ABI / reference-shaped Python API) against
+(1) outputs of the unmodified reference (tests/golden) and (2) the CPU oracle on seeded inputs.
+
+Bar: float32 within 1e-5 relative / 1e-6 absolute (on the normalised scale for topousm_fast),
+identical NoData masks; uint8/int16 within +-1 DN."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from conftest import assert_close_f32  # noqa: E402
+from oracle import terrain_oracle as orc  # noqa: E402
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _curvature_close(got, want, name):
+    """Curvature display value ((tanh(100k)+1)/2)^(1/2.2) is ill-conditioned where tanh saturates at
+    -1 (output < 0.05): one ulp of tanhf there moves the result by up to ~1e-4.  The reference itself
+    evaluates tanhf with the CUDA math library, NumPy with its own SIMD routine (1-ulp apart)."""
+    assert np.array_equal(np.isnan(got), np.isnan(want)), name
+    ok = ~np.isnan(want)
+    g, w = got[ok].astype(np.float64), want[ok].astype(np.float64)
+    well = w >= 0.05
+    err = np.abs(g - w)
+    assert np.all(err[well] <= 1e-6 + 1e-5 * np.abs(w[well])), (name, err[well].max())
+    assert np.all(err[~well] <= 2e-4), (name, err[~well].max() if (~well).any() else 0)
+
+
+def test_gradient_family_vs_reference_golden(golden, manifest):
+    from fujishadergpu_b200.algorithms._impl_hillshade import compute_hillshade_block
+    from fujishadergpu_b200.algorithms._impl_slope import compute_slope_block
+    from fujishadergpu_b200.algorithms._impl_curvature import compute_curvature_block
+    g = golden("gradient_family")
+    for name, meta in manifest["gradient_family"].items():
+        dem = _cuda(g[meta["input"]])
+        algo = name.split("__")[0]
+        if algo == "hillshade":
+            assert_close_f32(_np(compute_hillshade_block(dem, **meta["kw"])), g[name], what=name)
+        elif algo.startswith("slope"):
+            assert_close_f32(_np(compute_slope_block(dem, **meta["kw"])), g[name], what=name)
+        else:
+            _curvature_close(_np(compute_curvature_block(dem, **meta["kw"])), g[name], name)
+
+
+def test_gradient_family_large_vs_oracle():
+    from fujishadergpu_b200 import kernels as k
+    dem = orc.synth_dem(1500, 1111, seed=11, nodata=True)
+    d = _cuda(dem)
+    kw = dict(pixel_scale_x=1.0, pixel_scale_y=-1.0)
+    assert_close_f32(_np(k.hillshade(d, **kw)), orc.hillshade_block(dem, **kw), what="hillshade")
+    for unit in ("degree", "percent", "radian"):
+        assert_close_f32(_np(k.slope(d, unit=unit, **kw)), orc.slope_block(dem, unit=unit, **kw), what=unit)
+    for ct in ("mean", "gaussian", "planform", "profile"):
+        _curvature_close(_np(k.curvature(d, curvature_type=ct, **kw)), orc.curvature_block(dem, curvature_type=ct, **kw), ct)
+
+
+def test_gradient_small_raster_raises_like_numpy():
+    from fujishadergpu_b200 import kernels as k
+    with pytest.raises(ValueError):
+        k.hillshade(torch.zeros((2, 5), device="cuda"))
+
+
+def test_gradient_encoded_outputs():
+    from fujishadergpu_b200 import kernels as k
+    from fujishadergpu_b200.io.output_encoding import quantize_params, resolve_output_range
+    dem = orc.synth_dem(300, 260, seed=3, nodata=True)
+    d = _cuda(dem)
+    for algo, fn, ofn in (("hillshade", k.hillshade, orc.hillshade_block), ("slope", k.slope, orc.slope_block)):
+        for dt in ("uint8", "int16"):
+            qp = quantize_params(*resolve_output_range(algo), dt)
+            got = _np(fn(d, output_dtype=dt, qp=qp)).astype(np.int64)
+            want = orc.encode_array(ofn(dem), qp, dt).astype(np.int64)
+            assert np.array_equal(got == 0, want == 0), (algo, dt)      # identical NoData mask
+            assert np.abs(got - want).max() <= 1, (algo, dt)
+
+
+def _topo_close(got, want, scale, what):
+    assert np.array_equal(np.isnan(got), np.isnan(want)), what
+    ok = ~np.isnan(want)
+    err = np.abs(got[ok].astype(np.float64) - want[ok].astype(np.float64))
+    lim = 1e-6 * scale + 1e-5 * np.abs(want[ok].astype(np.float64))
+    assert np.all(err <= lim), (what, float(err.max()), float(scale), int((err > lim).sum()))
+    return float(np.mean(got[ok] == want[ok]))
+
+
+def test_topousm_fast_vs_reference_golden(golden, manifest):
+    from fujishadergpu_b200.algorithms._impl_topousm_fast import compute_topousm_fast_efficient_block
+    from fujishadergpu_b200 import kernels as k
+    g = golden("topousm_fast")
+    for cname, meta in manifest["topousm_fast"].items():
+        if cname == "large_part":
+            continue
+        dem = _cuda(g[meta["input"]])
+        raw = _np(compute_topousm_fast_efficient_block(dem, **meta["kw"]))
+        exact = _topo_close(raw, g[f"raw__{cname}"], meta["scale"], cname)
+        print(f"{cname}: bit-exact fraction {exact:.5f}")
+        if f"norm__{cname}" in g:
+            kw = dict(meta["kw"])
+            norm = _np(k.topousm_fast(dem, radii=kw.get("radii", [4, 16, 64]), weights=kw.get("weights"),
+                                      pixel_size=kw.get("pixel_size", 1.0), norm_scale=meta["scale"]))
+            assert_close_f32(norm, g[f"norm__{cname}"], what="norm " + cname)
+
+
+def test_topousm_helpers_vs_reference_golden(golden, manifest):
+    from fujishadergpu_b200 import kernels as k
+    g = golden("topousm_fast")
+    for key in ("tdense", "tholes", "tvoid"):
+        for f in (2, 4, 16):
+            got = _np(k.decimate(_cuda(g[key]), f))
+            assert_close_f32(got, g[f"decimate{f}__{key}"], rtol=1e-6, atol=0, what=f"decimate{f} {key}")
+    small = _cuda(g["decimate4__tdense"])
+    assert np.array_equal(_np(k.upsample(small, g["tdense"].shape)), g["upsample4__tdense"])
+    m = manifest["topousm_fast"]["large_part"]
+    r0, r1, c0, c1 = m["window"]
+    part = _np(k.topousm_large_part(_cuda(g["tdense"][r0:r1, c0:c1]), _cuda(g["large_field"]), w_large=m["w_large"],
+                                    off_r=r0, off_c=c0, full_h=g["tdense"].shape[0], full_w=g["tdense"].shape[1]))
+    assert_close_f32(part, g["large_part"], what="large_part")
+
+
+def test_topousm_fast_large_vs_oracle():
+    """2048 x 1792 with the full ladder (every pyramid level, several strips/bands, ragged edges)."""
+    from fujishadergpu_b200 import kernels as k
+    for nodata in (False, True):
+        dem = orc.synth_dem(2051, 1797, seed=21 + nodata, nodata=nodata)
+        radii, w = [2, 8, 32, 128, 512, 2048], orc.pow2_weights(6)
+        want = orc.topousm_fast_block(dem, radii=radii, weights=w)
+        scale = orc.abs_p99_scale(want)[0]
+        got = _np(k.topousm_fast(_cuda(dem), radii=radii, weights=w))
+        exact = _topo_close(got, want, scale, f"ladder6 nodata={nodata}")
+        print(f"nodata={nodata}: bit-exact fraction {exact:.6f}, scale {scale:.4f}")
+        qp = orc.encode_params(*orc.value_range("topousm_fast"), "uint8")
+        got8 = _np(k.topousm_fast(_cuda(dem), radii=radii, weights=w, norm_scale=scale, output_dtype="uint8", qp=qp))
+        want8 = orc.encode_array(orc.normalise_by_scale(want.copy(), (scale,)), qp, "uint8")
+        assert np.array_equal(got8 == 0, want8 == 0)
+        assert np.abs(got8.astype(int) - want8.astype(int)).max() <= 1
+
+
+def test_topousm_weights_length_mismatch_raises():
+    from fujishadergpu_b200.algorithms._impl_topousm_fast import compute_topousm_fast_efficient_block
+    with pytest.raises(ValueError):
+        compute_topousm_fast_efficient_block(torch.zeros((64, 64), device="cuda"), radii=[2, 8], weights=[1.0])
+
+
+def test_stats_percentile_matches_numpy():
+    from fujishadergpu_b200.algorithms._normalization import topousm_fast_stat_func
+    from fujishadergpu_b200.algorithms._global_stats import robust_unsigned_stretch_stat_func
+    rng = np.random.default_rng(4)
+    a = (rng.standard_normal((700, 900)) * 3).astype(np.float32)
+    a[rng.random(a.shape) < 0.05] = np.nan
+    assert topousm_fast_stat_func(_cuda(a))[0] == orc.abs_p99_scale(a)[0]
+    b = rng.random((500, 333)).astype(np.float32)
+    b[::7, ::5] = np.nan
+    assert robust_unsigned_stretch_stat_func(_cuda(b)) == orc.p1_p99_stretch_stats(b)
+    # pooled chunks (the stratified-window pre-pass)
+    parts = [a[:300, :400], a[350:, 100:], a[100:200, :]]
+    pooled = np.concatenate([p[~np.isnan(p)] for p in parts])
+    assert topousm_fast_stat_func([_cuda(p) for p in parts])[0] == orc.abs_p99_scale(pooled)[0]
+    # reference known answers (tests/test_topousm_fast_normalization.py:21-33)
+    data = np.concatenate([np.full(800, 0.01, np.float32), np.full(200, 0.5, np.float32)])
+    assert topousm_fast_stat_func(_cuda(data))[0] == pytest.approx(0.5, rel=1e-2)
+
+
+def test_openness_vs_reference_golden(golden, manifest):
+    from fujishadergpu_b200.algorithms._impl_openness import compute_openness_vectorized, compute_openness_spatial_block
+    from fujishadergpu_b200.algorithms._global_stats import _apply_display_stretch_block
+    g = golden("openness")
+    for name, meta in manifest["openness"].items():
+        if name == "stretch":
+            continue
+        fn = compute_openness_vectorized if name.startswith("local__") else compute_openness_spatial_block
+        got = _np(fn(_cuda(g[meta["input"]]), **meta["kw"]))
+        assert_close_f32(got, g[name], what=name)
+    st = manifest["openness"]["stretch"]
+    got = _np(_apply_display_stretch_block(_cuda(g[st["of"]]), tuple(st["stats"])))
+    assert_close_f32(got, g["stretch__pos8_r64"], what="stretch")
+
+
+def test_openness_known_answers():
+    """tests/test_openness_yokoyama.py:21-47 of the reference, on the CUDA path."""
+    from fujishadergpu_b200.algorithms._impl_openness import compute_openness_vectorized as op
+    yy, xx = np.mgrid[0:101, 0:101]
+    r = np.sqrt((xx - 50) ** 2 + (yy - 50) ** 2)
+    peak, pit = _cuda((50 - r).astype(np.float32)), _cuda((r - 50).astype(np.float32))
+    kw = dict(num_directions=16, max_distance=40)
+    assert op(peak, openness_type="positive", **kw)[50, 50] > op(pit, openness_type="positive", **kw)[50, 50]
+    assert op(pit, openness_type="negative", **kw)[50, 50] > op(peak, openness_type="negative", **kw)[50, 50]
+    flat = torch.zeros((101, 101), device="cuda")
+    for t in ("positive", "negative"):
+        assert float(op(flat, openness_type=t, **kw)[50, 50]) == pytest.approx(1.0, abs=1e-3)
+
+
+def test_tile_adapter_matches_reference(golden, manifest):
+    from fujishadergpu_b200.algorithms.tile.topousm_fast import TopoUSMFastAlgorithm
+    from fujishadergpu_b200.core.tile_compute import run_tile_algorithm
+    meta = manifest["tile_adapter"]["topousm_fast_gs7p25"]
+    dem = _cuda(golden("topousm_fast")["tdense"])
+    kw = dict(meta["kw"])
+    kw["global_stats"] = tuple(kw["global_stats"])
+    got = _np(TopoUSMFastAlgorithm().process(dem, **kw))
+    assert_close_f32(got, golden("tile_adapter")["topousm_fast_gs7p25"], what="tile adapter")
+    got2 = _np(run_tile_algorithm(TopoUSMFastAlgorithm(), "topousm_fast", dem, 1.0, False, 1.0,
+                                  {"radii": [2, 8, 32, 128], "global_stats": (7.25,)}))
+    assert np.array_equal(got, got2)
+
+
+def test_encode_known_vector():
+    """tests/test_audit_p1_regressions.py:45-62 of the reference."""
+    from fujishadergpu_b200.io.output_encoding import quantize_array, quantize_params
+    v = _cuda(np.array([np.inf, -np.inf, np.nan, 1.0], np.float32))
+    assert _np(quantize_array(v, quantize_params(0.0, 1.0, "uint8"), "uint8")).tolist() == [0, 0, 0, 255]
+    assert _np(quantize_array(v, quantize_params(0.0, 100.0, "int16"), "int16")).tolist()[:3] == [0, 0, 0]
+
+
+def test_library_is_the_path_that_ran():
+    from fujishadergpu_b200 import kernels as k
+    k.reset_launch_count()
+    k.hillshade(torch.zeros((64, 64), device="cuda"))
+    assert k.launch_count() >= 1

@@ -1,0 +1,141 @@
+"""CPU-side checks: host logic mirrors the reference tables; the C-ABI library loads and exports
+every symbol include/fsg_b200.h declares (no compute without a GPU)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import terrain_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    from fujishadergpu_b200.build import build_library
+    from fujishadergpu_b200 import _lib
+    build_library()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "fsg_b200.h")).read()
+    declared = set(re.findall(r"\b(fsg_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/fsg_b200.h but not exported"
+    assert declared == set(_lib.exported_symbols())
+    assert lib.fsg_version() >= 100
+
+
+def test_product_has_no_oracle_or_cpu_fallback():
+    """The product package must not import the oracle (or scipy filters) anywhere."""
+    pkg = os.path.join(ROOT, "fujishadergpu_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f
+                assert "scipy" not in src, f
+
+
+def test_missing_gpu_fails_loudly():
+    torch = pytest.importorskip("torch")
+    from fujishadergpu_b200.algorithms._impl_hillshade import compute_hillshade_block
+    with pytest.raises(TypeError):
+        compute_hillshade_block(np.zeros((8, 8), np.float32))
+    if not torch.cuda.is_available():
+        with pytest.raises(TypeError):
+            compute_hillshade_block(torch.zeros((8, 8)))
+
+
+def test_scale_construction_matches_reference(manifest):
+    from fujishadergpu_b200.algorithms.common import spatial_mode as sm
+    t = manifest["tables"]
+    for s, want in t["auto_radii"].items():
+        assert sm.auto_spatial_radii(int(s)) == want
+    assert sm.auto_spatial_radii(None) == t["auto_radii_none"]
+    for n, want in t["auto_weights"].items():
+        assert sm.auto_spatial_weights(int(n)) == want
+    assert sm.LOCAL_RADII == [1] and sm.LOCAL_WEIGHTS == [1.0]
+    assert sm.MULTISCALE_REQUIRED_ALGOS.isdisjoint(sm.RADII_DRIVEN_ALGOS)
+    assert max(sm.auto_spatial_radii(10 ** 9)) == sm.AUTO_RADIUS_MAX == max(sm.AUTO_RADII_SEQUENCE)
+    r, w = sm.auto_spatial_profile(10000, radii=[4, 16, 64, 256])
+    assert r == [4, 16, 64, 256] and w == pytest.approx([8 / 15, 4 / 15, 2 / 15, 1 / 15])
+
+
+def test_decimation_factor_matches_reference(manifest):
+    from fujishadergpu_b200.algorithms._nan_utils import _radius_to_downsample_factor as ds
+    t = manifest["tables"]
+    for r, want in t["ds_topousm_px1"].items():
+        assert ds(float(r), pixel_size=1.0, algorithm_name="topousm_fast") == want
+        # shape independence (tests/test_audit_p2_regressions.py:12-20 of the reference)
+        assert ds(float(r), block_shape=(17, 9001), pixel_size=1.0, algorithm_name="topousm_fast") == want
+    for r, want in t["ds_openness_px1"].items():
+        assert ds(float(r), pixel_size=1.0, algorithm_name="openness") == want
+    for r, want in t["ds_topousm_px0p5"].items():
+        assert ds(float(r), pixel_size=0.5, algorithm_name="topousm_fast") == want
+
+
+def test_quantize_params_match_reference(manifest):
+    from fujishadergpu_b200.io.output_encoding import quantize_params, resolve_output_range
+    for key, want in manifest["tables"]["quant"].items():
+        algo, dt = key.split(":")
+        assert quantize_params(*resolve_output_range(algo), dt) == want
+    assert resolve_output_range("slope", params={"unit": "percent"}) is None
+    assert resolve_output_range("slope", params={"unit": "radian"}) == (0.0, float(np.pi / 2))
+    with pytest.raises(ValueError):
+        resolve_output_range("slope", override=(1.0, 1.0))
+
+
+def test_tile_radii_normalisation_matches_reference(manifest):
+    from fujishadergpu_b200.core.tile_compute import _normalize_topousm_fast_radii_and_weights as norm
+    t = manifest["tables"]["tile_radii"]
+    assert list(norm(None, None, 1.0, manual_radii=[2, 8.4, 8, 0.2, 32], manual_weights=[1, 2, 3, 4, 5])) == t["dup"]
+    assert list(norm(None, None, 1.0, manual_radii=[2, 8, 32])) == t["noweights"]
+
+
+def test_radii_weight_resolution():
+    from fujishadergpu_b200.algorithms._nan_utils import _resolve_spatial_radii_weights as res
+    assert res(None, None, 1.0, short_side_px=5000)[0] == [2, 8, 32, 128]
+    rr, ww = res([4, 4.2, 16, -3], [3, 1], 1.0)
+    assert rr == [4, 16] and ww == [0.75, 0.25]
+    rr, ww = res([4, 16], [0, -1], 1.0)
+    assert ww == pytest.approx([2 / 3, 1 / 3])
+
+
+def test_registry_names_and_unaccelerated_error():
+    from fujishadergpu_b200.algorithms.dask_registry import ALGORITHMS, UNACCELERATED, get_algorithm
+    assert set(ALGORITHMS) == {"topousm_fast", "hillshade", "slope", "curvature", "openness"}
+    assert len(UNACCELERATED) == 16
+    with pytest.raises(NotImplementedError):
+        get_algorithm("frangi")
+    with pytest.raises(KeyError):
+        get_algorithm("nope")
+    assert ALGORITHMS["topousm_fast"].get_default_params()["mode"] == "radius"
+
+
+def test_openness_sample_table_matches_oracle():
+    from fujishadergpu_b200.kernels import openness_table
+    for nd, md in ((8, 256), (16, 50), (12, 25), (8, 5), (16, 1)):
+        start, ox, oy, dist = openness_table(nd, md, 1.0, 23.7, -30.9)
+        offs, D = orc.openness_offsets(nd, md)
+        assert [(d, x, y) for d, x, y in offs] == [
+            (d, int(ox[k]), int(oy[k])) for d in range(nd) for k in range(start[d], start[d + 1])]
+
+
+def test_percentile_host_arithmetic_equals_numpy():
+    """kernels.percentile() derives the rank and interpolates with NumPy f32 scalars; emulate the
+    device selection with a sort and require equality with np.percentile on the whole f32 sample."""
+    rng = np.random.default_rng(9)
+    for n in (1, 2, 3, 101, 4096, 100003):
+        a = (rng.standard_normal(n) * 7).astype(np.float32)
+        s = np.sort(a)
+        for q in (1.0, 50.0, 99.0):
+            q32 = np.true_divide(q, np.float32(100))
+            vi = (n - 1) * q32
+            prev = min(max(int(np.floor(vi)), 0), n - 1)
+            gamma = np.asanyarray(vi - np.floor(vi), dtype=np.asanyarray(vi).dtype)[()]
+            lo, hi = s[prev], s[min(prev + 1, n - 1)]
+            d = hi - lo
+            out = lo + d * gamma
+            if gamma >= 0.5:
+                out = hi - d * (1 - gamma)
+            assert float(out) == float(np.percentile(a, q)), (n, q)
