@@ -22,16 +22,20 @@ def _np(t):
 
 
 def _curvature_close(got, want, name):
-    """Curvature display value ((tanh(100k)+1)/2)^(1/2.2) is ill-conditioned where tanh saturates at
-    -1 (output < 0.05): one ulp of tanhf there moves the result by up to ~1e-4.  The reference itself
-    evaluates tanhf with the CUDA math library, NumPy with its own SIMD routine (1-ulp apart)."""
+    """Curvature display value ((tanh(100k)+1)/2)^(1/2.2).  Where tanh saturates at -1 (output < 0.05)
+    the f32 spacing of tanh (2^-24) alone moves the output by (2^-25)^(1/2.2) = 3.8e-4 per ulp, and the
+    reference itself evaluates tanhf with the CUDA math library (<= 2 ulp) while the NumPy oracle uses
+    its own routine (<= 1 ulp).  There the comparison is made before the gamma: |(t+1)/2| within 4 ulp
+    of tanh.  Everywhere else the standard bar applies."""
     assert np.array_equal(np.isnan(got), np.isnan(want)), name
     ok = ~np.isnan(want)
     g, w = got[ok].astype(np.float64), want[ok].astype(np.float64)
     well = w >= 0.05
     err = np.abs(g - w)
     assert np.all(err[well] <= 1e-6 + 1e-5 * np.abs(w[well])), (name, err[well].max())
-    assert np.all(err[~well] <= 2e-4), (name, err[~well].max() if (~well).any() else 0)
+    if (~well).any():
+        pre = np.abs(g[~well] ** 2.2 - w[~well] ** 2.2)
+        assert np.all(pre <= 4 * 2.0 ** -25 + 1e-5 * w[~well] ** 2.2), (name, pre.max())
 
 
 def test_gradient_family_vs_reference_golden(golden, manifest):
