@@ -35,6 +35,8 @@ _SIGNATURES = {
     "fsg_version": (_I, []),
     "fsg_launch_count": (_L, []),
     "fsg_reset_launch_count": (None, []),
+    "fsg_profile_enable": (None, [_I]),
+    "fsg_profile_read": (_I, [C.POINTER(C.c_int), C.POINTER(C.c_float), _I]),
     "fsg_hillshade": (_I, [_P, _P, C.POINTER(Window), _D, _D, _D, _D, _D, _D, C.POINTER(Encode), _P]),
     "fsg_slope": (_I, [_P, _P, C.POINTER(Window), _I, _D, _D, _D, C.POINTER(Encode), _P]),
     "fsg_curvature": (_I, [_P, _P, C.POINTER(Window), _I, _D, _D, _D, C.POINTER(Encode), _P]),

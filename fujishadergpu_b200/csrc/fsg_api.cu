@@ -30,9 +30,55 @@ int gauss_half_taps(double sigma, double* w, int max_radius) {
   return r;
 }
 
+// ---- optional per-thread kernel timing (bench.py's roofline measurement) -------------------
+// When enabled, instrumented call sites bracket their dominant kernel with CUDA events recorded on
+// the launch stream; fsg_profile_read() synchronises the events and returns the durations.
+constexpr int PROF_MAX = 256;
+struct ProfState {
+  int enabled = 0;
+  int n = 0;
+  cudaEvent_t ev[2 * PROF_MAX] = {};
+  int tag[PROF_MAX] = {};
+};
+static thread_local ProfState g_prof;
+
+int prof_begin(int tag, cudaStream_t s) {
+  ProfState& p = g_prof;
+  if (!p.enabled || p.n >= PROF_MAX) return -1;
+  int i = p.n;
+  for (int k = 0; k < 2; ++k)
+    if (!p.ev[2 * i + k] && cudaEventCreate(&p.ev[2 * i + k]) != cudaSuccess) return -1;
+  p.tag[i] = tag;
+  cudaEventRecord(p.ev[2 * i], s);
+  return i;
+}
+void prof_end(int slot, cudaStream_t s) {
+  if (slot < 0) return;
+  cudaEventRecord(g_prof.ev[2 * slot + 1], s);
+  g_prof.n = slot + 1;
+}
+
 }  // namespace fsg
 
 extern "C" {
+
+void fsg_profile_enable(int on) { fsg::g_prof.enabled = on; fsg::g_prof.n = 0; }
+
+// Writes up to `max` (tag, milliseconds) pairs; returns the number of records; resets the list.
+int fsg_profile_read(int* tags, float* ms, int max) {
+  fsg::ProfState& p = fsg::g_prof;
+  int n = p.n < max ? p.n : max;
+  for (int i = 0; i < n; ++i) {
+    cudaEventSynchronize(p.ev[2 * i + 1]);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, p.ev[2 * i], p.ev[2 * i + 1]);
+    tags[i] = p.tag[i];
+    ms[i] = t;
+  }
+  p.n = 0;
+  return n;
+}
+
 
 const char* fsg_last_error(void) { return fsg::last_error_buf(); }
 int fsg_version(void) { return 100; }

@@ -17,6 +17,9 @@ namespace fsg {
 char* last_error_buf();
 void count_launch(int n = 1);
 int fail(int code, const char* fmt, ...);
+int prof_begin(int tag, cudaStream_t s);   // returns a slot (or -1 when profiling is off)
+void prof_end(int slot, cudaStream_t s);
+enum { PROF_TOPOUSM_FUSED = 1, PROF_TOPOUSM_PYRAMID = 2, PROF_TOPOUSM_COARSE = 3, PROF_GRADIENT = 4, PROF_OPENNESS = 5 };
 
 #define FSG_CUDA_OK(expr)                                                              \
   do {                                                                                 \

@@ -235,9 +235,11 @@ static int run_grad(int cls, const float* dem, void* out, const fsg_window* win,
   if (p.out_rows == 0) return FSG_OK;
   dim3 grid((unsigned)((p.W + GT_W - 1) / GT_W), (unsigned)((p.out_rows + GT_H - 1) / GT_H));
   cudaStream_t s = (cudaStream_t)stream;
+  int slot = prof_begin(PROF_GRADIENT, s);
   if (cls == 0) grad_kernel<0><<<grid, G_THREADS, 0, s>>>(p);
   else if (cls == 1) grad_kernel<1><<<grid, G_THREADS, 0, s>>>(p);
   else grad_kernel<2><<<grid, G_THREADS, 0, s>>>(p);
+  prof_end(slot, s);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }

@@ -107,7 +107,9 @@ static int run_openness(const float* dem, void* out, const fsg_window* win, int 
   p.enc = make_encode(enc);
   if (p.out_rows == 0) return FSG_OK;
   dim3 grid((unsigned)((p.W + 63) / 64), (unsigned)((p.out_rows + 3) / 4));
+  int slot = prof_begin(PROF_OPENNESS, (cudaStream_t)stream);
   openness_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, tab);
+  prof_end(slot, (cudaStream_t)stream);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }

@@ -310,7 +310,6 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
   float* ring = reinterpret_cast<float*>(smraw);                 // NRING x SWp
   float* vplane = ring + (size_t)NRING * SWp;                    // FK_NB x SWp  (also output staging)
   unsigned char* cplane = reinterpret_cast<unsigned char*>(vplane + (size_t)FK_NB * SWp);  // FK_NB x SWp
-  __shared__ int s_nan;
 
   const int tid = threadIdx.x;
   const int64_t x0 = (int64_t)blockIdx.x * FK_TW;       // first output column of the strip
@@ -595,7 +594,9 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
       pp.gh[k] = plan.levels[k].h;
     }
     dim3 grid((unsigned)((W + PY_COLS - 1) / PY_COLS), (unsigned)((H + PY_ROWS - 1) / PY_ROWS));
+    int pslot = prof_begin(PROF_TOPOUSM_PYRAMID, s);
     pyramid_kernel<<<grid, 256, 0, s>>>(pp);
+    prof_end(pslot, s);
     FSG_LAUNCH_OK();
     // enclosed-void fill (runs only when the level has an all-NaN cell; device-side flag)
     for (int k = 0; k < plan.n_levels; ++k) {
@@ -654,7 +655,9 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
   size_t smem = fused_smem_bytes(plan.fused_R);
   FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)strips, (unsigned)bands);
+  int slot = prof_begin(PROF_TOPOUSM_FUSED, s);
   fused_kernel<<<grid, FK_THREADS, smem, s>>>(fp);
+  prof_end(slot, s);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }

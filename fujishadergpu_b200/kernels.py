@@ -304,3 +304,15 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     _lib.load().fsg_reset_launch_count()
+
+
+def profile_enable(on: bool) -> None:
+    _lib.load().fsg_profile_enable(1 if on else 0)
+
+
+def profile_read(max_records: int = 256):
+    """[(tag, milliseconds), ...] of the instrumented kernels launched by this thread since the last read."""
+    tags = (C.c_int * max_records)()
+    ms = (C.c_float * max_records)()
+    n = _lib.load().fsg_profile_read(tags, ms, max_records)
+    return [(int(tags[i]), float(ms[i])) for i in range(n)]

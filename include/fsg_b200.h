@@ -79,6 +79,10 @@ int fsg_version(void);
 /* number of kernels this thread has launched through the library since fsg_reset_launch_count */
 int64_t fsg_launch_count(void);
 void fsg_reset_launch_count(void);
+/* Optional per-thread timing of the dominant kernels (CUDA events on the launch stream); used by
+ * bench.py for the roofline figure.  tags: 1 topousm fused, 2 pyramid, 4 gradient, 5 openness. */
+void fsg_profile_enable(int on);
+int fsg_profile_read(int* tags, float* ms, int max);
 
 /* ---- gradient family -------------------------------------------------------------------
  * replaces compute_hillshade_block   (algorithms/_impl_hillshade.py:20-54)
