@@ -18,6 +18,8 @@
 //                       coarse means are sampled with scipy's zoom arithmetic; terms are combined
 //                       in list order in f32; normalise; NaN restore; optional u8/i16 encoding.
 //      Algorithmic traffic: 4 B/px read + 4 B/px (f32) or 1 B/px (u8) written.
+#include <stdlib.h>
+
 #include "fsg_filters.cuh"
 
 namespace fsg {
@@ -543,13 +545,302 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// 3b. fast variant of the fused kernel (rasters with H, W >= R + 2: a single mirror reflection is
+//     enough at the edges).  Same arithmetic as fused_kernel, but: 32-bit ring addressing through a
+//     per-batch row-slot table (no integer division in the hot loops), running-window state in
+//     registers (statically indexed), column reflection only in edge strips, and the coarse terms
+//     evaluated as one f64 FMA between row-interpolated neighbours.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect1(int64_t i, int64_t n) {  // one mirror, valid for -n <= i < 2n
+  return (int)(i < 0 ? -1 - i : (i >= n ? 2 * n - 1 - i : i));
+}
+
+template <bool EDGE>
+__device__ __forceinline__ int col_slot(int j, int x0, int cs0, int W) {  // strip slot of output column j (+-r)
+  if (!EDGE) return j - (cs0 - x0);
+  int64_t gx = (int64_t)x0 + j;
+  if (gx < 0 || gx >= W) gx = reflect1(gx, W);
+  return (int)(gx - cs0);
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void hphase_box(const float* __restrict__ vrow, const unsigned char* __restrict__ crow,
+                                           const float* __restrict__ xrow, int R, int r, int hj0, int hjn, int x0,
+                                           int cs0, int W, bool nanmode, float weight, bool first, float* acc) {
+  const double inv = 1.0 / (double)(2 * r + 1);
+  const double n = (double)(2 * r + 1);
+  const float nf32 = (float)(2 * r + 1);
+  double sv = 0.0, sw = 0.0;
+  for (int d = -r; d <= r; ++d) {
+    int sidx = col_slot<EDGE>(hj0 + d, x0, cs0, W);
+    sv += (double)vrow[sidx];
+    if (nanmode) sw += (double)((float)crow[sidx] / nf32);
+  }
+#pragma unroll
+  for (int jj = 0; jj < FK_SEG; ++jj) {
+    if (jj < hjn) {
+      const int j = hj0 + jj;
+      float mean;
+      if (nanmode) {
+        mean = (float)div_by_count(sv, n, inv);
+        float den = (float)div_by_count(sw, n, inv);
+        mean = den > 0.f ? mean / den : 0.f;
+      } else {
+        mean = (float)(sv * inv);  // see DESIGN.md: the rounded product already rounds like the exact quotient
+      }
+      float term = weight * (xrow[R + j] - mean);
+      acc[jj] = first ? term : acc[jj] + term;
+      if (jj + 1 < hjn) {
+        int sin_ = col_slot<EDGE>(j + r + 1, x0, cs0, W), sout = col_slot<EDGE>(j - r, x0, cs0, W);
+        sv += (double)vrow[sin_] - (double)vrow[sout];
+        if (nanmode) sw += (double)((float)crow[sin_] / nf32) - (double)((float)crow[sout] / nf32);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int R = p.R;
+  const int SW = FK_TW + 2 * R;
+  const int SWp = SW | 1;
+  const int NRING = FK_NB + 2 * R + 1;
+  float* ring = reinterpret_cast<float*>(smraw);
+  float* vplane = ring + (size_t)NRING * SWp;
+  unsigned char* cplane = reinterpret_cast<unsigned char*>(vplane + (size_t)FK_NB * SWp);
+  int* slot_tab = reinterpret_cast<int*>(cplane + (((size_t)FK_NB * SWp + 15) / 16) * 16);  // NRING+1 row offsets
+
+  const int tid = threadIdx.x;
+  const int W = (int)p.W;
+  const int64_t H = p.H;
+  const int x0 = blockIdx.x * FK_TW;
+  const int cs0 = x0 - R;
+  const int64_t yb0 = (int64_t)blockIdx.y * p.band_rows;
+  const int64_t yb1 = (yb0 + p.band_rows < H) ? yb0 + p.band_rows : H;
+  const bool edge_strip = (cs0 < 0) || (cs0 + SW > W);
+
+  const int vc = tid;
+  const int vgx = cs0 + vc;
+  const bool vcol_ok = vc < SW && vgx >= 0 && vgx < W;
+
+  double rs[FK_MAXF];
+  int rc[FK_MAXF];
+#pragma unroll
+  for (int k = 0; k < FK_MAXF; ++k) { rs[k] = 0.0; rc[k] = 0; }
+
+  const int hi = tid % FK_NB;
+  const int hg = tid / FK_NB;
+  const int hj0 = hg * FK_SEG;
+  int hjn = (hj0 + FK_SEG <= FK_TW) ? FK_SEG : (FK_TW - hj0 > 0 ? FK_TW - hj0 : 0);
+  if (x0 + hj0 + hjn > W) hjn = (W - x0 - hj0 > 0) ? (W - x0 - hj0) : 0;
+
+  unsigned nan_hist = 0;
+  int64_t loaded_hi = -1;
+  int base = 0;  // ring slot of row y
+
+  for (int64_t y = yb0; y < yb1; y += FK_NB) {
+    const int64_t need_lo = y - R < 0 ? 0 : y - R;
+    const int64_t need_hi = y + FK_NB + R >= H ? H - 1 : y + FK_NB + R;
+    const int64_t from = (y == yb0) ? need_lo : loaded_hi + 1;
+    if (y == yb0) base = (int)(y - need_lo); else { base += FK_NB; if (base >= NRING) base -= NRING; }
+    __syncthreads();
+    // slot table: entry (d + R + 1) = SWp * ring slot of (reflected) row y + d, d in [-R-1, NB+R]
+    for (int e = tid; e <= NRING; e += FK_THREADS) {
+      int d = e - R - 1;
+      int dd = reflect1(y + d, H) - (int)y;     // y is < 2^31 rows from the reflected row
+      int sl = (base + dd) % NRING;            // once per batch and table entry, not per pixel
+      if (sl < 0) sl += NRING;
+      slot_tab[e] = sl * SWp;
+    }
+    int my_nan = 0;
+    {
+      const int nrows = (int)(need_hi - from + 1);
+      const int c_lo = cs0 < 0 ? -cs0 : 0;
+      const int c_hi = (cs0 + SW > W) ? W - cs0 : SW;   // exclusive
+      for (int rr = 0; rr < nrows; ++rr) {
+        const int64_t row = from + rr;
+        int sl = base + (int)(row - y);
+        if (sl >= NRING) sl -= NRING;
+        if (sl < 0) sl += NRING;
+        const float* src = p.dem + row * p.ld_in + cs0;
+        float* dst = ring + (size_t)sl * SWp;
+        for (int c = c_lo + tid; c < c_hi; c += FK_THREADS) {
+          float v = __ldg(src + c);
+          my_nan |= (v != v);
+          dst[c] = v;
+        }
+      }
+    }
+    loaded_hi = need_hi;
+    const int any = __syncthreads_or(my_nan);
+    nan_hist = (y == yb0) ? (any ? 0x3fu : 0u) : ((nan_hist << 1) | (any ? 1u : 0u));
+    const bool nanmode = (nan_hist & 0x3fu) != 0;
+
+    if (y == yb0 && vcol_ok) {
+      int fk = 0;
+#pragma unroll
+      for (int k = 0; k < FK_MAXF; ++k) { rs[k] = 0.0; rc[k] = 0; }
+      for (int t = 0; t < p.n_terms; ++t) {
+        if (p.terms[t].kind != TERM_BOX_FUSED) continue;
+        const int r = p.terms[t].r;
+        double s = 0.0;
+        int c = 0;
+        for (int d = -r; d <= r; ++d) {
+          float v = ring[slot_tab[d + R + 1] + vc];
+          bool ok = v == v;
+          s += ok ? (double)v : 0.0;
+          c += ok;
+        }
+#pragma unroll
+        for (int k = 0; k < FK_MAXF; ++k) if (k == fk) { rs[k] = s; rc[k] = c; }
+        ++fk;
+      }
+    }
+
+    float acc[FK_SEG];
+    int fk = 0;
+    bool first = true;
+    const int64_t orow = y + hi;
+    const bool hrow_ok = orow < yb1;
+    const int nrows_b = (int)((yb1 - y) < FK_NB ? (yb1 - y) : FK_NB);
+    const float* xrow = ring + slot_tab[hi + R + 1];   // centre row of this thread (hi <= NB-1)
+    for (int t = 0; t < p.n_terms; ++t) {
+      const DevTerm& T = p.terms[t];
+      if (T.kind == TERM_BOX_FUSED) {
+        const int r = T.r;
+        if (vcol_ok && vc >= R - r && vc < R + FK_TW + r) {
+          double s = 0.0;
+          int c = 0;
+#pragma unroll
+          for (int k = 0; k < FK_MAXF; ++k) if (k == fk) { s = rs[k]; c = rc[k]; }
+          const double n = (double)(2 * r + 1), inv = 1.0 / n;
+          const int* tin = slot_tab + (r + 1 + R + 1);
+          const int* tout = slot_tab + (-r + R + 1);
+          if (!nanmode) {
+#pragma unroll 4
+            for (int i = 0; i < nrows_b; ++i) {
+              vplane[i * SWp + vc] = (float)(s * inv);
+              float vin = ring[tin[i] + vc];
+              float vout = ring[tout[i] + vc];
+              s += (double)vin - (double)vout;
+            }
+          } else {
+            for (int i = 0; i < nrows_b; ++i) {
+              vplane[i * SWp + vc] = (float)div_by_count(s, n, inv);
+              cplane[i * SWp + vc] = (unsigned char)c;
+              float vin = ring[tin[i] + vc];
+              float vout = ring[tout[i] + vc];
+              bool oin = vin == vin, oout = vout == vout;
+              s += (oin ? (double)vin : 0.0) - (oout ? (double)vout : 0.0);
+              c += (int)oin - (int)oout;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < FK_MAXF; ++k) if (k == fk) { rs[k] = s; rc[k] = c; }
+        }
+        __syncthreads();
+        if (hrow_ok && hjn > 0) {
+          const float* vrow = vplane + hi * SWp;
+          const unsigned char* crow = cplane + hi * SWp;
+          if (edge_strip) hphase_box<true>(vrow, crow, xrow, R, r, hj0, hjn, x0, cs0, W, nanmode, T.weight, first, acc);
+          else hphase_box<false>(vrow, crow, xrow, R, r, hj0, hjn, x0, cs0, W, nanmode, T.weight, first, acc);
+        }
+        __syncthreads();
+        ++fk;
+      } else if (T.kind == TERM_COARSE) {
+        if (hrow_ok && hjn > 0) {
+          // scipy zoom(order=1): coordinate = index*(n_in-1)/(n_out-1), weights [1-t, t], 'nearest' edge.
+          // Rows are interpolated first (A = a0*(1-tr) + a1*tr at the two neighbouring coarse
+          // columns), then one FMA along the row: A0 + tc*(A1 - A0).
+          double ri = (double)orow * T.rscale;
+          int64_t r0 = (int64_t)floor(ri);
+          if (r0 > T.gh - 1) r0 = T.gh - 1;
+          const double tr = ri - (double)r0;
+          const int64_t r1 = r0 + 1 < T.gh ? r0 + 1 : T.gh - 1;
+          const double wr0 = 1.0 - tr;
+          const float* g0 = T.grid + r0 * T.gw;
+          const float* g1 = T.grid + r1 * T.gw;
+          const int gwm1 = (int)T.gw - 1;
+          double ci = (double)(x0 + hj0) * T.cscale;
+          int c0 = (int)floor(ci);
+          if (c0 > gwm1) c0 = gwm1;
+          double c0f = (double)c0;
+          int c1 = c0 + 1 < gwm1 ? c0 + 1 : gwm1;
+          double A0 = (double)__ldg(g0 + c0) * wr0 + (double)__ldg(g1 + c0) * tr;
+          double A1 = (double)__ldg(g0 + c1) * wr0 + (double)__ldg(g1 + c1) * tr;
+          double dA = A1 - A0;
+#pragma unroll
+          for (int jj = 0; jj < FK_SEG; ++jj) {
+            if (jj < hjn) {
+              ci = (double)(x0 + hj0 + jj) * T.cscale;
+              while (ci >= c0f + 1.0 && c0 < gwm1) {
+                ++c0;
+                c0f += 1.0;
+                c1 = c0 + 1 < gwm1 ? c0 + 1 : gwm1;
+                A0 = A1;
+                A1 = (double)__ldg(g0 + c1) * wr0 + (double)__ldg(g1 + c1) * tr;
+                dA = A1 - A0;
+              }
+              float mean = (float)fma(ci - c0f, dA, A0);
+              float term = T.weight * (xrow[R + hj0 + jj] - mean);
+              acc[jj] = first ? term : acc[jj] + term;
+            }
+          }
+        }
+      } else {
+        if (hrow_ok && hjn > 0) {
+          const float* prow = T.grid + orow * W;
+#pragma unroll
+          for (int jj = 0; jj < FK_SEG; ++jj) {
+            if (jj < hjn) {
+              float term = T.weight * (xrow[R + hj0 + jj] - __ldg(prow + x0 + hj0 + jj));
+              acc[jj] = first ? term : acc[jj] + term;
+            }
+          }
+        }
+      }
+      first = false;
+    }
+
+    float* stage = vplane;
+    if (hrow_ok && hjn > 0) {
+#pragma unroll
+      for (int jj = 0; jj < FK_SEG; ++jj) {
+        if (jj < hjn) {
+          float v = acc[jj];
+          if (p.norm_mode == 1) v = v / p.norm_scale;
+          else if (p.norm_mode == 2) v = (v != v) ? v : 0.f;
+          stage[hi * (FK_TW + 1) + hj0 + jj] = v;
+        }
+      }
+    }
+    __syncthreads();
+    {
+      const int ncols = (W - x0) < FK_TW ? (W - x0) : FK_TW;
+      if (p.enc.kind == FSG_OUT_F32) {
+        float* o = (float*)p.out;
+        for (int idx = tid; idx < nrows_b * FK_TW; idx += FK_THREADS) {
+          int rr = idx / FK_TW, c = idx - rr * FK_TW;
+          if (c < ncols) o[(y + rr) * p.ld_out + x0 + c] = stage[rr * (FK_TW + 1) + c];
+        }
+      } else {
+        for (int idx = tid; idx < nrows_b * FK_TW; idx += FK_THREADS) {
+          int rr = idx / FK_TW, c = idx - rr * FK_TW;
+          if (c < ncols) store_out(p.out, (y + rr) * p.ld_out + x0 + c, stage[rr * (FK_TW + 1) + c], p.enc);
+        }
+      }
+    }
+  }
+}
+
 static size_t fused_smem_bytes(int R) {
   size_t SWp = (size_t)((FK_TW + 2 * R) | 1);
   size_t nring = FK_NB + 2 * R + 1;
   size_t vp = (size_t)FK_NB * SWp;
   size_t stage = (size_t)FK_NB * (FK_TW + 1);
   if (stage > vp) vp = stage;
-  return nring * SWp * 4 + vp * 4 + align_up((size_t)FK_NB * SWp, 16);
+  return nring * SWp * 4 + vp * 4 + align_up((size_t)FK_NB * SWp, 16) + align_up((nring + 1) * 4, 16);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -653,10 +944,13 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
   int64_t bands = (H + band_rows - 1) / band_rows;
   if (bands > 65535) return fail(FSG_E_UNSUPPORTED, "fsg_topousm_fast: raster too tall");
   size_t smem = fused_smem_bytes(plan.fused_R);
-  FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool fast = H >= plan.fused_R + 2 && W >= plan.fused_R + 2 && W < (1 << 30) && !getenv("FSG_FORCE_GENERIC");
+  FSG_CUDA_OK(cudaFuncSetAttribute(fast ? fused_kernel_fast : fused_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)strips, (unsigned)bands);
   int slot = prof_begin(PROF_TOPOUSM_FUSED, s);
-  fused_kernel<<<grid, FK_THREADS, smem, s>>>(fp);
+  if (fast) fused_kernel_fast<<<grid, FK_THREADS, smem, s>>>(fp);
+  else fused_kernel<<<grid, FK_THREADS, smem, s>>>(fp);
   prof_end(slot, s);
   FSG_LAUNCH_OK();
   return FSG_OK;

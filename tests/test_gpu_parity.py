@@ -147,6 +147,40 @@ def test_topousm_fast_large_vs_oracle():
         assert np.abs(got8.astype(int) - want8.astype(int)).max() <= 1
 
 
+def test_topousm_generic_and_fast_kernels_agree(monkeypatch):
+    """The streaming kernel has a general variant (any raster size, multiple mirror reflections) and a
+    fast variant; both must give the same bits, on dense and NoData rasters, f32 and uint8."""
+    from fujishadergpu_b200 import kernels as k
+    radii, w = [2, 8, 32, 128, 512], orc.pow2_weights(5)
+    qp = orc.encode_params(*orc.value_range("topousm_fast"), "uint8")
+    for nodata in (False, True):
+        dem = _cuda(orc.synth_dem(777, 1300, seed=31 + nodata, nodata=nodata))
+        monkeypatch.delenv("FSG_FORCE_GENERIC", raising=False)
+        fast = _np(k.topousm_fast(dem, radii=radii, weights=w))
+        fast8 = _np(k.topousm_fast(dem, radii=radii, weights=w, norm_scale=11.0, output_dtype="uint8", qp=qp))
+        monkeypatch.setenv("FSG_FORCE_GENERIC", "1")
+        gen = _np(k.topousm_fast(dem, radii=radii, weights=w))
+        gen8 = _np(k.topousm_fast(dem, radii=radii, weights=w, norm_scale=11.0, output_dtype="uint8", qp=qp))
+        monkeypatch.delenv("FSG_FORCE_GENERIC", raising=False)
+        assert np.array_equal(np.isnan(fast), np.isnan(gen))
+        scale = float(np.nanpercentile(np.abs(gen), 99))
+        _topo_close(fast, gen, scale, f"fast vs generic nodata={nodata}")
+        assert np.abs(fast8.astype(int) - gen8.astype(int)).max() <= 1
+
+
+def test_topousm_tiny_and_ragged_rasters_vs_oracle():
+    """Rasters smaller than the window (re-reflection), single rows/columns, ragged strip edges."""
+    from fujishadergpu_b200 import kernels as k
+    for shape, radii in (((20, 300), [2, 8, 32]), ((300, 19), [2, 8, 32, 128]), ((1, 50), [3]), ((50, 1), [3, 100]),
+                         ((33, 257), [41, 42]), ((97, 513), [2, 8, 32, 128, 512, 2048])):
+        dem = orc.synth_dem(shape[0], shape[1], seed=shape[0] + shape[1])
+        dem[shape[0] // 2, shape[1] // 3] = np.nan
+        want = orc.topousm_fast_block(dem, radii=radii)
+        got = _np(k.topousm_fast(_cuda(dem), radii=radii))
+        scale = max(1e-3, float(np.nanpercentile(np.abs(want), 99)))
+        _topo_close(got, want, scale, f"{shape} {radii}")
+
+
 def test_topousm_weights_length_mismatch_raises():
     from fujishadergpu_b200.algorithms._impl_topousm_fast import compute_topousm_fast_efficient_block
     with pytest.raises(ValueError):
