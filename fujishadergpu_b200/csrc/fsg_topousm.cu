@@ -219,6 +219,37 @@ __device__ __forceinline__ void cell_reduce(const float* sm, int row0, int col0,
   *cnt = Cn;
 }
 
+// Single-column coarse grid (W <= f): NumPy coalesces the two reduced axes into ONE contiguous run of
+// f*f elements and reduces it with its pairwise routine (n<8 sequential; n<=128: 8 lanes + tree;
+// n=256: two 128-element halves).
+template <typename GET>
+__device__ __forceinline__ float pairwise_block(GET get, int start, int n) {  // 8 <= n <= 128, n % 8 == 0
+  float r[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = get(start + k);
+  for (int i = 8; i < n; i += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = r[k] + get(start + i + k);
+  }
+  return ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+}
+
+__device__ void cell_reduce_contig(const float* sm, int f, int row0, int col0, float* tot, float* cnt) {
+  auto val = [&](int e) { float v = sm[py_idx(row0 + e / f, col0 + e % f)]; return isfinite(v) ? v : 0.f; };
+  auto one = [&](int e) { float v = sm[py_idx(row0 + e / f, col0 + e % f)]; return isfinite(v) ? 1.f : 0.f; };
+  const int n = f * f;
+  if (n < 8) {
+    float a = val(0), c = one(0);
+    for (int e = 1; e < n; ++e) { a = a + val(e); c = c + one(e); }
+    *tot = a; *cnt = c;
+  } else if (n <= 128) {
+    *tot = pairwise_block(val, 0, n); *cnt = pairwise_block(one, 0, n);
+  } else {
+    *tot = pairwise_block(val, 0, 128) + pairwise_block(val, 128, 128);
+    *cnt = pairwise_block(one, 0, 128) + pairwise_block(one, 128, 128);
+  }
+}
+
 __global__ void __launch_bounds__(256) pyramid_kernel(PyramidParams p) {
   __shared__ float sm[PY_ROWS * PY_STRIDE];
   const int64_t x0 = (int64_t)blockIdx.x * PY_COLS;
@@ -253,7 +284,8 @@ __global__ void __launch_bounds__(256) pyramid_kernel(PyramidParams p) {
       int64_t oy = y0 / f + cy, ox = x0 / f + cx;
       if (oy >= p.gh[lv] || ox >= p.gw[lv]) continue;
       float tot, cnt;
-      if (f == 2) cell_reduce<2>(sm, cy * 2, cx * 2, &tot, &cnt);
+      if (p.gw[lv] == 1) cell_reduce_contig(sm, f, cy * f, cx * f, &tot, &cnt);
+      else if (f == 2) cell_reduce<2>(sm, cy * 2, cx * 2, &tot, &cnt);
       else if (f == 4) cell_reduce<4>(sm, cy * 4, cx * 4, &tot, &cnt);
       else if (f == 8) cell_reduce<8>(sm, cy * 8, cx * 8, &tot, &cnt);
       else cell_reduce<16>(sm, cy * 16, cx * 16, &tot, &cnt);
@@ -276,7 +308,7 @@ __global__ void zero_flags_kernel(int* flags) {
 // ------------------------------------------------------------------------------------------
 constexpr int FK_THREADS = 352;             // 11 warps
 constexpr int FK_NB = 32;                   // rows per batch
-constexpr int FK_TW = 256;                  // output columns per strip
+constexpr int FK_TW = 264;                  // output columns per strip (11 segments of 24)
 constexpr int FK_NSEG = FK_THREADS / FK_NB; // 11 column segments in the horizontal phase
 constexpr int FK_SEG = (FK_TW + FK_NSEG - 1) / FK_NSEG;  // 24
 constexpr int FK_MAXF = 8;
@@ -298,6 +330,7 @@ struct FusedParams {
   DevTerm terms[MAX_TERMS];
   int R;           // halo (max fused radius, 0 if none)
   int band_rows;   // rows per CTA band (multiple of FK_NB)
+  int ring_rows;   // rows held by the shared-memory ring (fast kernel)
   int norm_mode;   // 0 none, 1 divide by norm_scale, 2 zeros
   float norm_scale;
   EncodeDev enc;
@@ -600,14 +633,34 @@ __device__ __forceinline__ void hphase_box(const float* __restrict__ vrow, const
   }
 }
 
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Streaming kernel, fast variant.  One CTA = one strip of FK_TW output columns x one band of rows.
+//   ring   : the last NB+2R+1 (+NB prefetched) DEM rows of the strip, filled with cp.async (LDGSTS);
+//            the rows of batch b+1 are in flight while batch b is being computed;
+//   vphase : thread = column; exact f64 running window sum down the rows (state lives in registers
+//            across batches); one f32 rounding per output (scipy's axis-0 rounding point);
+//   hphase : thread = (row, 24-column segment), lanes of a warp = 32 different rows (odd row stride ->
+//            conflict-free); f64 sliding sum along the row; second f32 rounding; weighted difference
+//            accumulated in f32 in list order;
+//   coarse : align-corners bilinear tap of the decimated mean (one f64 FMA per pixel);
+//   output : staged through shared memory -> coalesced stores (f32 / i16 / u8 encoding fused).
 __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int R = p.R;
   const int SW = FK_TW + 2 * R;
   const int SWp = SW | 1;
-  const int NRING = FK_NB + 2 * R + 1;
+  const int NRING = FK_NB + 2 * R + 1;   // rows one batch needs
+  const int NRT = p.ring_rows;           // rows the ring holds (NRING, or NRING + NB with prefetch)
+  const bool prefetch = NRT >= NRING + FK_NB;
   float* ring = reinterpret_cast<float*>(smraw);
-  float* vplane = ring + (size_t)NRING * SWp;
+  float* vplane = ring + (size_t)NRT * SWp;
   unsigned char* cplane = reinterpret_cast<unsigned char*>(vplane + (size_t)FK_NB * SWp);
   int* slot_tab = reinterpret_cast<int*>(cplane + (((size_t)FK_NB * SWp + 15) / 16) * 16);  // NRING+1 row offsets
 
@@ -635,52 +688,60 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
   int hjn = (hj0 + FK_SEG <= FK_TW) ? FK_SEG : (FK_TW - hj0 > 0 ? FK_TW - hj0 : 0);
   if (x0 + hj0 + hjn > W) hjn = (W - x0 - hj0 > 0) ? (W - x0 - hj0) : 0;
 
-  unsigned nan_hist = 0;
-  int64_t loaded_hi = -1;
-  int base = 0;  // ring slot of row y
-
-  for (int64_t y = yb0; y < yb1; y += FK_NB) {
-    const int64_t need_lo = y - R < 0 ? 0 : y - R;
-    const int64_t need_hi = y + FK_NB + R >= H ? H - 1 : y + FK_NB + R;
-    const int64_t from = (y == yb0) ? need_lo : loaded_hi + 1;
-    if (y == yb0) base = (int)(y - need_lo); else { base += FK_NB; if (base >= NRING) base -= NRING; }
-    __syncthreads();
-    // slot table: entry (d + R + 1) = SWp * ring slot of (reflected) row y + d, d in [-R-1, NB+R]
-    for (int e = tid; e <= NRING; e += FK_THREADS) {
-      int d = e - R - 1;
-      int dd = reflect1(y + d, H) - (int)y;     // y is < 2^31 rows from the reflected row
-      int sl = (base + dd) % NRING;            // once per batch and table entry, not per pixel
-      if (sl < 0) sl += NRING;
-      slot_tab[e] = sl * SWp;
-    }
-    int my_nan = 0;
-    {
-      const int nrows = (int)(need_hi - from + 1);
-      const int c_lo = cs0 < 0 ? -cs0 : 0;
-      const int c_hi = (cs0 + SW > W) ? W - cs0 : SW;   // exclusive
-      for (int rr = 0; rr < nrows; ++rr) {
-        const int64_t row = from + rr;
-        int sl = base + (int)(row - y);
-        if (sl >= NRING) sl -= NRING;
-        if (sl < 0) sl += NRING;
-        const float* src = p.dem + row * p.ld_in + cs0;
-        float* dst = ring + (size_t)sl * SWp;
-        for (int c = c_lo + tid; c < c_hi; c += FK_THREADS) {
-          float v = __ldg(src + c);
-          my_nan |= (v != v);
-          dst[c] = v;
-        }
+  // rows are stored at slot (row - row_org) mod NRT
+  const int64_t row_org = yb0 - R < 0 ? 0 : yb0 - R;
+  auto need_hi_of = [&](int64_t yy) { return yy + FK_NB + R >= H ? H - 1 : yy + FK_NB + R; };
+  auto issue_rows = [&](int64_t from, int64_t to) {   // cp.async rows [from, to] of this thread's column
+    if (vc < SW && vgx >= 0 && vgx < W && from <= to) {
+      int sl = (int)((from - row_org) % NRT);
+      const float* src = p.dem + from * p.ld_in + vgx;
+      for (int64_t row = from; row <= to; ++row) {
+        cp_async4(ring + (size_t)sl * SWp + vc, src);
+        src += p.ld_in;
+        if (++sl == NRT) sl = 0;
       }
     }
-    loaded_hi = need_hi;
+  };
+
+  unsigned nan_hist = 0;
+  int base = (int)(yb0 - row_org);  // ring slot of row y
+  issue_rows(row_org, need_hi_of(yb0));
+  cp_async_commit();
+
+  for (int64_t y = yb0; y < yb1; y += FK_NB) {
+    const int64_t need_hi = need_hi_of(y);
+    const int64_t prev_hi = (y == yb0) ? row_org - 1 : need_hi_of(y - FK_NB);
+    __syncthreads();   // every warp is done with batch b-1: its oldest rows and vplane may be reused
+    if (prefetch) { if (y + FK_NB < yb1) issue_rows(need_hi + 1, need_hi_of(y + FK_NB)); }
+    else if (y > yb0) issue_rows(prev_hi + 1, need_hi);
+    cp_async_commit();
+    if (prefetch) cp_async_wait<1>(); else cp_async_wait<0>();
+    // slot table: entry (d + R + 1) = SWp * ring slot of (mirrored) row y + d, d in [-R-1, NB+R]
+    for (int e = tid; e <= NRING; e += FK_THREADS) {
+      int d = e - R - 1;
+      int dd = reflect1(y + d, H) - (int)y;
+      int sl = (base + dd) % NRT;
+      if (sl < 0) sl += NRT;
+      slot_tab[e] = sl * SWp;
+    }
+    __syncthreads();   // this batch's rows (all threads' cp.async) and the slot table are visible
+    int my_nan = 0;
+    if (vcol_ok) {
+      int sl = (int)((prev_hi + 1 - row_org) % NRT);
+      for (int64_t row = prev_hi + 1; row <= need_hi; ++row) {
+        float v = ring[(size_t)sl * SWp + vc];
+        my_nan |= (v != v);
+        if (++sl == NRT) sl = 0;
+      }
+    }
     const int any = __syncthreads_or(my_nan);
     nan_hist = (y == yb0) ? (any ? 0x3fu : 0u) : ((nan_hist << 1) | (any ? 1u : 0u));
     const bool nanmode = (nan_hist & 0x3fu) != 0;
+    const int nrows_b = (int)((yb1 - y) < FK_NB ? (yb1 - y) : FK_NB);
+    const bool interior_rows = (y - R - 1 >= 0) && (y + FK_NB + R + 1 < H);
 
     if (y == yb0 && vcol_ok) {
       int fk = 0;
-#pragma unroll
-      for (int k = 0; k < FK_MAXF; ++k) { rs[k] = 0.0; rc[k] = 0; }
       for (int t = 0; t < p.n_terms; ++t) {
         if (p.terms[t].kind != TERM_BOX_FUSED) continue;
         const int r = p.terms[t].r;
@@ -698,53 +759,102 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
       }
     }
 
-    float acc[FK_SEG];
-    int fk = 0;
-    bool first = true;
     const int64_t orow = y + hi;
     const bool hrow_ok = orow < yb1;
-    const int nrows_b = (int)((yb1 - y) < FK_NB ? (yb1 - y) : FK_NB);
-    const float* xrow = ring + slot_tab[hi + R + 1];   // centre row of this thread (hi <= NB-1)
+    const float* xrow = ring + slot_tab[hi + R + 1];
+    const bool hfast = hrow_ok && !edge_strip && hjn == FK_SEG && !nanmode;
+    float acc[FK_SEG], xr[FK_SEG];
+#pragma unroll
+    for (int jj = 0; jj < FK_SEG; ++jj) {
+      acc[jj] = 0.f;
+      xr[jj] = (hrow_ok && jj < hjn) ? xrow[R + hj0 + jj] : 0.f;
+    }
+    int fk = 0;
     for (int t = 0; t < p.n_terms; ++t) {
       const DevTerm& T = p.terms[t];
       if (T.kind == TERM_BOX_FUSED) {
         const int r = T.r;
+        const double n = (double)(2 * r + 1), inv = 1.0 / n;
         if (vcol_ok && vc >= R - r && vc < R + FK_TW + r) {
           double s = 0.0;
           int c = 0;
 #pragma unroll
           for (int k = 0; k < FK_MAXF; ++k) if (k == fk) { s = rs[k]; c = rc[k]; }
-          const double n = (double)(2 * r + 1), inv = 1.0 / n;
-          const int* tin = slot_tab + (r + 1 + R + 1);
-          const int* tout = slot_tab + (-r + R + 1);
-          if (!nanmode) {
-#pragma unroll 4
-            for (int i = 0; i < nrows_b; ++i) {
-              vplane[i * SWp + vc] = (float)(s * inv);
-              float vin = ring[tin[i] + vc];
-              float vout = ring[tout[i] + vc];
-              s += (double)vin - (double)vout;
+          if (!nanmode && interior_rows) {
+            // rows are consecutive ring slots: walk them with plain pointer increments, splitting the
+            // batch where the incoming or the outgoing row wraps around the ring
+            int sin = base + r + 1; if (sin >= NRT) sin -= NRT;
+            int sout = base - r; if (sout < 0) sout += NRT;
+            int i = 0;
+            while (i < nrows_b) {
+              int run = nrows_b - i;
+              if (NRT - sin < run) run = NRT - sin;
+              if (NRT - sout < run) run = NRT - sout;
+              const float* pin = ring + (size_t)sin * SWp + vc;
+              const float* pout = ring + (size_t)sout * SWp + vc;
+              float* pv = vplane + (size_t)i * SWp + vc;
+              int k = 0;
+              for (; k + 4 <= run; k += 4) {
+                float a0 = pin[0], a1 = pin[SWp], a2 = pin[2 * SWp], a3 = pin[3 * SWp];
+                float b0 = pout[0], b1 = pout[SWp], b2 = pout[2 * SWp], b3 = pout[3 * SWp];
+                double d0 = (double)a0 - (double)b0, d1 = (double)a1 - (double)b1;
+                double d2 = (double)a2 - (double)b2, d3 = (double)a3 - (double)b3;
+                pv[0] = (float)(s * inv); s += d0;
+                pv[SWp] = (float)(s * inv); s += d1;
+                pv[2 * SWp] = (float)(s * inv); s += d2;
+                pv[3 * SWp] = (float)(s * inv); s += d3;
+                pin += 4 * SWp; pout += 4 * SWp; pv += 4 * SWp;
+              }
+              for (; k < run; ++k) {
+                pv[0] = (float)(s * inv);
+                s += (double)pin[0] - (double)pout[0];
+                pin += SWp; pout += SWp; pv += SWp;
+              }
+              i += run;
+              sin += run; if (sin >= NRT) sin -= NRT;
+              sout += run; if (sout >= NRT) sout -= NRT;
             }
           } else {
-            for (int i = 0; i < nrows_b; ++i) {
-              vplane[i * SWp + vc] = (float)div_by_count(s, n, inv);
-              cplane[i * SWp + vc] = (unsigned char)c;
-              float vin = ring[tin[i] + vc];
-              float vout = ring[tout[i] + vc];
-              bool oin = vin == vin, oout = vout == vout;
-              s += (oin ? (double)vin : 0.0) - (oout ? (double)vout : 0.0);
-              c += (int)oin - (int)oout;
+            const int* tin = slot_tab + (r + 1 + R + 1);
+            const int* tout = slot_tab + (-r + R + 1);
+            if (!nanmode) {
+              for (int i = 0; i < nrows_b; ++i) {
+                vplane[i * SWp + vc] = (float)(s * inv);
+                s += (double)ring[tin[i] + vc] - (double)ring[tout[i] + vc];
+              }
+            } else {
+              for (int i = 0; i < nrows_b; ++i) {
+                vplane[i * SWp + vc] = (float)div_by_count(s, n, inv);
+                cplane[i * SWp + vc] = (unsigned char)c;
+                float vin = ring[tin[i] + vc];
+                float vout = ring[tout[i] + vc];
+                bool oin = vin == vin, oout = vout == vout;
+                s += (oin ? (double)vin : 0.0) - (oout ? (double)vout : 0.0);
+                c += (int)oin - (int)oout;
+              }
             }
           }
 #pragma unroll
           for (int k = 0; k < FK_MAXF; ++k) if (k == fk) { rs[k] = s; rc[k] = c; }
         }
         __syncthreads();
-        if (hrow_ok && hjn > 0) {
+        if (hfast) {
+          const float* pl = vplane + hi * SWp + R + hj0 - r;   // leftmost tap of the first window
+          const float* pr = pl + 2 * r + 1;                    // first tap entering
+          double sv = 0.0;
+          for (int d = 0; d <= 2 * r; ++d) sv += (double)pl[d];
+          const float wgt = T.weight;
+#pragma unroll
+          for (int jj = 0; jj < FK_SEG; ++jj) {
+            float mean = (float)(sv * inv);
+            acc[jj] = acc[jj] + wgt * (xr[jj] - mean);
+            if (jj + 1 < FK_SEG) sv += (double)pr[jj] - (double)pl[jj];
+          }
+        } else if (hrow_ok && hjn > 0) {
           const float* vrow = vplane + hi * SWp;
           const unsigned char* crow = cplane + hi * SWp;
-          if (edge_strip) hphase_box<true>(vrow, crow, xrow, R, r, hj0, hjn, x0, cs0, W, nanmode, T.weight, first, acc);
-          else hphase_box<false>(vrow, crow, xrow, R, r, hj0, hjn, x0, cs0, W, nanmode, T.weight, first, acc);
+          if (edge_strip) hphase_box<true>(vrow, crow, xrow, R, r, hj0, hjn, x0, cs0, W, nanmode, T.weight, false, acc);
+          else hphase_box<false>(vrow, crow, xrow, R, r, hj0, hjn, x0, cs0, W, nanmode, T.weight, false, acc);
         }
         __syncthreads();
         ++fk;
@@ -770,10 +880,13 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
           double A0 = (double)__ldg(g0 + c0) * wr0 + (double)__ldg(g1 + c0) * tr;
           double A1 = (double)__ldg(g0 + c1) * wr0 + (double)__ldg(g1 + c1) * tr;
           double dA = A1 - A0;
+          const float wgt = T.weight;
+          const double cs = T.cscale;
+          const double gx0 = (double)(x0 + hj0);
 #pragma unroll
           for (int jj = 0; jj < FK_SEG; ++jj) {
-            if (jj < hjn) {
-              ci = (double)(x0 + hj0 + jj) * T.cscale;
+            if (hfast || jj < hjn) {
+              ci = (gx0 + (double)jj) * cs;
               while (ci >= c0f + 1.0 && c0 < gwm1) {
                 ++c0;
                 c0f += 1.0;
@@ -783,8 +896,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
                 dA = A1 - A0;
               }
               float mean = (float)fma(ci - c0f, dA, A0);
-              float term = T.weight * (xrow[R + hj0 + jj] - mean);
-              acc[jj] = first ? term : acc[jj] + term;
+              acc[jj] = acc[jj] + wgt * (xr[jj] - mean);
             }
           }
         }
@@ -792,15 +904,10 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
         if (hrow_ok && hjn > 0) {
           const float* prow = T.grid + orow * W;
 #pragma unroll
-          for (int jj = 0; jj < FK_SEG; ++jj) {
-            if (jj < hjn) {
-              float term = T.weight * (xrow[R + hj0 + jj] - __ldg(prow + x0 + hj0 + jj));
-              acc[jj] = first ? term : acc[jj] + term;
-            }
-          }
+          for (int jj = 0; jj < FK_SEG; ++jj)
+            if (jj < hjn) acc[jj] = acc[jj] + T.weight * (xr[jj] - __ldg(prow + x0 + hj0 + jj));
         }
       }
-      first = false;
     }
 
     float* stage = vplane;
@@ -818,25 +925,26 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
     __syncthreads();
     {
       const int ncols = (W - x0) < FK_TW ? (W - x0) : FK_TW;
-      if (p.enc.kind == FSG_OUT_F32) {
-        float* o = (float*)p.out;
-        for (int idx = tid; idx < nrows_b * FK_TW; idx += FK_THREADS) {
-          int rr = idx / FK_TW, c = idx - rr * FK_TW;
-          if (c < ncols) o[(y + rr) * p.ld_out + x0 + c] = stage[rr * (FK_TW + 1) + c];
-        }
-      } else {
-        for (int idx = tid; idx < nrows_b * FK_TW; idx += FK_THREADS) {
-          int rr = idx / FK_TW, c = idx - rr * FK_TW;
-          if (c < ncols) store_out(p.out, (y + rr) * p.ld_out + x0 + c, stage[rr * (FK_TW + 1) + c], p.enc);
+      for (int rr = tid / 32; rr < nrows_b; rr += FK_THREADS / 32) {   // one warp per output row
+        const float* srow = stage + rr * (FK_TW + 1);
+        const int64_t obase = (y + rr) * p.ld_out + x0;
+        if (p.enc.kind == FSG_OUT_F32) {
+          float* o = (float*)p.out + obase;
+          for (int c = tid & 31; c < ncols; c += 32) o[c] = srow[c];
+        } else {
+          for (int c = tid & 31; c < ncols; c += 32) store_out(p.out, obase + c, srow[c], p.enc);
         }
       }
     }
+    base += FK_NB;
+    if (base >= NRT) base -= NRT;
   }
+  cp_async_wait<0>();
 }
 
-static size_t fused_smem_bytes(int R) {
+static size_t fused_smem_bytes(int R, int extra_rows = 0) {
   size_t SWp = (size_t)((FK_TW + 2 * R) | 1);
-  size_t nring = FK_NB + 2 * R + 1;
+  size_t nring = FK_NB + 2 * R + 1 + extra_rows;
   size_t vp = (size_t)FK_NB * SWp;
   size_t stage = (size_t)FK_NB * (FK_TW + 1);
   if (stage > vp) vp = stage;
@@ -944,6 +1052,11 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
   int64_t bands = (H + band_rows - 1) / band_rows;
   if (bands > 65535) return fail(FSG_E_UNSUPPORTED, "fsg_topousm_fast: raster too tall");
   size_t smem = fused_smem_bytes(plan.fused_R);
+  fp.ring_rows = FK_NB + 2 * plan.fused_R + 1;
+  if (fused_smem_bytes(plan.fused_R, FK_NB) <= 227 * 1024) {   // room to prefetch the next batch
+    smem = fused_smem_bytes(plan.fused_R, FK_NB);
+    fp.ring_rows += FK_NB;
+  }
   const bool fast = H >= plan.fused_R + 2 && W >= plan.fused_R + 2 && W < (1 << 30) && !getenv("FSG_FORCE_GENERIC");
   FSG_CUDA_OK(cudaFuncSetAttribute(fast ? fused_kernel_fast : fused_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
