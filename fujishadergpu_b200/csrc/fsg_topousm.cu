@@ -320,6 +320,7 @@ struct DevTerm {
   const float* grid; // coarse mean grid / plane
   int64_t gh, gw;    // coarse dims
   double rscale, cscale;  // (gh-1)/(H-1), (gw-1)/(W-1)
+  int lvl;                // coarse terms: index of the pyramid level (column-fraction table)
 };
 
 struct FusedParams {
@@ -331,6 +332,10 @@ struct FusedParams {
   int R;           // halo (max fused radius, 0 if none)
   int band_rows;   // rows per CTA band (multiple of FK_NB)
   int ring_rows;   // rows held by the shared-memory ring (fast kernel)
+  int n_lvls;      // pyramid levels referenced by coarse terms
+  double lvl_cscale[MAX_LEVELS];
+  int lvl_gw[MAX_LEVELS];
+  float norm_rinv; // f32(1/norm_scale)
   int norm_mode;   // 0 none, 1 divide by norm_scale, 2 zeros
   float norm_scale;
   EncodeDev enc;
@@ -663,6 +668,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
   float* vplane = ring + (size_t)NRT * SWp;
   unsigned char* cplane = reinterpret_cast<unsigned char*>(vplane + (size_t)FK_NB * SWp);
   int* slot_tab = reinterpret_cast<int*>(cplane + (((size_t)FK_NB * SWp + 15) / 16) * 16);  // NRING+1 row offsets
+  double* tctab = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(slot_tab) + (((size_t)(NRING + 1) * 4 + 15) / 16) * 16);
 
   const int tid = threadIdx.x;
   const int W = (int)p.W;
@@ -687,6 +693,35 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
   const int hj0 = hg * FK_SEG;
   int hjn = (hj0 + FK_SEG <= FK_TW) ? FK_SEG : (FK_TW - hj0 > 0 ? FK_TW - hj0 : 0);
   if (x0 + hj0 + hjn > W) hjn = (W - x0 - hj0 > 0) ? (W - x0 - hj0) : 0;
+
+  // Column coordinates of the coarse levels are the same for every row of the strip: the fraction
+  // tc(j) = j*cscale - floor(j*cscale) goes to shared memory once per CTA, and each thread keeps the
+  // first coarse column of its segment plus a bit mask of the pixels where that column advances.
+  int lv_c0[MAX_LEVELS];
+  unsigned lv_adv[MAX_LEVELS];
+#pragma unroll
+  for (int l = 0; l < MAX_LEVELS; ++l) {
+    lv_c0[l] = 0;
+    lv_adv[l] = 0u;
+    if (l < p.n_lvls) {
+      const double cs = p.lvl_cscale[l];
+      const int gwm1 = p.lvl_gw[l] - 1;
+      for (int j = tid; j < FK_TW; j += FK_THREADS) {
+        double ci = (double)(x0 + j) * cs;
+        double fl = floor(ci);
+        if (fl > (double)gwm1) fl = (double)gwm1;
+        tctab[l * FK_TW + j] = ci - fl;
+      }
+      int prev = 0;
+      for (int jj = 0; jj < FK_SEG; ++jj) {
+        int c = (int)floor((double)(x0 + hj0 + jj) * cs);
+        if (c > gwm1) c = gwm1;
+        if (jj == 0) lv_c0[l] = c;
+        else if (c > prev) lv_adv[l] |= 1u << jj;
+        prev = c;
+      }
+    }
+  }
 
   // rows are stored at slot (row - row_org) mod NRT
   const int64_t row_org = yb0 - R < 0 ? 0 : yb0 - R;
@@ -872,30 +907,27 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
           const float* g0 = T.grid + r0 * T.gw;
           const float* g1 = T.grid + r1 * T.gw;
           const int gwm1 = (int)T.gw - 1;
-          double ci = (double)(x0 + hj0) * T.cscale;
-          int c0 = (int)floor(ci);
-          if (c0 > gwm1) c0 = gwm1;
-          double c0f = (double)c0;
+          int c0 = 0;
+          unsigned adv = 0u;
+#pragma unroll
+          for (int l = 0; l < MAX_LEVELS; ++l) if (l == T.lvl) { c0 = lv_c0[l]; adv = lv_adv[l]; }
           int c1 = c0 + 1 < gwm1 ? c0 + 1 : gwm1;
           double A0 = (double)__ldg(g0 + c0) * wr0 + (double)__ldg(g1 + c0) * tr;
           double A1 = (double)__ldg(g0 + c1) * wr0 + (double)__ldg(g1 + c1) * tr;
           double dA = A1 - A0;
           const float wgt = T.weight;
-          const double cs = T.cscale;
-          const double gx0 = (double)(x0 + hj0);
+          const double* tcp = tctab + T.lvl * FK_TW + hj0;
 #pragma unroll
           for (int jj = 0; jj < FK_SEG; ++jj) {
-            if (hfast || jj < hjn) {
-              ci = (gx0 + (double)jj) * cs;
-              while (ci >= c0f + 1.0 && c0 < gwm1) {
+            if (jj < hjn) {
+              if ((adv >> jj) & 1u) {
                 ++c0;
-                c0f += 1.0;
                 c1 = c0 + 1 < gwm1 ? c0 + 1 : gwm1;
                 A0 = A1;
                 A1 = (double)__ldg(g0 + c1) * wr0 + (double)__ldg(g1 + c1) * tr;
                 dA = A1 - A0;
               }
-              float mean = (float)fma(ci - c0f, dA, A0);
+              float mean = (float)fma(tcp[jj], dA, A0);
               acc[jj] = acc[jj] + wgt * (xr[jj] - mean);
             }
           }
@@ -912,27 +944,42 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
 
     float* stage = vplane;
     if (hrow_ok && hjn > 0) {
+      float* sp = stage + hi * (FK_TW + 1) + hj0;
+      if (p.norm_mode == 1) {
+        // v / s, correctly rounded: q = v*rinv, one FMA residual correction (Markstein); NaN stays NaN
+        const float sc = p.norm_scale, ri = p.norm_rinv;
 #pragma unroll
-      for (int jj = 0; jj < FK_SEG; ++jj) {
-        if (jj < hjn) {
-          float v = acc[jj];
-          if (p.norm_mode == 1) v = v / p.norm_scale;
-          else if (p.norm_mode == 2) v = (v != v) ? v : 0.f;
-          stage[hi * (FK_TW + 1) + hj0 + jj] = v;
+        for (int jj = 0; jj < FK_SEG; ++jj) {
+          if (jj < hjn) {
+            float q = acc[jj] * ri;
+            float rem = fmaf(-q, sc, acc[jj]);
+            sp[jj] = fmaf(rem, ri, q);
+          }
         }
+      } else if (p.norm_mode == 2) {
+#pragma unroll
+        for (int jj = 0; jj < FK_SEG; ++jj) if (jj < hjn) sp[jj] = (acc[jj] != acc[jj]) ? acc[jj] : 0.f;
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < FK_SEG; ++jj) if (jj < hjn) sp[jj] = acc[jj];
       }
     }
     __syncthreads();
     {
       const int ncols = (W - x0) < FK_TW ? (W - x0) : FK_TW;
       for (int rr = tid / 32; rr < nrows_b; rr += FK_THREADS / 32) {   // one warp per output row
-        const float* srow = stage + rr * (FK_TW + 1);
-        const int64_t obase = (y + rr) * p.ld_out + x0;
-        if (p.enc.kind == FSG_OUT_F32) {
+        const float* srow = stage + rr * (FK_TW + 1) + (tid & 31);
+        const int64_t obase = (y + rr) * p.ld_out + x0 + (tid & 31);
+        if (p.enc.kind == FSG_OUT_F32 && ncols == FK_TW) {
           float* o = (float*)p.out + obase;
-          for (int c = tid & 31; c < ncols; c += 32) o[c] = srow[c];
+#pragma unroll
+          for (int c = 0; c < FK_TW / 32; ++c) o[c * 32] = srow[c * 32];
+          if ((tid & 31) < FK_TW % 32) o[(FK_TW / 32) * 32] = srow[(FK_TW / 32) * 32];
+        } else if (p.enc.kind == FSG_OUT_F32) {
+          float* o = (float*)p.out + obase;
+          for (int c = 0; c + (tid & 31) < ncols; c += 32) o[c] = srow[c];
         } else {
-          for (int c = tid & 31; c < ncols; c += 32) store_out(p.out, obase + c, srow[c], p.enc);
+          for (int c = 0; c + (tid & 31) < ncols; c += 32) store_out(p.out, obase + c, srow[c], p.enc);
         }
       }
     }
@@ -942,13 +989,14 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
   cp_async_wait<0>();
 }
 
-static size_t fused_smem_bytes(int R, int extra_rows = 0) {
+static size_t fused_smem_bytes(int R, int extra_rows = 0, int n_lvls = 0) {
   size_t SWp = (size_t)((FK_TW + 2 * R) | 1);
   size_t nring = FK_NB + 2 * R + 1 + extra_rows;
   size_t vp = (size_t)FK_NB * SWp;
   size_t stage = (size_t)FK_NB * (FK_TW + 1);
   if (stage > vp) vp = stage;
-  return nring * SWp * 4 + vp * 4 + align_up((size_t)FK_NB * SWp, 16) + align_up((nring + 1) * 4, 16);
+  return nring * SWp * 4 + vp * 4 + align_up((size_t)FK_NB * SWp, 16) + align_up((nring + 1) * 4, 16) +
+         (size_t)n_lvls * FK_TW * 8 + 16;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1017,7 +1065,7 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
   fp.n_terms = n; fp.R = plan.fused_R;
   fp.enc = make_encode(enc);
   if (is_none(norm_scale)) fp.norm_mode = 0;
-  else if (norm_scale > 0.0) { fp.norm_mode = 1; fp.norm_scale = (float)norm_scale; }
+  else if (norm_scale > 0.0) { fp.norm_mode = 1; fp.norm_scale = (float)norm_scale; fp.norm_rinv = (float)(1.0 / (double)fp.norm_scale); }
   else fp.norm_mode = 2;
   for (int i = 0; i < n; ++i) {
     const HostTerm& t = plan.terms[i];
@@ -1032,6 +1080,9 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
       // scipy.ndimage.zoom: zoom = (n_in - 1) / (n_out - 1)  (1.0 when n_out == 1)
       d.rscale = H > 1 ? (double)(l.h - 1) / (double)(H - 1) : 1.0;
       d.cscale = W > 1 ? (double)(l.w - 1) / (double)(W - 1) : 1.0;
+      d.lvl = t.level;
+      fp.lvl_cscale[t.level] = d.cscale;
+      fp.lvl_gw[t.level] = (int)l.w;
     } else if (t.kind == TERM_PLANE) {
       float* mean = (float*)(base + t.grid_off);
       Grid g{dem, H, W, ld_in};
@@ -1051,10 +1102,11 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
   fp.band_rows = (int)band_rows;
   int64_t bands = (H + band_rows - 1) / band_rows;
   if (bands > 65535) return fail(FSG_E_UNSUPPORTED, "fsg_topousm_fast: raster too tall");
-  size_t smem = fused_smem_bytes(plan.fused_R);
+  fp.n_lvls = plan.n_levels;
+  size_t smem = fused_smem_bytes(plan.fused_R, 0, plan.n_levels);
   fp.ring_rows = FK_NB + 2 * plan.fused_R + 1;
-  if (fused_smem_bytes(plan.fused_R, FK_NB) <= 227 * 1024) {   // room to prefetch the next batch
-    smem = fused_smem_bytes(plan.fused_R, FK_NB);
+  if (fused_smem_bytes(plan.fused_R, FK_NB, plan.n_levels) <= 227 * 1024) {   // room to prefetch the next batch
+    smem = fused_smem_bytes(plan.fused_R, FK_NB, plan.n_levels);
     fp.ring_rows += FK_NB;
   }
   const bool fast = H >= plan.fused_R + 2 && W >= plan.fused_R + 2 && W < (1 << 30) && !getenv("FSG_FORCE_GENERIC");

@@ -140,6 +140,10 @@ def test_topousm_fast_large_vs_oracle():
         got = _np(k.topousm_fast(_cuda(dem), radii=radii, weights=w))
         exact = _topo_close(got, want, scale, f"ladder6 nodata={nodata}")
         print(f"nodata={nodata}: bit-exact fraction {exact:.6f}, scale {scale:.4f}")
+        # fused normalisation == IEEE f32 division of the raw output (block / scale)
+        for sc in (scale, 3.0, 0.731):
+            normed = _np(k.topousm_fast(_cuda(dem), radii=radii, weights=w, norm_scale=sc))
+            assert np.array_equal(normed, got / np.float32(sc), equal_nan=True), sc
         qp = orc.encode_params(*orc.value_range("topousm_fast"), "uint8")
         got8 = _np(k.topousm_fast(_cuda(dem), radii=radii, weights=w, norm_scale=scale, output_dtype="uint8", qp=qp))
         want8 = orc.encode_array(orc.normalise_by_scale(want.copy(), (scale,)), qp, "uint8")
