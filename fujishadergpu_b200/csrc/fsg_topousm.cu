@@ -667,8 +667,12 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
   float* ring = reinterpret_cast<float*>(smraw);
   float* vplane = ring + (size_t)NRT * SWp;
   unsigned char* cplane = reinterpret_cast<unsigned char*>(vplane + (size_t)FK_NB * SWp);
-  int* slot_tab = reinterpret_cast<int*>(cplane + (((size_t)FK_NB * SWp + 15) / 16) * 16);  // NRING+1 row offsets
-  double* tctab = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(slot_tab) + (((size_t)(NRING + 1) * 4 + 15) / 16) * 16);
+  // byte offsets from the (16-byte aligned) base: tables start on 16-byte boundaries
+  const size_t off_c = ((size_t)NRT * SWp + (size_t)FK_NB * SWp) * 4;
+  const size_t off_slot = (off_c + (size_t)FK_NB * SWp + 15) / 16 * 16;
+  const size_t off_tc = (off_slot + (size_t)(NRING + 1) * 4 + 15) / 16 * 16;
+  int* slot_tab = reinterpret_cast<int*>(smraw + off_slot);  // NRING+1 row offsets
+  double* tctab = reinterpret_cast<double*>(smraw + off_tc);
 
   const int tid = threadIdx.x;
   const int W = (int)p.W;
@@ -995,7 +999,7 @@ static size_t fused_smem_bytes(int R, int extra_rows = 0, int n_lvls = 0) {
   size_t vp = (size_t)FK_NB * SWp;
   size_t stage = (size_t)FK_NB * (FK_TW + 1);
   if (stage > vp) vp = stage;
-  return nring * SWp * 4 + vp * 4 + align_up((size_t)FK_NB * SWp, 16) + align_up((nring + 1) * 4, 16) +
+  return nring * SWp * 4 + vp * 4 + align_up((size_t)FK_NB * SWp, 16) + 16 + align_up((nring + 1) * 4, 16) + 16 +
          (size_t)n_lvls * FK_TW * 8 + 16;
 }
 
