@@ -585,10 +585,24 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
 
 // ------------------------------------------------------------------------------------------
 // 3b. fast variant of the fused kernel (rasters with H, W >= R + 2: a single mirror reflection is
-//     enough at the edges).  Same arithmetic as fused_kernel, but: 32-bit ring addressing through a
-//     per-batch row-slot table (no integer division in the hot loops), running-window state in
-//     registers (statically indexed), column reflection only in edge strips, and the coarse terms
-//     evaluated as one f64 FMA between row-interpolated neighbours.
+//     enough at the edges).  Same arithmetic as fused_kernel.
+//
+//   ring   : the NB+2R+1 DEM rows one batch needs, filled with cp.async (LDGSTS).  The rows of batch
+//            b+1 are issued as soon as the last vertical pass of batch b has consumed the rows they
+//            replace, so the copy overlaps the horizontal passes, the coarse terms and the stores.
+//   vphase : thread = column; exact f64 running window sum down the rows (state in registers across
+//            batches).  The mean is rounded to the f32 grid WITHOUT leaving f64 (add/subtract
+//            2^(e+29): RN-even at 24 bits == scipy's f32 store after axis 0) and kept as f64 in
+//            shared memory, so the horizontal pass needs no f32->f64 conversions (conversions run at
+//            1/4 rate on B200 and were the top stall reason).
+//   hphase : thread = (row, SEG-column segment); lanes of a warp = different rows (odd row stride ->
+//            conflict-free); f64 sliding sum along the row; f32 rounding (scipy's store after axis 1);
+//            weighted difference accumulated in f32 in list order.
+//   coarse : align-corners bilinear tap of the decimated mean (one f64 FMA per pixel; column
+//            fractions tabulated once per CTA).
+//   output : staged through shared memory -> coalesced stores (f32 / i16 / u8 encoding fused).
+//   NaN    : batches whose ring holds a NaN take the NaN-aware form (value and validity sums, f32
+//            planes); results are bit-identical to the dense form where no NaN is in reach.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int reflect1(int64_t i, int64_t n) {  // one mirror, valid for -n <= i < 2n
   return (int)(i < 0 ? -1 - i : (i >= n ? 2 * n - 1 - i : i));
@@ -602,10 +616,25 @@ __device__ __forceinline__ int col_slot(int j, int x0, int cs0, int W) {  // str
   return (int)(gx - cs0);
 }
 
-template <bool EDGE>
-__device__ __forceinline__ void hphase_box(const float* __restrict__ vrow, const unsigned char* __restrict__ crow,
-                                           const float* __restrict__ xrow, int R, int r, int hj0, int hjn, int x0,
-                                           int cs0, int W, bool nanmode, float weight, bool first, float* acc) {
+// round an f64 to the nearest f32-representable value (ties to even), staying in f64
+__device__ __forceinline__ double round_to_f32_grid(double q) {
+  int hi = __double2hiint(q);
+  double m = __hiloint2double((hi & 0xfff00000) + (29 << 20), 0);
+  return (q + m) - m;
+}
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// generic horizontal pass (edge strips, partial segments, NaN mode).  PLANE = double (dense) or float.
+template <bool EDGE, int SEG, typename PLANE>
+__device__ __forceinline__ void hphase_generic(const PLANE* __restrict__ vrow, const unsigned char* __restrict__ crow,
+                                               const float* xr, int r, int hj0, int hjn, int x0, int cs0, int W,
+                                               bool nanmode, float weight, float* acc) {
   const double inv = 1.0 / (double)(2 * r + 1);
   const double n = (double)(2 * r + 1);
   const float nf32 = (float)(2 * r + 1);
@@ -616,7 +645,7 @@ __device__ __forceinline__ void hphase_box(const float* __restrict__ vrow, const
     if (nanmode) sw += (double)((float)crow[sidx] / nf32);
   }
 #pragma unroll
-  for (int jj = 0; jj < FK_SEG; ++jj) {
+  for (int jj = 0; jj < SEG; ++jj) {
     if (jj < hjn) {
       const int j = hj0 + jj;
       float mean;
@@ -625,10 +654,9 @@ __device__ __forceinline__ void hphase_box(const float* __restrict__ vrow, const
         float den = (float)div_by_count(sw, n, inv);
         mean = den > 0.f ? mean / den : 0.f;
       } else {
-        mean = (float)(sv * inv);  // see DESIGN.md: the rounded product already rounds like the exact quotient
+        mean = (float)(sv * inv);
       }
-      float term = weight * (xrow[R + j] - mean);
-      acc[jj] = first ? term : acc[jj] + term;
+      acc[jj] = acc[jj] + weight * (xr[jj] - mean);
       if (jj + 1 < hjn) {
         int sin_ = col_slot<EDGE>(j + r + 1, x0, cs0, W), sout = col_slot<EDGE>(j - r, x0, cs0, W);
         sv += (double)vrow[sin_] - (double)vrow[sout];
@@ -638,40 +666,25 @@ __device__ __forceinline__ void hphase_box(const float* __restrict__ vrow, const
   }
 }
 
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-// Streaming kernel, fast variant.  One CTA = one strip of FK_TW output columns x one band of rows.
-//   ring   : the last NB+2R+1 (+NB prefetched) DEM rows of the strip, filled with cp.async (LDGSTS);
-//            the rows of batch b+1 are in flight while batch b is being computed;
-//   vphase : thread = column; exact f64 running window sum down the rows (state lives in registers
-//            across batches); one f32 rounding per output (scipy's axis-0 rounding point);
-//   hphase : thread = (row, 24-column segment), lanes of a warp = 32 different rows (odd row stride ->
-//            conflict-free); f64 sliding sum along the row; second f32 rounding; weighted difference
-//            accumulated in f32 in list order;
-//   coarse : align-corners bilinear tap of the decimated mean (one f64 FMA per pixel);
-//   output : staged through shared memory -> coalesced stores (f32 / i16 / u8 encoding fused).
+template <int NB>
 __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p) {
+  constexpr int NSEG = FK_THREADS / NB;
+  constexpr int SEG = FK_TW / NSEG;
+  static_assert(SEG * NSEG == FK_TW, "segments must tile the strip");
   extern __shared__ __align__(16) unsigned char smraw[];
   const int R = p.R;
   const int SW = FK_TW + 2 * R;
   const int SWp = SW | 1;
-  const int NRING = FK_NB + 2 * R + 1;   // rows one batch needs
-  const int NRT = p.ring_rows;           // rows the ring holds (NRING, or NRING + NB with prefetch)
-  const bool prefetch = NRT >= NRING + FK_NB;
-  float* ring = reinterpret_cast<float*>(smraw);
-  float* vplane = ring + (size_t)NRT * SWp;
-  unsigned char* cplane = reinterpret_cast<unsigned char*>(vplane + (size_t)FK_NB * SWp);
-  // byte offsets from the (16-byte aligned) base: tables start on 16-byte boundaries
-  const size_t off_c = ((size_t)NRT * SWp + (size_t)FK_NB * SWp) * 4;
-  const size_t off_slot = (off_c + (size_t)FK_NB * SWp + 15) / 16 * 16;
+  const int NRING = NB + 2 * R + 1;
+  // layout (bytes from the 16-byte aligned base): ring f32 | plane (f64, or f32 + u8 counts) | tables
+  const size_t off_plane = ((size_t)NRING * SWp * 4 + 15) / 16 * 16;
+  const size_t off_slot = off_plane + (size_t)NB * SWp * 8;
   const size_t off_tc = (off_slot + (size_t)(NRING + 1) * 4 + 15) / 16 * 16;
-  int* slot_tab = reinterpret_cast<int*>(smraw + off_slot);  // NRING+1 row offsets
+  float* ring = reinterpret_cast<float*>(smraw);
+  double* plane64 = reinterpret_cast<double*>(smraw + off_plane);
+  float* plane32 = reinterpret_cast<float*>(smraw + off_plane);
+  unsigned char* cplane = smraw + off_plane + (size_t)NB * SWp * 4;
+  int* slot_tab = reinterpret_cast<int*>(smraw + off_slot);
   double* tctab = reinterpret_cast<double*>(smraw + off_tc);
 
   const int tid = threadIdx.x;
@@ -691,11 +704,14 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
   int rc[FK_MAXF];
 #pragma unroll
   for (int k = 0; k < FK_MAXF; ++k) { rs[k] = 0.0; rc[k] = 0; }
+  int last_fused = -1;
+  for (int t = 0; t < p.n_terms; ++t)
+    if (p.terms[t].kind == TERM_BOX_FUSED) last_fused = t;
 
-  const int hi = tid % FK_NB;
-  const int hg = tid / FK_NB;
-  const int hj0 = hg * FK_SEG;
-  int hjn = (hj0 + FK_SEG <= FK_TW) ? FK_SEG : (FK_TW - hj0 > 0 ? FK_TW - hj0 : 0);
+  const int hi = tid % NB;
+  const int hg = tid / NB;
+  const int hj0 = hg * SEG;
+  int hjn = SEG;
   if (x0 + hj0 + hjn > W) hjn = (W - x0 - hj0 > 0) ? (W - x0 - hj0) : 0;
 
   // Column coordinates of the coarse levels are the same for every row of the strip: the fraction
@@ -717,7 +733,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
         tctab[l * FK_TW + j] = ci - fl;
       }
       int prev = 0;
-      for (int jj = 0; jj < FK_SEG; ++jj) {
+#pragma unroll
+      for (int jj = 0; jj < SEG; ++jj) {
         int c = (int)floor((double)(x0 + hj0 + jj) * cs);
         if (c > gwm1) c = gwm1;
         if (jj == 0) lv_c0[l] = c;
@@ -727,17 +744,17 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
     }
   }
 
-  // rows are stored at slot (row - row_org) mod NRT
+  // rows live at ring slot (row - row_org) mod NRING
   const int64_t row_org = yb0 - R < 0 ? 0 : yb0 - R;
-  auto need_hi_of = [&](int64_t yy) { return yy + FK_NB + R >= H ? H - 1 : yy + FK_NB + R; };
+  auto need_hi_of = [&](int64_t yy) { return yy + NB + R >= H ? H - 1 : yy + NB + R; };
   auto issue_rows = [&](int64_t from, int64_t to) {   // cp.async rows [from, to] of this thread's column
-    if (vc < SW && vgx >= 0 && vgx < W && from <= to) {
-      int sl = (int)((from - row_org) % NRT);
+    if (vcol_ok && from <= to) {
+      int sl = (int)((from - row_org) % NRING);
       const float* src = p.dem + from * p.ld_in + vgx;
       for (int64_t row = from; row <= to; ++row) {
         cp_async4(ring + (size_t)sl * SWp + vc, src);
         src += p.ld_in;
-        if (++sl == NRT) sl = 0;
+        if (++sl == NRING) sl = 0;
       }
     }
   };
@@ -747,37 +764,34 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
   issue_rows(row_org, need_hi_of(yb0));
   cp_async_commit();
 
-  for (int64_t y = yb0; y < yb1; y += FK_NB) {
+  for (int64_t y = yb0; y < yb1; y += NB) {
     const int64_t need_hi = need_hi_of(y);
-    const int64_t prev_hi = (y == yb0) ? row_org - 1 : need_hi_of(y - FK_NB);
-    __syncthreads();   // every warp is done with batch b-1: its oldest rows and vplane may be reused
-    if (prefetch) { if (y + FK_NB < yb1) issue_rows(need_hi + 1, need_hi_of(y + FK_NB)); }
-    else if (y > yb0) issue_rows(prev_hi + 1, need_hi);
-    cp_async_commit();
-    if (prefetch) cp_async_wait<1>(); else cp_async_wait<0>();
+    const int64_t prev_hi = (y == yb0) ? row_org - 1 : need_hi_of(y - NB);
+    cp_async_wait_all();
     // slot table: entry (d + R + 1) = SWp * ring slot of (mirrored) row y + d, d in [-R-1, NB+R]
     for (int e = tid; e <= NRING; e += FK_THREADS) {
       int d = e - R - 1;
       int dd = reflect1(y + d, H) - (int)y;
-      int sl = (base + dd) % NRT;
-      if (sl < 0) sl += NRT;
+      int sl = (base + dd) % NRING;
+      if (sl < 0) sl += NRING;
       slot_tab[e] = sl * SWp;
     }
-    __syncthreads();   // this batch's rows (all threads' cp.async) and the slot table are visible
+    __syncthreads();   // this batch's rows (every thread's cp.async) and the slot table are visible
     int my_nan = 0;
     if (vcol_ok) {
-      int sl = (int)((prev_hi + 1 - row_org) % NRT);
+      int sl = (int)((prev_hi + 1 - row_org) % NRING);
       for (int64_t row = prev_hi + 1; row <= need_hi; ++row) {
         float v = ring[(size_t)sl * SWp + vc];
         my_nan |= (v != v);
-        if (++sl == NRT) sl = 0;
+        if (++sl == NRING) sl = 0;
       }
     }
     const int any = __syncthreads_or(my_nan);
     nan_hist = (y == yb0) ? (any ? 0x3fu : 0u) : ((nan_hist << 1) | (any ? 1u : 0u));
     const bool nanmode = (nan_hist & 0x3fu) != 0;
-    const int nrows_b = (int)((yb1 - y) < FK_NB ? (yb1 - y) : FK_NB);
-    const bool interior_rows = (y - R - 1 >= 0) && (y + FK_NB + R + 1 < H);
+    const int nrows_b = (int)((yb1 - y) < NB ? (yb1 - y) : NB);
+    const bool interior_rows = (y - R - 1 >= 0) && (y + NB + R + 1 < H);
+    const bool more = y + NB < yb1;
 
     if (y == yb0 && vcol_ok) {
       int fk = 0;
@@ -800,13 +814,20 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
 
     const int64_t orow = y + hi;
     const bool hrow_ok = orow < yb1;
-    const float* xrow = ring + slot_tab[hi + R + 1];
-    const bool hfast = hrow_ok && !edge_strip && hjn == FK_SEG && !nanmode;
-    float acc[FK_SEG], xr[FK_SEG];
+    const bool hfast = hrow_ok && !edge_strip && hjn == SEG && !nanmode;
+    float acc[SEG], xr[SEG];
+    {
+      const float* xrow = ring + slot_tab[hi + R + 1];
 #pragma unroll
-    for (int jj = 0; jj < FK_SEG; ++jj) {
-      acc[jj] = 0.f;
-      xr[jj] = (hrow_ok && jj < hjn) ? xrow[R + hj0 + jj] : 0.f;
+      for (int jj = 0; jj < SEG; ++jj) {
+        acc[jj] = 0.f;
+        xr[jj] = (hrow_ok && jj < hjn) ? xrow[R + hj0 + jj] : 0.f;
+      }
+    }
+    if (last_fused < 0) {   // no vertical pass will read the ring: the next rows can start right away
+      __syncthreads();
+      if (more) issue_rows(need_hi + 1, need_hi_of(y + NB));
+      cp_async_commit();
     }
     int fk = 0;
     for (int t = 0; t < p.n_terms; ++t) {
@@ -820,50 +841,50 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
 #pragma unroll
           for (int k = 0; k < FK_MAXF; ++k) if (k == fk) { s = rs[k]; c = rc[k]; }
           if (!nanmode && interior_rows) {
-            // rows are consecutive ring slots: walk them with plain pointer increments, splitting the
-            // batch where the incoming or the outgoing row wraps around the ring
-            int sin = base + r + 1; if (sin >= NRT) sin -= NRT;
-            int sout = base - r; if (sout < 0) sout += NRT;
+            // rows are consecutive ring slots: plain pointer increments, splitting the batch where
+            // the incoming or the outgoing row wraps around the ring
+            int sin = base + r + 1; if (sin >= NRING) sin -= NRING;
+            int sout = base - r; if (sout < 0) sout += NRING;
             int i = 0;
             while (i < nrows_b) {
               int run = nrows_b - i;
-              if (NRT - sin < run) run = NRT - sin;
-              if (NRT - sout < run) run = NRT - sout;
+              if (NRING - sin < run) run = NRING - sin;
+              if (NRING - sout < run) run = NRING - sout;
               const float* pin = ring + (size_t)sin * SWp + vc;
               const float* pout = ring + (size_t)sout * SWp + vc;
-              float* pv = vplane + (size_t)i * SWp + vc;
+              double* pv = plane64 + (size_t)i * SWp + vc;
               int k = 0;
               for (; k + 4 <= run; k += 4) {
                 float a0 = pin[0], a1 = pin[SWp], a2 = pin[2 * SWp], a3 = pin[3 * SWp];
                 float b0 = pout[0], b1 = pout[SWp], b2 = pout[2 * SWp], b3 = pout[3 * SWp];
                 double d0 = (double)a0 - (double)b0, d1 = (double)a1 - (double)b1;
                 double d2 = (double)a2 - (double)b2, d3 = (double)a3 - (double)b3;
-                pv[0] = (float)(s * inv); s += d0;
-                pv[SWp] = (float)(s * inv); s += d1;
-                pv[2 * SWp] = (float)(s * inv); s += d2;
-                pv[3 * SWp] = (float)(s * inv); s += d3;
+                pv[0] = round_to_f32_grid(s * inv); s += d0;
+                pv[SWp] = round_to_f32_grid(s * inv); s += d1;
+                pv[2 * SWp] = round_to_f32_grid(s * inv); s += d2;
+                pv[3 * SWp] = round_to_f32_grid(s * inv); s += d3;
                 pin += 4 * SWp; pout += 4 * SWp; pv += 4 * SWp;
               }
               for (; k < run; ++k) {
-                pv[0] = (float)(s * inv);
+                pv[0] = round_to_f32_grid(s * inv);
                 s += (double)pin[0] - (double)pout[0];
                 pin += SWp; pout += SWp; pv += SWp;
               }
               i += run;
-              sin += run; if (sin >= NRT) sin -= NRT;
-              sout += run; if (sout >= NRT) sout -= NRT;
+              sin += run; if (sin >= NRING) sin -= NRING;
+              sout += run; if (sout >= NRING) sout -= NRING;
             }
           } else {
             const int* tin = slot_tab + (r + 1 + R + 1);
             const int* tout = slot_tab + (-r + R + 1);
             if (!nanmode) {
               for (int i = 0; i < nrows_b; ++i) {
-                vplane[i * SWp + vc] = (float)(s * inv);
+                plane64[i * SWp + vc] = round_to_f32_grid(s * inv);
                 s += (double)ring[tin[i] + vc] - (double)ring[tout[i] + vc];
               }
             } else {
               for (int i = 0; i < nrows_b; ++i) {
-                vplane[i * SWp + vc] = (float)div_by_count(s, n, inv);
+                plane32[i * SWp + vc] = (float)div_by_count(s, n, inv);
                 cplane[i * SWp + vc] = (unsigned char)c;
                 float vin = ring[tin[i] + vc];
                 float vout = ring[tout[i] + vc];
@@ -877,23 +898,33 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
           for (int k = 0; k < FK_MAXF; ++k) if (k == fk) { rs[k] = s; rc[k] = c; }
         }
         __syncthreads();
+        if (t == last_fused) {   // the ring rows this batch no longer needs are free: start the next copy
+          if (more) issue_rows(need_hi + 1, need_hi_of(y + NB));
+          cp_async_commit();
+        }
         if (hfast) {
-          const float* pl = vplane + hi * SWp + R + hj0 - r;   // leftmost tap of the first window
-          const float* pr = pl + 2 * r + 1;                    // first tap entering
+          const double* pl = plane64 + hi * SWp + R + hj0 - r;   // leftmost tap of the first window
+          const double* pr = pl + 2 * r + 1;                     // first tap entering
           double sv = 0.0;
-          for (int d = 0; d <= 2 * r; ++d) sv += (double)pl[d];
+          for (int d = 0; d <= 2 * r; ++d) sv += pl[d];
           const float wgt = T.weight;
 #pragma unroll
-          for (int jj = 0; jj < FK_SEG; ++jj) {
+          for (int jj = 0; jj < SEG; ++jj) {
             float mean = (float)(sv * inv);
             acc[jj] = acc[jj] + wgt * (xr[jj] - mean);
-            if (jj + 1 < FK_SEG) sv += (double)pr[jj] - (double)pl[jj];
+            if (jj + 1 < SEG) sv += pr[jj] - pl[jj];
           }
         } else if (hrow_ok && hjn > 0) {
-          const float* vrow = vplane + hi * SWp;
           const unsigned char* crow = cplane + hi * SWp;
-          if (edge_strip) hphase_box<true>(vrow, crow, xrow, R, r, hj0, hjn, x0, cs0, W, nanmode, T.weight, false, acc);
-          else hphase_box<false>(vrow, crow, xrow, R, r, hj0, hjn, x0, cs0, W, nanmode, T.weight, false, acc);
+          if (nanmode) {
+            const float* vrow = plane32 + hi * SWp;
+            if (edge_strip) hphase_generic<true, SEG, float>(vrow, crow, xr, r, hj0, hjn, x0, cs0, W, true, T.weight, acc);
+            else hphase_generic<false, SEG, float>(vrow, crow, xr, r, hj0, hjn, x0, cs0, W, true, T.weight, acc);
+          } else {
+            const double* vrow = plane64 + hi * SWp;
+            if (edge_strip) hphase_generic<true, SEG, double>(vrow, crow, xr, r, hj0, hjn, x0, cs0, W, false, T.weight, acc);
+            else hphase_generic<false, SEG, double>(vrow, crow, xr, r, hj0, hjn, x0, cs0, W, false, T.weight, acc);
+          }
         }
         __syncthreads();
         ++fk;
@@ -922,7 +953,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
           const float wgt = T.weight;
           const double* tcp = tctab + T.lvl * FK_TW + hj0;
 #pragma unroll
-          for (int jj = 0; jj < FK_SEG; ++jj) {
+          for (int jj = 0; jj < SEG; ++jj) {
             if (jj < hjn) {
               if ((adv >> jj) & 1u) {
                 ++c0;
@@ -940,32 +971,32 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
         if (hrow_ok && hjn > 0) {
           const float* prow = T.grid + orow * W;
 #pragma unroll
-          for (int jj = 0; jj < FK_SEG; ++jj)
+          for (int jj = 0; jj < SEG; ++jj)
             if (jj < hjn) acc[jj] = acc[jj] + T.weight * (xr[jj] - __ldg(prow + x0 + hj0 + jj));
         }
       }
     }
 
-    float* stage = vplane;
+    float* stage = plane32;   // NB x (FK_TW + 1) floats, inside the plane region
     if (hrow_ok && hjn > 0) {
       float* sp = stage + hi * (FK_TW + 1) + hj0;
       if (p.norm_mode == 1) {
         // v / s, correctly rounded: q = v*rinv, one FMA residual correction (Markstein); NaN stays NaN
-        const float sc = p.norm_scale, ri = p.norm_rinv;
+        const float sc = p.norm_scale, rinv = p.norm_rinv;
 #pragma unroll
-        for (int jj = 0; jj < FK_SEG; ++jj) {
+        for (int jj = 0; jj < SEG; ++jj) {
           if (jj < hjn) {
-            float q = acc[jj] * ri;
+            float q = acc[jj] * rinv;
             float rem = fmaf(-q, sc, acc[jj]);
-            sp[jj] = fmaf(rem, ri, q);
+            sp[jj] = fmaf(rem, rinv, q);
           }
         }
       } else if (p.norm_mode == 2) {
 #pragma unroll
-        for (int jj = 0; jj < FK_SEG; ++jj) if (jj < hjn) sp[jj] = (acc[jj] != acc[jj]) ? acc[jj] : 0.f;
+        for (int jj = 0; jj < SEG; ++jj) if (jj < hjn) sp[jj] = (acc[jj] != acc[jj]) ? acc[jj] : 0.f;
       } else {
 #pragma unroll
-        for (int jj = 0; jj < FK_SEG; ++jj) if (jj < hjn) sp[jj] = acc[jj];
+        for (int jj = 0; jj < SEG; ++jj) if (jj < hjn) sp[jj] = acc[jj];
       }
     }
     __syncthreads();
@@ -987,20 +1018,30 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
         }
       }
     }
-    base += FK_NB;
-    if (base >= NRT) base -= NRT;
+    __syncthreads();   // the plane (staging) is free again before the next batch's vertical pass
+    base += NB;
+    if (base >= NRING) base -= NRING;
   }
-  cp_async_wait<0>();
+  cp_async_wait_all();
 }
 
-static size_t fused_smem_bytes(int R, int extra_rows = 0, int n_lvls = 0) {
+template <int NB>
+static size_t fused_fast_smem_bytes(int R, int n_lvls) {
   size_t SWp = (size_t)((FK_TW + 2 * R) | 1);
-  size_t nring = FK_NB + 2 * R + 1 + extra_rows;
+  size_t nring = NB + 2 * R + 1;
+  size_t off_plane = align_up(nring * SWp * 4, 16);
+  size_t off_slot = off_plane + (size_t)NB * SWp * 8;
+  size_t off_tc = align_up(off_slot + (nring + 1) * 4, 16);
+  return off_tc + (size_t)n_lvls * FK_TW * 8;
+}
+
+static size_t fused_smem_bytes(int R) {
+  size_t SWp = (size_t)((FK_TW + 2 * R) | 1);
+  size_t nring = FK_NB + 2 * R + 1;
   size_t vp = (size_t)FK_NB * SWp;
   size_t stage = (size_t)FK_NB * (FK_TW + 1);
   if (stage > vp) vp = stage;
-  return nring * SWp * 4 + vp * 4 + align_up((size_t)FK_NB * SWp, 16) + 16 + align_up((nring + 1) * 4, 16) + 16 +
-         (size_t)n_lvls * FK_TW * 8 + 16;
+  return nring * SWp * 4 + vp * 4 + align_up((size_t)FK_NB * SWp, 16);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1094,7 +1135,13 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
       d.grid = mean; d.gh = H; d.gw = W;
     }
   }
-  // bands: enough CTAs to fill the machine, few enough that the (2R+1)-row warm-up stays small
+  fp.n_lvls = plan.n_levels;
+  const bool fast_ok = H >= plan.fused_R + 2 && W >= plan.fused_R + 2 && W < (1 << 30) && !getenv("FSG_FORCE_GENERIC");
+  const size_t smem_cap = 227 * 1024;
+  int nb = 0;   // rows per batch of the fast kernel (0: general kernel)
+  if (fast_ok && fused_fast_smem_bytes<32>(plan.fused_R, plan.n_levels) <= smem_cap) nb = 32;
+  else if (fast_ok && fused_fast_smem_bytes<16>(plan.fused_R, plan.n_levels) <= smem_cap) nb = 16;
+  // bands: few enough that the (2R+1)-row warm-up per band stays small, enough CTAs to fill 148 SMs
   int64_t strips = (W + FK_TW - 1) / FK_TW;
   int64_t want_bands = (H + 1023) / 2048;
   if (want_bands < 1) want_bands = 1;
@@ -1106,19 +1153,15 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
   fp.band_rows = (int)band_rows;
   int64_t bands = (H + band_rows - 1) / band_rows;
   if (bands > 65535) return fail(FSG_E_UNSUPPORTED, "fsg_topousm_fast: raster too tall");
-  fp.n_lvls = plan.n_levels;
-  size_t smem = fused_smem_bytes(plan.fused_R, 0, plan.n_levels);
-  fp.ring_rows = FK_NB + 2 * plan.fused_R + 1;
-  if (fused_smem_bytes(plan.fused_R, FK_NB, plan.n_levels) <= 227 * 1024) {   // room to prefetch the next batch
-    smem = fused_smem_bytes(plan.fused_R, FK_NB, plan.n_levels);
-    fp.ring_rows += FK_NB;
-  }
-  const bool fast = H >= plan.fused_R + 2 && W >= plan.fused_R + 2 && W < (1 << 30) && !getenv("FSG_FORCE_GENERIC");
-  FSG_CUDA_OK(cudaFuncSetAttribute(fast ? fused_kernel_fast : fused_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)strips, (unsigned)bands);
+  size_t smem = nb == 32 ? fused_fast_smem_bytes<32>(plan.fused_R, plan.n_levels)
+                         : (nb == 16 ? fused_fast_smem_bytes<16>(plan.fused_R, plan.n_levels) : fused_smem_bytes(plan.fused_R));
+  if (nb == 32) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (nb == 16) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int slot = prof_begin(PROF_TOPOUSM_FUSED, s);
-  if (fast) fused_kernel_fast<<<grid, FK_THREADS, smem, s>>>(fp);
+  if (nb == 32) fused_kernel_fast<32><<<grid, FK_THREADS, smem, s>>>(fp);
+  else if (nb == 16) fused_kernel_fast<16><<<grid, FK_THREADS, smem, s>>>(fp);
   else fused_kernel<<<grid, FK_THREADS, smem, s>>>(fp);
   prof_end(slot, s);
   FSG_LAUNCH_OK();
