@@ -666,6 +666,30 @@ __device__ __forceinline__ void hphase_generic(const PLANE* __restrict__ vrow, c
   }
 }
 
+// bilinear taps of one coarse term along a thread's segment: A0/A1 are the row-interpolated coarse
+// values left/right of the current pixel; `adv` marks the pixels where the coarse column advances
+template <int SEG, bool FULL>
+__device__ __forceinline__ void coarse_taps(const float* __restrict__ g0, const float* __restrict__ g1, double wr0,
+                                            double tr, int c0, int c1, int gwm1, unsigned adv,
+                                            const double* __restrict__ tcp, double A0, double A1, float wgt,
+                                            const float* xr, float* acc, int hjn) {
+  double dA = A1 - A0;
+#pragma unroll
+  for (int jj = 0; jj < SEG; ++jj) {
+    if (FULL || jj < hjn) {
+      if ((adv >> jj) & 1u) {
+        ++c0;
+        c1 = c0 + 1 < gwm1 ? c0 + 1 : gwm1;
+        A0 = A1;
+        A1 = (double)__ldg(g0 + c1) * wr0 + (double)__ldg(g1 + c1) * tr;
+        dA = A1 - A0;
+      }
+      float mean = (float)fma(tcp[jj], dA, A0);
+      acc[jj] = acc[jj] + wgt * (xr[jj] - mean);
+    }
+  }
+}
+
 template <int NB>
 __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p) {
   constexpr int NSEG = FK_THREADS / NB;
@@ -747,14 +771,25 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
   // rows live at ring slot (row - row_org) mod NRING
   const int64_t row_org = yb0 - R < 0 ? 0 : yb0 - R;
   auto need_hi_of = [&](int64_t yy) { return yy + NB + R >= H ? H - 1 : yy + NB + R; };
+  const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring) + 4u * (unsigned)vc;
+  const unsigned row_bytes = 4u * (unsigned)SWp;
   auto issue_rows = [&](int64_t from, int64_t to) {   // cp.async rows [from, to] of this thread's column
     if (vcol_ok && from <= to) {
       int sl = (int)((from - row_org) % NRING);
+      int n = (int)(to - from + 1);
       const float* src = p.dem + from * p.ld_in + vgx;
-      for (int64_t row = from; row <= to; ++row) {
-        cp_async4(ring + (size_t)sl * SWp + vc, src);
-        src += p.ld_in;
-        if (++sl == NRING) sl = 0;
+      while (n > 0) {
+        int run = NRING - sl < n ? NRING - sl : n;   // rows until the ring wraps
+        unsigned sa = ring_sa + (unsigned)sl * row_bytes;
+#pragma unroll 4
+        for (int k = 0; k < run; ++k) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src) : "memory");
+          sa += row_bytes;
+          src += p.ld_in;
+        }
+        n -= run;
+        sl += run;
+        if (sl >= NRING) sl = 0;
       }
     }
   };
@@ -780,11 +815,18 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
     int my_nan = 0;
     if (vcol_ok) {
       int sl = (int)((prev_hi + 1 - row_org) % NRING);
-      for (int64_t row = prev_hi + 1; row <= need_hi; ++row) {
-        float v = ring[(size_t)sl * SWp + vc];
-        my_nan |= (v != v);
-        if (++sl == NRING) sl = 0;
+      int n = (int)(need_hi - prev_hi);
+      float probe = 0.f;   // NaN is sticky under addition of 0*x: one FFMA-free test at the end
+      while (n > 0) {
+        int run = NRING - sl < n ? NRING - sl : n;
+        const float* pp = ring + (size_t)sl * SWp + vc;
+#pragma unroll 4
+        for (int k = 0; k < run; ++k) { probe += pp[0] * 0.f; pp += SWp; }
+        n -= run;
+        sl += run;
+        if (sl >= NRING) sl = 0;
       }
+      my_nan = (probe != probe);
     }
     const int any = __syncthreads_or(my_nan);
     nan_hist = (y == yb0) ? (any ? 0x3fu : 0u) : ((nan_hist << 1) | (any ? 1u : 0u));
@@ -949,23 +991,12 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
           int c1 = c0 + 1 < gwm1 ? c0 + 1 : gwm1;
           double A0 = (double)__ldg(g0 + c0) * wr0 + (double)__ldg(g1 + c0) * tr;
           double A1 = (double)__ldg(g0 + c1) * wr0 + (double)__ldg(g1 + c1) * tr;
-          double dA = A1 - A0;
           const float wgt = T.weight;
           const double* tcp = tctab + T.lvl * FK_TW + hj0;
-#pragma unroll
-          for (int jj = 0; jj < SEG; ++jj) {
-            if (jj < hjn) {
-              if ((adv >> jj) & 1u) {
-                ++c0;
-                c1 = c0 + 1 < gwm1 ? c0 + 1 : gwm1;
-                A0 = A1;
-                A1 = (double)__ldg(g0 + c1) * wr0 + (double)__ldg(g1 + c1) * tr;
-                dA = A1 - A0;
-              }
-              float mean = (float)fma(tcp[jj], dA, A0);
-              acc[jj] = acc[jj] + wgt * (xr[jj] - mean);
-            }
-          }
+          if (hjn == SEG)
+            coarse_taps<SEG, true>(g0, g1, wr0, tr, c0, c1, gwm1, adv, tcp, A0, A1, wgt, xr, acc, hjn);
+          else
+            coarse_taps<SEG, false>(g0, g1, wr0, tr, c0, c1, gwm1, adv, tcp, A0, A1, wgt, xr, acc, hjn);
         }
       } else {
         if (hrow_ok && hjn > 0) {
