@@ -43,6 +43,14 @@ _SIGNATURES = {
     "fsg_topousm_fast_workspace_bytes": (C.c_size_t, [_L, _L, C.POINTER(C.c_int32), _I, _D]),
     "fsg_topousm_fast": (_I, [_P, _P, _L, _L, _L, _L, C.POINTER(C.c_int32), C.POINTER(C.c_float), _I,
                               _D, _D, C.POINTER(Encode), _P, C.c_size_t, _P]),
+    "fsg_topousm_plan": (_I, [C.POINTER(C.c_int32), _I, _D, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                              C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "fsg_pyramid_band": (_I, [_P, _L, _L, _L, C.POINTER(C.c_int32), _I, C.POINTER(_P), _P, _P]),
+    "fsg_grid_mean_band_workspace_bytes": (C.c_size_t, [_L, _L]),
+    "fsg_grid_mean_band": (_I, [_P, _L, _L, _L, _L, _L, _I, _L, _L, _P, _P, C.c_size_t, _P]),
+    "fsg_topousm_fused_band": (_I, [_P, _L, _L, _L, _L, _L, _P, _L, _L, _L, C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_float), _I, _D, C.POINTER(_P), C.POINTER(_L), C.POINTER(_L),
+                                    _D, C.POINTER(Encode), _P]),
     "fsg_topousm_large_part": (_I, [_P, _P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _L, _L, _L, _D, _P]),
     "fsg_openness": (_I, [_P, _P, C.POINTER(Window), _I, _I, _I, _D, _D, _D, _D, _D, C.POINTER(Encode), _P]),
     "fsg_decimate_workspace_bytes": (C.c_size_t, [_L, _L, _I]),
@@ -56,6 +64,12 @@ _SIGNATURES = {
     "fsg_order_stats_workspace_bytes": (C.c_size_t, []),
     "fsg_order_stats": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, _L, _I, _I,
                              _P, _P, C.c_size_t, _P]),
+    "fsg_grid_void_fill": (_I, [_P, _L, _L, _P, C.c_size_t, _P]),
+    "fsg_key_histogram": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, _I, C.c_uint32,
+                               C.c_uint32, _I, _I, _P, _P, _P]),
+    "fsg_key_rank_info": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, C.c_uint32, _I, _I,
+                               _P, _P]),
+    "fsg_key_to_float": (C.c_float, [C.c_uint32, _I]),
     "fsg_synth_dem": (_I, [_P, _L, _L, _L, _L, _L, C.c_uint64, _I, _P]),
 }
 

@@ -7,27 +7,28 @@ constexpr int A0_CHUNK = 128;  // rows per thread in the axis-0 running-sum pass
 constexpr int A1_CW = 256;     // output columns per CTA in the axis-1 pass
 
 // ---------------------------------------------------------------- box, axis 0 (running sums)
-__global__ void __launch_bounds__(128) box_axis0_kernel(Grid g, int size, float* __restrict__ tv, float* __restrict__ tw) {
+__global__ void __launch_bounds__(128) box_axis0_kernel(Grid g, int size, float* __restrict__ tv, float* __restrict__ tw,
+                                                        int64_t oy0, int64_t oh) {
   int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= g.w) return;
-  int64_t y0 = (int64_t)blockIdx.y * A0_CHUNK;
-  int64_t y1 = y0 + A0_CHUNK < g.h ? y0 + A0_CHUNK : g.h;
+  int64_t y0 = oy0 + (int64_t)blockIdx.y * A0_CHUNK;
+  int64_t y1 = y0 + A0_CHUNK < oy0 + oh ? y0 + A0_CHUNK : oy0 + oh;
   const int lo = size / 2, hi = size - 1 - lo;
   const double n = (double)size, inv = 1.0 / n;
   const float nf = (float)size;
   double s = 0.0;
   int cnt = 0;
   for (int k = -lo; k <= hi; ++k) {
-    float v = g.src[reflect_index(y0 + k, g.h) * g.ld + x];
+    float v = g.src[(reflect_index(y0 + k, g.h) - g.row_off) * g.ld + x];
     bool ok = v == v;
     s += ok ? (double)v : 0.0;
     cnt += ok;
   }
   for (int64_t y = y0; y < y1; ++y) {
-    tv[y * g.w + x] = (float)div_by_count(s, n, inv);
-    tw[y * g.w + x] = (float)cnt / nf;
-    float vin = g.src[reflect_index(y + hi + 1, g.h) * g.ld + x];
-    float vout = g.src[reflect_index(y - lo, g.h) * g.ld + x];
+    tv[(y - oy0) * g.w + x] = (float)div_by_count(s, n, inv);
+    tw[(y - oy0) * g.w + x] = (float)cnt / nf;
+    float vin = g.src[(reflect_index(y + hi + 1, g.h) - g.row_off) * g.ld + x];
+    float vout = g.src[(reflect_index(y - lo, g.h) - g.row_off) * g.ld + x];
     bool oin = vin == vin, oout = vout == vout;
     s += (oin ? (double)vin : 0.0) - (oout ? (double)vout : 0.0);
     cnt += (int)oin - (int)oout;
@@ -91,21 +92,32 @@ __global__ void __launch_bounds__(256) box_axis1_kernel(const float* __restrict_
 
 // ---------------------------------------------------------------- gaussian passes (direct)
 __global__ void gauss_taps_kernel(double sigma, int radius, double* w) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double s2 = sigma * sigma, tot = 0.0;
-  for (int x = -radius; x <= radius; ++x) tot += exp(-0.5 / s2 * (double)x * (double)x);
-  for (int x = 0; x <= radius; ++x) w[x] = exp(-0.5 / s2 * (double)x * (double)x) / tot;
+  // one block; the normalising sum is accumulated by thread 0 in index order (deterministic)
+  __shared__ double tot;
+  double s2 = sigma * sigma;
+  for (int x = threadIdx.x; x <= radius; x += blockDim.x) w[x] = exp(-0.5 / s2 * (double)x * (double)x);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int x = radius; x >= 1; --x) t += w[x];   // phi(-r..-1)
+    t += w[0];
+    for (int x = 1; x <= radius; ++x) t += w[x];
+    tot = t;
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x <= radius; x += blockDim.x) w[x] = w[x] / tot;
 }
 
 __global__ void __launch_bounds__(256) gauss_axis0_kernel(Grid g, const double* __restrict__ taps, int radius,
                                                           float* __restrict__ tv, float* __restrict__ tw,
-                                                          const int* run_flag) {
+                                                          const int* run_flag, int64_t oy0, int64_t oh) {
   if (run_flag && *run_flag == 0) return;
   int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t y = (int64_t)blockIdx.y + (int64_t)blockIdx.z * 32768;
-  if (x >= g.w || y >= g.h) return;
+  int64_t yl = (int64_t)blockIdx.y + (int64_t)blockIdx.z * 32768;
+  if (x >= g.w || yl >= oh) return;
+  const int64_t y = oy0 + yl;
   auto at = [&](int64_t yy, double* ok) {
-    float v = g.src[clamp_index(yy, g.h) * g.ld + x];
+    float v = g.src[(clamp_index(yy, g.h) - g.row_off) * g.ld + x];
     bool good = v == v;
     *ok = good ? 1.0 : 0.0;
     return good ? (double)v : 0.0;
@@ -119,8 +131,8 @@ __global__ void __launch_bounds__(256) gauss_axis0_kernel(Grid g, const double* 
     sv += (va + vb) * taps[j];
     sw += (oa + ob) * taps[j];
   }
-  tv[y * g.w + x] = (float)sv;
-  tw[y * g.w + x] = (float)sw;
+  tv[yl * g.w + x] = (float)sv;
+  tw[yl * g.w + x] = (float)sw;
 }
 
 __global__ void __launch_bounds__(256) gauss_axis1_kernel(const float* __restrict__ tv, const float* __restrict__ tw,
@@ -153,9 +165,10 @@ __global__ void __launch_bounds__(256) gauss_axis1_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------- launchers
-int launch_box_axis0(const Grid& g, int size, float* tv, float* tw, cudaStream_t s) {
-  dim3 grid((unsigned)((g.w + 127) / 128), (unsigned)((g.h + A0_CHUNK - 1) / A0_CHUNK));
-  box_axis0_kernel<<<grid, 128, 0, s>>>(g, size, tv, tw);
+int launch_box_axis0(const Grid& g, int size, float* tv, float* tw, int64_t oy0, int64_t oh, cudaStream_t s) {
+  if (oh <= 0) return FSG_OK;
+  dim3 grid((unsigned)((g.w + 127) / 128), (unsigned)((oh + A0_CHUNK - 1) / A0_CHUNK));
+  box_axis0_kernel<<<grid, 128, 0, s>>>(g, size, tv, tw, oy0, oh);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }
@@ -183,15 +196,16 @@ int launch_box_axis1(const float* tv, const float* tw, int64_t h, int64_t w, int
 }
 
 int launch_gauss_taps(double sigma, int radius, double* taps_dev, cudaStream_t s) {
-  gauss_taps_kernel<<<1, 32, 0, s>>>(sigma, radius, taps_dev);
+  gauss_taps_kernel<<<1, 256, 0, s>>>(sigma, radius, taps_dev);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }
 
 int launch_gauss_axis0(const Grid& g, const double* taps_dev, int radius, float* tv, float* tw, const int* run_flag,
-                       cudaStream_t s) {
-  dim3 grid((unsigned)((g.w + 255) / 256), (unsigned)(g.h < 32768 ? g.h : 32768), (unsigned)((g.h + 32767) / 32768));
-  gauss_axis0_kernel<<<grid, 256, 0, s>>>(g, taps_dev, radius, tv, tw, run_flag);
+                       int64_t oy0, int64_t oh, cudaStream_t s) {
+  if (oh <= 0) return FSG_OK;
+  dim3 grid((unsigned)((g.w + 255) / 256), (unsigned)(oh < 32768 ? oh : 32768), (unsigned)((oh + 32767) / 32768));
+  gauss_axis0_kernel<<<grid, 256, 0, s>>>(g, taps_dev, radius, tv, tw, run_flag, oy0, oh);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }

@@ -15,14 +15,16 @@
 namespace fsg {
 
 struct Grid {
-  const float* src;  // input grid (may hold NaN)
-  int64_t h, w, ld;
+  const float* src;  // input grid (may hold NaN); src row 0 is GLOBAL row `row_off`
+  int64_t h, w, ld;  // h = GLOBAL number of rows (edge rules), w columns, ld row stride
+  int64_t row_off = 0;  // row-band shards: global row of src[0]; the band must hold every row the
+                        // pass touches after mirroring / clamping at the GLOBAL edges
 };
 
-// pass A (axis 0).  tv/tw: f32 planes h x w (ld = w).
-int launch_box_axis0(const Grid& g, int size, float* tv, float* tw, cudaStream_t s);
+// pass A (axis 0) for global output rows [oy0, oy0+oh); tv/tw: f32 planes oh x w (ld = w).
+int launch_box_axis0(const Grid& g, int size, float* tv, float* tw, int64_t oy0, int64_t oh, cudaStream_t s);
 int launch_gauss_axis0(const Grid& g, const double* taps_dev, int radius, float* tv, float* tw, const int* run_flag,
-                       cudaStream_t s);
+                       int64_t oy0, int64_t oh, cudaStream_t s);
 
 // pass B (axis 1) + combine.  mode 0: mean = tw>0 ? tv/tw : 0 -> out
 //                            mode 1 (void fill, _nan_utils.py:655-667): where isnan(orig) & (sw > 0.5):

@@ -160,6 +160,53 @@ __global__ void init_state_kernel(SelState* st, unsigned int* hist, unsigned lon
   }
 }
 
+// by-value variants for the staged (distributed) selection
+__global__ void __launch_bounds__(256) hist_kernel_v(Chunks c, int level, int take_abs, int finite_only,
+                                                     unsigned int prefix, unsigned int mask, unsigned int* hist,
+                                                     unsigned long long* count) {
+  __shared__ unsigned int sh[2048];
+  for (int i = threadIdx.x; i < 2048; i += 256) sh[i] = 0;
+  __syncthreads();
+  const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
+  const unsigned int bins_mask = level == 2 ? 1023u : 2047u;
+  const int64_t total = c.start[c.n];
+  unsigned long long local = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    unsigned int key;
+    if (!sample_key(fetch(c, i), take_abs, finite_only, &key)) continue;
+    ++local;
+    if ((key & mask) == prefix) atomicAdd(&sh[(key >> shift) & bins_mask], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += 256)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+  for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
+__global__ void __launch_bounds__(256) rank_info_kernel(Chunks c, int take_abs, int finite_only, unsigned int kk,
+                                                        unsigned long long* out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { /* out[] is pre-set by init below */ }
+  const int64_t total = c.start[c.n];
+  unsigned long long le = 0;
+  unsigned int mn = 0xffffffffu;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    unsigned int key;
+    if (!sample_key(fetch(c, i), take_abs, finite_only, &key)) continue;
+    if (key <= kk) ++le;
+    else if (key < mn) mn = key;
+  }
+  for (int o = 16; o; o >>= 1) {
+    le += __shfl_down_sync(0xffffffffu, le, o);
+    unsigned int other = __shfl_down_sync(0xffffffffu, mn, o);
+    mn = other < mn ? other : mn;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (le) atomicAdd(&out[0], le);
+    atomicMin(&out[1], (unsigned long long)mn);
+  }
+}
+
 }  // namespace fsg
 
 extern "C" {
@@ -212,6 +259,73 @@ int fsg_order_stats(const float* const* chunks_host, const int64_t* rows_host, c
   finish_kernel<<<1, 32, 0, s>>>(st, take_abs, result_dev, 0ull);
   FSG_LAUNCH_OK();
   return FSG_OK;
+}
+
+
+/* ---- staged selection for distributed (multi-GPU) percentiles ---------------------------------
+ * Every rank histograms the keys of its own chunks that match (key & mask) == prefix; the host
+ * all-reduces the 2048 bins, picks the bucket that holds the wanted rank and recurses (3 levels:
+ * bits 31..21, 20..10, 9..0).  fsg_key_rank_info then returns #keys <= key and the smallest larger
+ * key, which the host all-reduces (sum / min) to obtain a[k+1].  Keys: take_abs -> bits of |x|;
+ * otherwise the order-preserving signed mapping.  fsg_key_to_float converts a key back. */
+int fsg_key_histogram(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                      const int64_t* ld_host, int n_chunks, int level, uint32_t prefix, uint32_t mask, int take_abs,
+                      int finite_only, uint32_t* hist_dev /* 2048 */, uint64_t* count_dev, void* stream) {
+  using namespace fsg;
+  if (n_chunks < 0 || n_chunks > MAX_CHUNKS || level < 0 || level > 2 || !hist_dev || !count_dev)
+    return fail(FSG_E_INVALID, "fsg_key_histogram: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  FSG_CUDA_OK(cudaMemsetAsync(hist_dev, 0, 2048 * sizeof(uint32_t), s));
+  FSG_CUDA_OK(cudaMemsetAsync(count_dev, 0, sizeof(uint64_t), s));
+  if (n_chunks == 0) return FSG_OK;
+  Chunks c{};
+  c.n = n_chunks;
+  int64_t tot = 0;
+  for (int i = 0; i < n_chunks; ++i) {
+    c.ptr[i] = chunks_host[i]; c.rows[i] = rows_host[i]; c.cols[i] = cols_host[i]; c.ld[i] = ld_host[i];
+    c.start[i] = tot;
+    tot += rows_host[i] * cols_host[i];
+  }
+  c.start[n_chunks] = tot;
+  if (tot == 0) return FSG_OK;
+  int blocks = (int)((tot + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  hist_kernel_v<<<blocks, 256, 0, s>>>(c, level, take_abs, finite_only, prefix, mask, hist_dev,
+                                       (unsigned long long*)count_dev);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_key_rank_info(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                      const int64_t* ld_host, int n_chunks, uint32_t key, int take_abs, int finite_only,
+                      uint64_t* out_dev /* [0] = #keys <= key, [1] = min key > key (0xffffffff if none) */, void* stream) {
+  using namespace fsg;
+  if (n_chunks < 0 || n_chunks > MAX_CHUNKS || !out_dev) return fail(FSG_E_INVALID, "fsg_key_rank_info: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  Chunks c{};
+  c.n = n_chunks;
+  int64_t tot = 0;
+  for (int i = 0; i < n_chunks; ++i) {
+    c.ptr[i] = chunks_host[i]; c.rows[i] = rows_host[i]; c.cols[i] = cols_host[i]; c.ld[i] = ld_host[i];
+    c.start[i] = tot;
+    tot += rows_host[i] * cols_host[i];
+  }
+  c.start[n_chunks] = tot;
+  int blocks = (int)((tot + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  const unsigned long long init[2] = {0ull, 0xffffffffull};
+  FSG_CUDA_OK(cudaMemcpyAsync(out_dev, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  rank_info_kernel<<<blocks, 256, 0, s>>>(c, take_abs, finite_only, key, (unsigned long long*)out_dev);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+float fsg_key_to_float(uint32_t key, int take_abs) {
+  uint32_t b = take_abs ? key : ((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
 }
 
 }  // extern "C"

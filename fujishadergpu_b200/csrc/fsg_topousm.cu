@@ -321,12 +321,15 @@ struct DevTerm {
   int64_t gh, gw;    // coarse dims
   double rscale, cscale;  // (gh-1)/(H-1), (gw-1)/(W-1)
   int lvl;                // coarse terms: index of the pyramid level (column-fraction table)
+  int64_t grow0;          // global row of grid row 0 (row-band shards hold a window of the grid)
 };
 
 struct FusedParams {
   const float* dem;
   void* out;
-  int64_t H, W, ld_in, ld_out;
+  int64_t H, W, ld_in, ld_out;   // H, W: GLOBAL raster size (edge rules, zoom mapping)
+  int64_t dem_row0, dem_rows;    // global row of dem[0] and rows held (row-band shards; 0, H for a whole raster)
+  int64_t out_row0, out_rows;    // global rows to produce; out[0] is row out_row0
   int n_terms;
   DevTerm terms[MAX_TERMS];
   int R;           // halo (max fused radius, 0 if none)
@@ -354,8 +357,9 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
   const int tid = threadIdx.x;
   const int64_t x0 = (int64_t)blockIdx.x * FK_TW;       // first output column of the strip
   const int64_t cs0 = x0 - R;                            // global column of strip slot 0
-  const int64_t yb0 = (int64_t)blockIdx.y * p.band_rows;
-  const int64_t yb1 = (yb0 + p.band_rows < p.H) ? yb0 + p.band_rows : p.H;
+  const int64_t out_end = p.out_row0 + p.out_rows;
+  const int64_t yb0 = p.out_row0 + (int64_t)blockIdx.y * p.band_rows;
+  const int64_t yb1 = (yb0 + p.band_rows < out_end) ? yb0 + p.band_rows : out_end;
   const int64_t H = p.H, W = p.W;
 
   // column owned in the vertical phase
@@ -387,6 +391,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
     // ---- (1) make rows [y-R, y+NB+R] (clipped to the raster) resident ----
     int64_t need_lo = y - R < 0 ? 0 : y - R;
     int64_t need_hi = y + FK_NB + R >= H ? H - 1 : y + FK_NB + R;
+    if (need_hi > p.dem_row0 + p.dem_rows - 1) need_hi = p.dem_row0 + p.dem_rows - 1;
     int64_t from = (y == yb0) ? need_lo : loaded_hi + 1;
     __syncthreads();  // everyone is done with the rows about to be overwritten
     int my_nan = 0;
@@ -394,7 +399,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
       for (int c = tid; c < SW; c += FK_THREADS) {
         int64_t gx = cs0 + c;
         if (gx >= 0 && gx < W) {
-          float v = p.dem[row * p.ld_in + gx];
+          float v = p.dem[(row - p.dem_row0) * p.ld_in + gx];
           my_nan |= (v != v);
           ring_at(row, c) = v;
         }
@@ -505,8 +510,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
           double tr = ri - (double)r0;
           int64_t r1 = r0 + 1 < T.gh ? r0 + 1 : T.gh - 1;
           double wr0 = 1.0 - tr, wr1 = tr;
-          const float* g0 = T.grid + r0 * T.gw;
-          const float* g1 = T.grid + r1 * T.gw;
+          const float* g0 = T.grid + (r0 - T.grow0) * T.gw;
+          const float* g1 = T.grid + (r1 - T.grow0) * T.gw;
           double ci = (double)(x0 + hj0) * T.cscale;
           int64_t c0 = (int64_t)floor(ci);
           if (c0 > T.gw - 1) c0 = T.gw - 1;
@@ -544,7 +549,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
       } else {  // TERM_PLANE: precomputed full-resolution mean
         if (hrow_ok && hjn > 0) {
           const float* xrow = ring + (size_t)(orow % NRING) * SWp;
-          const float* prow = T.grid + orow * W;
+          const float* prow = T.grid + (orow - T.grow0) * W;
 #pragma unroll
           for (int jj = 0; jj < FK_SEG; ++jj) {
             if (jj < hjn) {
@@ -578,7 +583,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
     for (int idx = tid; idx < FK_NB * FK_TW; idx += FK_THREADS) {
       int rr = idx / FK_TW, c = idx - rr * FK_TW;
       int64_t gy = y + rr, gx = x0 + c;
-      if (gy < yb1 && gx < W) store_out(p.out, gy * p.ld_out + gx, stage[rr * (FK_TW + 1) + c], p.enc);
+      if (gy < yb1 && gx < W) store_out(p.out, (gy - p.out_row0) * p.ld_out + gx, stage[rr * (FK_TW + 1) + c], p.enc);
     }
   }
 }
@@ -716,8 +721,9 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
   const int64_t H = p.H;
   const int x0 = blockIdx.x * FK_TW;
   const int cs0 = x0 - R;
-  const int64_t yb0 = (int64_t)blockIdx.y * p.band_rows;
-  const int64_t yb1 = (yb0 + p.band_rows < H) ? yb0 + p.band_rows : H;
+  const int64_t out_end = p.out_row0 + p.out_rows;
+  const int64_t yb0 = p.out_row0 + (int64_t)blockIdx.y * p.band_rows;
+  const int64_t yb1 = (yb0 + p.band_rows < out_end) ? yb0 + p.band_rows : out_end;
   const bool edge_strip = (cs0 < 0) || (cs0 + SW > W);
 
   const int vc = tid;
@@ -770,14 +776,18 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
 
   // rows live at ring slot (row - row_org) mod NRING
   const int64_t row_org = yb0 - R < 0 ? 0 : yb0 - R;
-  auto need_hi_of = [&](int64_t yy) { return yy + NB + R >= H ? H - 1 : yy + NB + R; };
+  const int64_t dem_last = p.dem_row0 + p.dem_rows - 1;   // last row the caller's buffer holds
+  auto need_hi_of = [&](int64_t yy) {
+    int64_t v = yy + NB + R >= H ? H - 1 : yy + NB + R;
+    return v > dem_last ? dem_last : v;
+  };
   const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring) + 4u * (unsigned)vc;
   const unsigned row_bytes = 4u * (unsigned)SWp;
   auto issue_rows = [&](int64_t from, int64_t to) {   // cp.async rows [from, to] of this thread's column
     if (vcol_ok && from <= to) {
       int sl = (int)((from - row_org) % NRING);
       int n = (int)(to - from + 1);
-      const float* src = p.dem + from * p.ld_in + vgx;
+      const float* src = p.dem + (from - p.dem_row0) * p.ld_in + vgx;
       while (n > 0) {
         int run = NRING - sl < n ? NRING - sl : n;   // rows until the ring wraps
         unsigned sa = ring_sa + (unsigned)sl * row_bytes;
@@ -981,8 +991,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
           const double tr = ri - (double)r0;
           const int64_t r1 = r0 + 1 < T.gh ? r0 + 1 : T.gh - 1;
           const double wr0 = 1.0 - tr;
-          const float* g0 = T.grid + r0 * T.gw;
-          const float* g1 = T.grid + r1 * T.gw;
+          const float* g0 = T.grid + (r0 - T.grow0) * T.gw;
+          const float* g1 = T.grid + (r1 - T.grow0) * T.gw;
           const int gwm1 = (int)T.gw - 1;
           int c0 = 0;
           unsigned adv = 0u;
@@ -1000,7 +1010,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
         }
       } else {
         if (hrow_ok && hjn > 0) {
-          const float* prow = T.grid + orow * W;
+          const float* prow = T.grid + (orow - T.grow0) * W;
 #pragma unroll
           for (int jj = 0; jj < SEG; ++jj)
             if (jj < hjn) acc[jj] = acc[jj] + T.weight * (xr[jj] - __ldg(prow + x0 + hj0 + jj));
@@ -1035,7 +1045,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
       const int ncols = (W - x0) < FK_TW ? (W - x0) : FK_TW;
       for (int rr = tid / 32; rr < nrows_b; rr += FK_THREADS / 32) {   // one warp per output row
         const float* srow = stage + rr * (FK_TW + 1) + (tid & 31);
-        const int64_t obase = (y + rr) * p.ld_out + x0 + (tid & 31);
+        const int64_t obase = (y + rr - p.out_row0) * p.ld_out + x0 + (tid & 31);
         if (p.enc.kind == FSG_OUT_F32 && ncols == FK_TW) {
           float* o = (float*)p.out + obase;
 #pragma unroll
@@ -1078,15 +1088,81 @@ static size_t fused_smem_bytes(int R) {
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
-static int mean_on_grid(const Grid& g, int size, float* out, float* tv, float* tw, double* taps, cudaStream_t s) {
+static int mean_on_grid(const Grid& g, int size, float* out, float* tv, float* tw, double* taps, int64_t oy0,
+                        int64_t oh, cudaStream_t s) {
   int rc;
   if (size == 0) {  // sigma = 1 gaussian, 'nearest'
     if ((rc = launch_gauss_taps(1.0, 4, taps, s))) return rc;
-    if ((rc = launch_gauss_axis0(g, taps, 4, tv, tw, nullptr, s))) return rc;
-    return launch_gauss_axis1(tv, tw, g.h, g.w, taps, 4, COMBINE_MEAN, out, nullptr, nullptr, s);
+    if ((rc = launch_gauss_axis0(g, taps, 4, tv, tw, nullptr, oy0, oh, s))) return rc;
+    return launch_gauss_axis1(tv, tw, oh, g.w, taps, 4, COMBINE_MEAN, out, nullptr, nullptr, s);
   }
-  if ((rc = launch_box_axis0(g, size, tv, tw, s))) return rc;
-  return launch_box_axis1(tv, tw, g.h, g.w, size, out, s);
+  if ((rc = launch_box_axis0(g, size, tv, tw, oy0, oh, s))) return rc;
+  return launch_box_axis1(tv, tw, oh, g.w, size, out, s);
+}
+
+static int launch_pyramid(const float* dem, int64_t rows, int64_t W, int64_t ld, int n_levels, const int* factors,
+                          float* const* grids, int* flags, cudaStream_t s) {
+  PyramidParams pp{};
+  pp.dem = dem; pp.H = rows; pp.W = W; pp.ld = ld; pp.n_levels = n_levels; pp.flags = flags;
+  for (int k = 0; k < n_levels; ++k) {
+    pp.f[k] = factors[k];
+    pp.grid[k] = grids[k];
+    pp.gw[k] = (W + factors[k] - 1) / factors[k];
+    pp.gh[k] = (rows + factors[k] - 1) / factors[k];
+  }
+  dim3 grid((unsigned)((W + PY_COLS - 1) / PY_COLS), (unsigned)((rows + PY_ROWS - 1) / PY_ROWS));
+  int pslot = prof_begin(PROF_TOPOUSM_PYRAMID, s);
+  pyramid_kernel<<<grid, 256, 0, s>>>(pp);
+  prof_end(pslot, s);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+// Fills the per-launch fields of `fp` (kernel variant, grid, shared memory) and launches the fused pass
+// over global output rows [fp.out_row0, +fp.out_rows).
+static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t s) {
+  const int64_t H = fp.H, W = fp.W;
+  fp.R = fused_R;
+  fp.n_lvls = n_levels;
+  if (fp.out_rows <= 0) return FSG_OK;
+  const bool fast_ok = H >= fused_R + 2 && W >= fused_R + 2 && W < (1 << 30) && !getenv("FSG_FORCE_GENERIC");
+  const size_t smem_cap = 227 * 1024;
+  int nb = 0;   // rows per batch of the fast kernel (0: general kernel)
+  if (fast_ok && fused_fast_smem_bytes<32>(fused_R, n_levels) <= smem_cap) nb = 32;
+  else if (fast_ok && fused_fast_smem_bytes<16>(fused_R, n_levels) <= smem_cap) nb = 16;
+  // bands: few enough that the (2R+1)-row warm-up per band stays small, enough CTAs to fill 148 SMs
+  const int64_t rows = fp.out_rows;
+  int64_t strips = (W + FK_TW - 1) / FK_TW;
+  int64_t want_bands = (rows + 1023) / 2048;
+  if (want_bands < 1) want_bands = 1;
+  const int64_t min_rows = 8 * (int64_t)(2 * fused_R + 1);
+  while (strips * want_bands < 148 * 6 && (rows + 2 * want_bands - 1) / (2 * want_bands) >= min_rows) want_bands *= 2;
+  int64_t band_rows = (rows + want_bands - 1) / want_bands;
+  band_rows = (band_rows + FK_NB - 1) / FK_NB * FK_NB;
+  if (band_rows > (1 << 30)) band_rows = 1 << 30;
+  fp.band_rows = (int)band_rows;
+  int64_t bands = (rows + band_rows - 1) / band_rows;
+  if (bands > 65535) return fail(FSG_E_UNSUPPORTED, "fsg_topousm_fast: raster too tall");
+  dim3 grid((unsigned)strips, (unsigned)bands);
+  size_t smem = nb == 32 ? fused_fast_smem_bytes<32>(fused_R, n_levels)
+                         : (nb == 16 ? fused_fast_smem_bytes<16>(fused_R, n_levels) : fused_smem_bytes(fused_R));
+  if (nb == 32) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (nb == 16) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int slot = prof_begin(PROF_TOPOUSM_FUSED, s);
+  if (nb == 32) fused_kernel_fast<32><<<grid, FK_THREADS, smem, s>>>(fp);
+  else if (nb == 16) fused_kernel_fast<16><<<grid, FK_THREADS, smem, s>>>(fp);
+  else fused_kernel<<<grid, FK_THREADS, smem, s>>>(fp);
+  prof_end(slot, s);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+static void set_norm(FusedParams& fp, double norm_scale) {
+  if (is_none(norm_scale)) fp.norm_mode = 0;
+  else if (norm_scale > 0.0) {
+    fp.norm_mode = 1; fp.norm_scale = (float)norm_scale; fp.norm_rinv = (float)(1.0 / (double)fp.norm_scale);
+  } else fp.norm_mode = 2;
 }
 
 static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_t ld_in, int64_t ld_out,
@@ -1108,19 +1184,10 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
   if (plan.n_levels > 0) {
     zero_flags_kernel<<<1, 32, 0, s>>>(flags);
     FSG_LAUNCH_OK();
-    PyramidParams pp{};
-    pp.dem = dem; pp.H = H; pp.W = W; pp.ld = ld_in; pp.n_levels = plan.n_levels; pp.flags = flags;
-    for (int k = 0; k < plan.n_levels; ++k) {
-      pp.f[k] = plan.levels[k].f;
-      pp.grid[k] = (float*)(base + plan.levels[k].off);
-      pp.gw[k] = plan.levels[k].w;
-      pp.gh[k] = plan.levels[k].h;
-    }
-    dim3 grid((unsigned)((W + PY_COLS - 1) / PY_COLS), (unsigned)((H + PY_ROWS - 1) / PY_ROWS));
-    int pslot = prof_begin(PROF_TOPOUSM_PYRAMID, s);
-    pyramid_kernel<<<grid, 256, 0, s>>>(pp);
-    prof_end(pslot, s);
-    FSG_LAUNCH_OK();
+    int factors[MAX_LEVELS];
+    float* grids[MAX_LEVELS];
+    for (int k = 0; k < plan.n_levels; ++k) { factors[k] = plan.levels[k].f; grids[k] = (float*)(base + plan.levels[k].off); }
+    if ((rc = launch_pyramid(dem, H, W, ld_in, plan.n_levels, factors, grids, flags, s))) return rc;
     // enclosed-void fill (runs only when the level has an all-NaN cell; device-side flag)
     for (int k = 0; k < plan.n_levels; ++k) {
       const HostLevel& l = plan.levels[k];
@@ -1130,7 +1197,7 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
       float* grid_k = (float*)(base + l.off);
       Grid g{grid_k, l.h, l.w, l.w};
       if ((rc = launch_gauss_taps(sigma, radius, taps, s))) return rc;
-      if ((rc = launch_gauss_axis0(g, taps, radius, tv, tw, flags + k, s))) return rc;
+      if ((rc = launch_gauss_axis0(g, taps, radius, tv, tw, flags + k, 0, l.h, s))) return rc;
       if ((rc = launch_gauss_axis1(tv, tw, l.h, l.w, taps, radius, COMBINE_VOIDFILL, grid_k, flags + k, flags + 4 + k, s)))
         return rc;
     }
@@ -1138,20 +1205,19 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
 
   FusedParams fp{};
   fp.dem = dem; fp.out = out; fp.H = H; fp.W = W; fp.ld_in = ld_in; fp.ld_out = ld_out;
-  fp.n_terms = n; fp.R = plan.fused_R;
+  fp.dem_row0 = 0; fp.dem_rows = H; fp.out_row0 = 0; fp.out_rows = H;
+  fp.n_terms = n;
   fp.enc = make_encode(enc);
-  if (is_none(norm_scale)) fp.norm_mode = 0;
-  else if (norm_scale > 0.0) { fp.norm_mode = 1; fp.norm_scale = (float)norm_scale; fp.norm_rinv = (float)(1.0 / (double)fp.norm_scale); }
-  else fp.norm_mode = 2;
+  set_norm(fp, norm_scale);
   for (int i = 0; i < n; ++i) {
     const HostTerm& t = plan.terms[i];
     DevTerm& d = fp.terms[i];
-    d.kind = t.kind; d.r = t.radius; d.weight = weights[i];
+    d.kind = t.kind; d.r = t.radius; d.weight = weights[i]; d.grow0 = 0;
     if (t.kind == TERM_COARSE) {
       const HostLevel& l = plan.levels[t.level];
       float* mean = (float*)(base + t.grid_off);
       Grid g{(const float*)(base + l.off), l.h, l.w, l.w};
-      if ((rc = mean_on_grid(g, t.size, mean, tv, tw, taps, s))) return rc;
+      if ((rc = mean_on_grid(g, t.size, mean, tv, tw, taps, 0, l.h, s))) return rc;
       d.grid = mean; d.gh = l.h; d.gw = l.w;
       // scipy.ndimage.zoom: zoom = (n_in - 1) / (n_out - 1)  (1.0 when n_out == 1)
       d.rscale = H > 1 ? (double)(l.h - 1) / (double)(H - 1) : 1.0;
@@ -1162,43 +1228,69 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
     } else if (t.kind == TERM_PLANE) {
       float* mean = (float*)(base + t.grid_off);
       Grid g{dem, H, W, ld_in};
-      if ((rc = mean_on_grid(g, t.size, mean, tv, tw, taps, s))) return rc;
+      if ((rc = mean_on_grid(g, t.size, mean, tv, tw, taps, 0, H, s))) return rc;
       d.grid = mean; d.gh = H; d.gw = W;
     }
   }
-  fp.n_lvls = plan.n_levels;
-  const bool fast_ok = H >= plan.fused_R + 2 && W >= plan.fused_R + 2 && W < (1 << 30) && !getenv("FSG_FORCE_GENERIC");
-  const size_t smem_cap = 227 * 1024;
-  int nb = 0;   // rows per batch of the fast kernel (0: general kernel)
-  if (fast_ok && fused_fast_smem_bytes<32>(plan.fused_R, plan.n_levels) <= smem_cap) nb = 32;
-  else if (fast_ok && fused_fast_smem_bytes<16>(plan.fused_R, plan.n_levels) <= smem_cap) nb = 16;
-  // bands: few enough that the (2R+1)-row warm-up per band stays small, enough CTAs to fill 148 SMs
-  int64_t strips = (W + FK_TW - 1) / FK_TW;
-  int64_t want_bands = (H + 1023) / 2048;
-  if (want_bands < 1) want_bands = 1;
-  const int64_t min_rows = 8 * (int64_t)(2 * plan.fused_R + 1);
-  while (strips * want_bands < 148 * 6 && (H + 2 * want_bands - 1) / (2 * want_bands) >= min_rows) want_bands *= 2;
-  int64_t band_rows = (H + want_bands - 1) / want_bands;
-  band_rows = (band_rows + FK_NB - 1) / FK_NB * FK_NB;
-  if (band_rows > (1 << 30)) band_rows = 1 << 30;
-  fp.band_rows = (int)band_rows;
-  int64_t bands = (H + band_rows - 1) / band_rows;
-  if (bands > 65535) return fail(FSG_E_UNSUPPORTED, "fsg_topousm_fast: raster too tall");
-  dim3 grid((unsigned)strips, (unsigned)bands);
-  size_t smem = nb == 32 ? fused_fast_smem_bytes<32>(plan.fused_R, plan.n_levels)
-                         : (nb == 16 ? fused_fast_smem_bytes<16>(plan.fused_R, plan.n_levels) : fused_smem_bytes(plan.fused_R));
-  if (nb == 32) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else if (nb == 16) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int slot = prof_begin(PROF_TOPOUSM_FUSED, s);
-  if (nb == 32) fused_kernel_fast<32><<<grid, FK_THREADS, smem, s>>>(fp);
-  else if (nb == 16) fused_kernel_fast<16><<<grid, FK_THREADS, smem, s>>>(fp);
-  else fused_kernel<<<grid, FK_THREADS, smem, s>>>(fp);
-  prof_end(slot, s);
-  FSG_LAUNCH_OK();
-  return FSG_OK;
+  return launch_fused(fp, plan.fused_R, plan.n_levels, s);
 }
 
+// ---- row-band shard entry points (multi-GPU; see fujishadergpu_b200/core/sharding.py) ------------
+static int run_fused_band(const float* dem, int64_t dem_row0, int64_t dem_rows, int64_t H, int64_t W, int64_t ld_in,
+                          void* out, int64_t out_row0, int64_t out_rows, int64_t ld_out, const int32_t* radii,
+                          const float* weights, int n, double pixel_size, const float* const* grids,
+                          const int64_t* grow0, const int64_t* grows, double norm_scale, const fsg_encode* enc,
+                          cudaStream_t s) {
+  HostPlan plan;
+  int rc = make_plan(H, W, radii, n, pixel_size, &plan);
+  if (rc) return rc;
+  if (!dem || !out) return fail(FSG_E_INVALID, "fsg_topousm_fused_band: NULL buffer");
+  if (out_row0 < 0 || out_rows < 0 || out_row0 + out_rows > H)
+    return fail(FSG_E_INVALID, "fsg_topousm_fused_band: output rows outside the raster");
+  const int R = plan.fused_R;
+  int64_t lo = out_row0 - R < 0 ? 0 : out_row0 - R;
+  int64_t hi = out_row0 + out_rows + R > H ? H : out_row0 + out_rows + R;
+  if (dem_row0 > lo || dem_row0 + dem_rows < hi)
+    return fail(FSG_E_INVALID, "fsg_topousm_fused_band: DEM rows [%lld,%lld) do not cover the %d-row halo [%lld,%lld)",
+                (long long)dem_row0, (long long)(dem_row0 + dem_rows), R, (long long)lo, (long long)hi);
+  FusedParams fp{};
+  fp.dem = dem; fp.out = out; fp.H = H; fp.W = W; fp.ld_in = ld_in; fp.ld_out = ld_out;
+  fp.dem_row0 = dem_row0; fp.dem_rows = dem_rows; fp.out_row0 = out_row0; fp.out_rows = out_rows;
+  fp.n_terms = n;
+  fp.enc = make_encode(enc);
+  set_norm(fp, norm_scale);
+  for (int i = 0; i < n; ++i) {
+    const HostTerm& t = plan.terms[i];
+    DevTerm& d = fp.terms[i];
+    d.kind = t.kind; d.r = t.radius; d.weight = weights[i]; d.grow0 = 0;
+    if (t.kind == TERM_COARSE || t.kind == TERM_PLANE) {
+      if (!grids || !grids[i] || !grow0 || !grows)
+        return fail(FSG_E_INVALID, "fsg_topousm_fused_band: term %d (radius %d) needs a precomputed mean grid", i, t.radius);
+      d.grid = grids[i]; d.grow0 = grow0[i];
+      if (t.kind == TERM_COARSE) {
+        const HostLevel& l = plan.levels[t.level];
+        d.gh = l.h; d.gw = l.w;
+        d.rscale = H > 1 ? (double)(l.h - 1) / (double)(H - 1) : 1.0;
+        d.cscale = W > 1 ? (double)(l.w - 1) / (double)(W - 1) : 1.0;
+        d.lvl = t.level;
+        fp.lvl_cscale[t.level] = d.cscale;
+        fp.lvl_gw[t.level] = (int)l.w;
+        // rows the bilinear taps of this band touch
+        int64_t c_lo = (int64_t)floor((double)out_row0 * d.rscale);
+        int64_t c_hi = (int64_t)floor((double)(out_row0 + out_rows - 1) * d.rscale) + 1;
+        if (c_hi > l.h - 1) c_hi = l.h - 1;
+        if (grow0[i] > c_lo || grow0[i] + grows[i] <= c_hi)
+          return fail(FSG_E_INVALID, "fsg_topousm_fused_band: mean grid rows [%lld,%lld) of term %d do not cover [%lld,%lld]",
+                      (long long)grow0[i], (long long)(grow0[i] + grows[i]), i, (long long)c_lo, (long long)c_hi);
+      } else {
+        d.gh = H; d.gw = W;
+        if (grow0[i] > out_row0 || grow0[i] + grows[i] < out_row0 + out_rows)
+          return fail(FSG_E_INVALID, "fsg_topousm_fused_band: mean plane of term %d does not cover the output rows", i);
+      }
+    }
+  }
+  return launch_fused(fp, plan.fused_R, plan.n_levels, s);
+}
 
 // ------------------------------------------------------------------------------------------
 // stand-alone helpers (exposed for parity tests and for the reference's other call sites)
@@ -1295,16 +1387,12 @@ static int run_decimate(const float* in, float* out, int64_t H, int64_t W, int64
   int* flags = (int*)(base + 2 * plane + align_up((size_t)(radius + 1) * 8, 256));
   zero_flags_kernel<<<1, 32, 0, s>>>(flags);
   FSG_LAUNCH_OK();
-  PyramidParams pp{};
-  pp.dem = in; pp.H = H; pp.W = W; pp.ld = ld_in; pp.n_levels = 1; pp.flags = flags;
-  pp.f[0] = f; pp.grid[0] = out; pp.gw[0] = w; pp.gh[0] = h;
-  dim3 grid((unsigned)((W + PY_COLS - 1) / PY_COLS), (unsigned)((H + PY_ROWS - 1) / PY_ROWS));
-  pyramid_kernel<<<grid, 256, 0, s>>>(pp);
-  FSG_LAUNCH_OK();
-  Grid g{out, h, w, w};
   int rc;
+  float* grids1[1] = {out};
+  if ((rc = launch_pyramid(in, H, W, ld_in, 1, &f, grids1, flags, s))) return rc;
+  Grid g{out, h, w, w};
   if ((rc = launch_gauss_taps(sigma, radius, taps, s))) return rc;
-  if ((rc = launch_gauss_axis0(g, taps, radius, tv, tw, flags, s))) return rc;
+  if ((rc = launch_gauss_axis0(g, taps, radius, tv, tw, flags, 0, h, s))) return rc;
   return launch_gauss_axis1(tv, tw, h, w, taps, radius, COMBINE_VOIDFILL, out, flags, flags + 4, s);
 }
 
@@ -1376,6 +1464,123 @@ int fsg_topousm_large_part(const float* block, float* out, int64_t h, int64_t w,
                                                            off_r, off_c, sr, sc, (float)w_large);
   FSG_LAUNCH_OK();
   return FSG_OK;
+}
+
+
+/* ---- row-band shard entry points ---------------------------------------------------------- */
+int fsg_topousm_plan(const int32_t* radii_host, int n_radii, double pixel_size, int32_t* kind_host,
+                     int32_t* factor_host, int32_t* size_host, int32_t* fused_halo_host) {
+  fsg::HostPlan plan;
+  if (!radii_host || !kind_host || !factor_host || !size_host || !fused_halo_host)
+    return fsg::fail(FSG_E_INVALID, "fsg_topousm_plan: NULL argument");
+  int rc = fsg::make_plan(1 << 20, 1 << 20, radii_host, n_radii, pixel_size, &plan);  // kinds do not depend on H, W
+  if (rc) return rc;
+  for (int i = 0; i < n_radii; ++i) {
+    kind_host[i] = plan.terms[i].kind;
+    factor_host[i] = plan.terms[i].ds;
+    size_host[i] = plan.terms[i].size;
+  }
+  *fused_halo_host = plan.fused_R;
+  return FSG_OK;
+}
+
+int fsg_pyramid_band(const float* dem, int64_t rows, int64_t W, int64_t ld, const int32_t* factors_host, int n_levels,
+                     float* const* grids_host, int32_t* flags_dev, void* stream) {
+  using namespace fsg;
+  if (!dem || !factors_host || !grids_host || !flags_dev || rows < 1 || W < 1 || ld < W)
+    return fail(FSG_E_INVALID, "fsg_pyramid_band: bad argument");
+  if (n_levels < 1 || n_levels > MAX_LEVELS) return fail(FSG_E_INVALID, "fsg_pyramid_band: 1..4 levels");
+  int factors[MAX_LEVELS];
+  for (int k = 0; k < n_levels; ++k) {
+    factors[k] = factors_host[k];
+    if (factors[k] != 2 && factors[k] != 4 && factors[k] != 8 && factors[k] != 16)
+      return fail(FSG_E_INVALID, "fsg_pyramid_band: factor must be 2, 4, 8 or 16");
+    if (!grids_host[k]) return fail(FSG_E_INVALID, "fsg_pyramid_band: NULL grid");
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  zero_flags_kernel<<<1, 32, 0, s>>>((int*)flags_dev);
+  FSG_LAUNCH_OK();
+  return launch_pyramid(dem, rows, W, ld, n_levels, factors, grids_host, (int*)flags_dev, s);
+}
+
+size_t fsg_grid_mean_band_workspace_bytes(int64_t out_rows, int64_t gw) {
+  if (out_rows < 1 || gw < 1) return 256;
+  return 2 * fsg::align_up((size_t)out_rows * gw * 4, 256) + 256;
+}
+
+int fsg_grid_mean_band(const float* src, int64_t src_row0, int64_t src_rows, int64_t gh, int64_t gw, int64_t ld,
+                       int size, int64_t out_row0, int64_t out_rows, float* out, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  using namespace fsg;
+  if (!src || !out || gh < 1 || gw < 1 || ld < gw || src_rows < 1) return fail(FSG_E_INVALID, "fsg_grid_mean_band: bad argument");
+  if (size < 0 || (size > 0 && size % 2 == 0)) return fail(FSG_E_INVALID, "fsg_grid_mean_band: size must be 0 (gaussian) or odd");
+  if (out_row0 < 0 || out_rows < 0 || out_row0 + out_rows > gh) return fail(FSG_E_INVALID, "fsg_grid_mean_band: output rows outside the grid");
+  if (out_rows == 0) return FSG_OK;
+  // rows the vertical pass touches after mirroring / clamping at the global edges
+  int64_t reach = size == 0 ? 4 : size / 2;
+  int64_t lo = out_row0 - reach, hi = out_row0 + out_rows - 1 + reach;
+  int64_t need_lo = lo < 0 ? 0 : lo, need_hi = hi > gh - 1 ? gh - 1 : hi;
+  if (size > 0) {  // mirrored rows may reach further inside
+    if (lo < 0 && -lo - 1 > need_hi) need_hi = (-lo - 1 > gh - 1) ? gh - 1 : -lo - 1;
+    if (hi > gh - 1 && 2 * gh - 1 - hi < need_lo) need_lo = (2 * gh - 1 - hi < 0) ? 0 : 2 * gh - 1 - hi;
+  }
+  if (src_row0 > need_lo || src_row0 + src_rows - 1 < need_hi)
+    return fail(FSG_E_INVALID, "fsg_grid_mean_band: source rows [%lld,%lld) do not cover [%lld,%lld]",
+                (long long)src_row0, (long long)(src_row0 + src_rows), (long long)need_lo, (long long)need_hi);
+  size_t plane = align_up((size_t)out_rows * gw * 4, 256);
+  if (!workspace || workspace_bytes < 2 * plane + 256) return fail(FSG_E_WORKSPACE, "fsg_grid_mean_band: workspace too small");
+  unsigned char* base = (unsigned char*)workspace;
+  float* tv = (float*)base;
+  float* tw = (float*)(base + plane);
+  double* taps = (double*)(base + 2 * plane);
+  Grid g{src, gh, gw, ld};
+  g.row_off = src_row0;
+  return mean_on_grid(g, size, out, tv, tw, taps, out_row0, out_rows, (cudaStream_t)stream);
+}
+
+int fsg_topousm_fused_band(const float* dem, int64_t dem_row0, int64_t dem_rows, int64_t H, int64_t W, int64_t ld_in,
+                           void* out, int64_t out_row0, int64_t out_rows, int64_t ld_out,
+                           const int32_t* radii_host, const float* weights_host, int n_radii, double pixel_size,
+                           const float* const* term_grids_host, const int64_t* term_grow0_host,
+                           const int64_t* term_grows_host, double norm_scale, const fsg_encode* enc, void* stream) {
+  if (!radii_host || !weights_host) return fsg::fail(FSG_E_INVALID, "fsg_topousm_fused_band: radii/weights are NULL");
+  if (ld_in < W || ld_out < W) return fsg::fail(FSG_E_INVALID, "fsg_topousm_fused_band: row stride smaller than width");
+  return fsg::run_fused_band(dem, dem_row0, dem_rows, H, W, ld_in, out, out_row0, out_rows, ld_out, radii_host,
+                             weights_host, n_radii, pixel_size, term_grids_host, term_grow0_host, term_grows_host,
+                             norm_scale, enc, (cudaStream_t)stream);
+}
+
+
+/* Enclosed-void fill of a WHOLE decimated grid, in place (algorithms/_nan_utils.py:655-667): a no-op
+ * unless the grid holds a NaN cell.  workspace: fsg_decimate_workspace_bytes(gh*factor, gw*factor, factor)
+ * or simply 2*gh*gw*4 + 8*(4*sigma+2) + 1024 bytes. */
+int fsg_grid_void_fill(float* grid, int64_t gh, int64_t gw, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace fsg;
+  if (!grid || gh < 1 || gw < 1) return fail(FSG_E_INVALID, "fsg_grid_void_fill: bad argument");
+  double sigma = (double)(gh < gw ? gh : gw) / 64.0;
+  if (sigma < 1.0) sigma = 1.0;
+  int radius = (int)(4.0 * sigma + 0.5);
+  size_t plane = align_up((size_t)gh * gw * 4, 256);
+  size_t need = 2 * plane + align_up((size_t)(radius + 1) * 8, 256) + 512;
+  if (!workspace || workspace_bytes < need) return fail(FSG_E_WORKSPACE, "fsg_grid_void_fill: workspace of %zu bytes needed", need);
+  unsigned char* base = (unsigned char*)workspace;
+  float* tv = (float*)base;
+  float* tw = (float*)(base + plane);
+  double* taps = (double*)(base + 2 * plane);
+  int* flags = (int*)(base + 2 * plane + align_up((size_t)(radius + 1) * 8, 256));
+  cudaStream_t s = (cudaStream_t)stream;
+  zero_flags_kernel<<<1, 32, 0, s>>>(flags);
+  FSG_LAUNCH_OK();
+  int64_t n = gh * gw;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  any_nan_kernel<<<blocks, 256, 0, s>>>(grid, n, flags);
+  FSG_LAUNCH_OK();
+  Grid g{grid, gh, gw, gw};
+  int rc;
+  if ((rc = launch_gauss_taps(sigma, radius, taps, s))) return rc;
+  if ((rc = launch_gauss_axis0(g, taps, radius, tv, tw, flags, 0, gh, s))) return rc;
+  return launch_gauss_axis1(tv, tw, gh, gw, taps, radius, COMBINE_VOIDFILL, grid, flags, flags + 4, s);
 }
 
 }  // extern "C"

@@ -316,3 +316,117 @@ def profile_read(max_records: int = 256):
     ms = (C.c_float * max_records)()
     n = _lib.load().fsg_profile_read(tags, ms, max_records)
     return [(int(tags[i]), float(ms[i])) for i in range(n)]
+
+
+# ---- row-band shard stages (multi-GPU) ----------------------------------------------------------
+def topousm_plan(radii: Sequence, pixel_size: float = 1.0) -> dict:
+    """Per-radius evaluation plan: kind 0 = fused full-res box, 1 = decimated level, 2 = full-res plane."""
+    rr = np.ascontiguousarray(np.asarray([int(r) for r in radii], dtype=np.int32))
+    n = len(rr)
+    kind = np.zeros(n, np.int32); factor = np.zeros(n, np.int32); size = np.zeros(n, np.int32)
+    halo = C.c_int32(0)
+    i32 = C.POINTER(C.c_int32)
+    check(_lib.load().fsg_topousm_plan(rr.ctypes.data_as(i32), n, float(pixel_size), kind.ctypes.data_as(i32),
+                                       factor.ctypes.data_as(i32), size.ctypes.data_as(i32), C.byref(halo)),
+          "fsg_topousm_plan")
+    return {"kind": kind.tolist(), "factor": factor.tolist(), "size": size.tolist(), "fused_halo": int(halo.value)}
+
+
+def pyramid_band(band, factors: Sequence[int]):
+    """f x f valid means of a band's own rows for every factor; returns (grids, has_void flags)."""
+    t = dev.as_f32_2d(band)
+    rows, W = int(t.shape[0]), int(t.shape[1])
+    fl = np.ascontiguousarray(np.asarray(list(factors), dtype=np.int32))
+    grids = [torch.empty(((rows + f - 1) // f, (W + f - 1) // f), dtype=torch.float32, device=t.device) for f in factors]
+    flags = torch.zeros(16, dtype=torch.int32, device=t.device)
+    ptrs = (C.c_void_p * len(grids))(*[g.data_ptr() for g in grids])
+    check(_lib.load().fsg_pyramid_band(_ptr(t), rows, W, int(t.stride(0)), fl.ctypes.data_as(C.POINTER(C.c_int32)),
+                                       len(grids), ptrs, _ptr(flags), C.c_void_p(dev.stream_ptr(t))), "fsg_pyramid_band")
+    return grids, flags[: len(grids)]
+
+
+def grid_mean_band(src, src_row0: int, gh: int, size: int, out_row0: int, out_rows: int) -> torch.Tensor:
+    """NaN-aware box (size > 0, 'reflect') / sigma-1 Gaussian (size == 0, 'nearest') mean of grid rows
+    [out_row0, out_row0+out_rows); `src` holds global rows [src_row0, src_row0+len(src))."""
+    t = dev.as_f32_2d(src)
+    gw = int(t.shape[1])
+    out = torch.empty((int(out_rows), gw), dtype=torch.float32, device=t.device)
+    lib = _lib.load()
+    need = int(lib.fsg_grid_mean_band_workspace_bytes(int(out_rows), gw))
+    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=t.device)
+    check(lib.fsg_grid_mean_band(_ptr(t), int(src_row0), int(t.shape[0]), int(gh), gw, int(t.stride(0)), int(size),
+                                 int(out_row0), int(out_rows), _ptr(out), _ptr(ws), need,
+                                 C.c_void_p(dev.stream_ptr(t))), "fsg_grid_mean_band")
+    return out
+
+
+def grid_void_fill(grid) -> torch.Tensor:
+    """Enclosed-void fill of a whole decimated grid (returns a filled copy)."""
+    t = dev.as_f32_2d(grid).contiguous().clone()
+    gh, gw = int(t.shape[0]), int(t.shape[1])
+    sigma = max(1.0, min(gh, gw) / 64.0)
+    need = 2 * ((gh * gw * 4 + 255) // 256 * 256) + (int(4 * sigma + 0.5) + 1) * 8 + 2048
+    ws = torch.empty(need, dtype=torch.uint8, device=t.device)
+    check(_lib.load().fsg_grid_void_fill(_ptr(t), gh, gw, _ptr(ws), need, C.c_void_p(dev.stream_ptr(t))),
+          "fsg_grid_void_fill")
+    return t
+
+
+def topousm_fused_band(dem_ext, dem_row0: int, H: int, out_row0: int, out_rows: int, *, radii, weights=None,
+                       pixel_size=1.0, term_grids=None, term_grow0=None, norm_scale=None, output_dtype="float32",
+                       qp=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused pass over one row band.  term_grids[i] is None for fused terms, else a window of the term's
+    mean grid whose first row is global grid row term_grow0[i]."""
+    t = dev.as_f32_2d(dem_ext)
+    W = int(t.shape[1])
+    rr, ww = _radii_weights(radii, weights)
+    n = len(rr)
+    if out is None:
+        out = dev.empty_out(t, (int(out_rows), W), output_dtype)
+    enc = make_encode(output_dtype, qp)
+    grids = [None if g is None else dev.as_f32_2d(g).contiguous() for g in (term_grids or [None] * n)]
+    ptrs = (C.c_void_p * n)(*[(g.data_ptr() if g is not None else None) for g in grids])
+    g0 = (C.c_int64 * n)(*[int(v) if v is not None else 0 for v in (term_grow0 or [0] * n)])
+    gn = (C.c_int64 * n)(*[int(g.shape[0]) if g is not None else 0 for g in grids])
+    check(_lib.load().fsg_topousm_fused_band(
+        _ptr(t), int(dem_row0), int(t.shape[0]), int(H), W, int(t.stride(0)), _ptr(out), int(out_row0), int(out_rows),
+        int(out.stride(0)), rr.ctypes.data_as(C.POINTER(C.c_int32)), ww.ctypes.data_as(C.POINTER(C.c_float)), n,
+        float(pixel_size), ptrs, g0, gn, opt(norm_scale), C.byref(enc), C.c_void_p(dev.stream_ptr(t))),
+        "fsg_topousm_fused_band")
+    return out
+
+
+def _chunk_args(views):
+    n = len(views)
+    ptrs = (C.c_void_p * max(n, 1))(*[v.data_ptr() for v in views])
+    rows = (C.c_int64 * max(n, 1))(*[int(v.shape[0]) for v in views])
+    cols = (C.c_int64 * max(n, 1))(*[int(v.shape[1]) for v in views])
+    lds = (C.c_int64 * max(n, 1))(*[int(v.stride(0)) if v.shape[0] > 1 else int(v.shape[1]) for v in views])
+    return ptrs, rows, cols, lds
+
+
+def key_histogram(chunks, level: int, prefix: int, mask: int, *, take_abs: bool, finite_only: bool, device):
+    """(hist int64[2048], count int) of this rank's sample keys matching (key & mask) == prefix."""
+    views = _pooled_views(chunks) if chunks else []
+    hist = torch.zeros(2048, dtype=torch.int32, device=device)
+    cnt = torch.zeros(1, dtype=torch.int64, device=device)
+    ptrs, rows, cols, lds = _chunk_args(views)
+    check(_lib.load().fsg_key_histogram(ptrs, rows, cols, lds, len(views), int(level), int(prefix), int(mask),
+                                        1 if take_abs else 0, 1 if finite_only else 0, _ptr(hist), _ptr(cnt),
+                                        C.c_void_p(int(torch.cuda.current_stream(device).cuda_stream))), "fsg_key_histogram")
+    return hist.to(torch.int64), cnt
+
+
+def key_rank_info(chunks, key: int, *, take_abs: bool, finite_only: bool, device):
+    """int64[2]: (#keys <= key, min key > key or 0xffffffff) over this rank's samples."""
+    views = _pooled_views(chunks) if chunks else []
+    out = torch.zeros(2, dtype=torch.int64, device=device)
+    ptrs, rows, cols, lds = _chunk_args(views)
+    check(_lib.load().fsg_key_rank_info(ptrs, rows, cols, lds, len(views), int(key), 1 if take_abs else 0,
+                                        1 if finite_only else 0, _ptr(out),
+                                        C.c_void_p(int(torch.cuda.current_stream(device).cuda_stream))), "fsg_key_rank_info")
+    return out
+
+
+def key_to_float(key: int, take_abs: bool) -> float:
+    return float(_lib.load().fsg_key_to_float(int(key), 1 if take_abs else 0))

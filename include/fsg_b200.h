@@ -120,6 +120,36 @@ int fsg_topousm_fast(const float* dem, void* out, int64_t H, int64_t W, int64_t 
                      double pixel_size, double norm_scale, const fsg_encode* enc,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- row-band shards of topousm_fast (multi-GPU; one band of rows per GPU) ----------------------
+ * The whole-raster pipeline above, cut into stages so that the host can exchange halo rows between
+ * neighbouring bands (fujishadergpu_b200/core/sharding.py does it with torch.distributed / NCCL):
+ *   fsg_topousm_plan       : per radius -> kind (0 fused full-res box, 1 decimated level, 2 full-res
+ *                            plane), decimation factor, box taps on its grid (0 = sigma-1 Gaussian),
+ *                            and the DEM halo rows the fused pass needs (max fused radius).
+ *   fsg_pyramid_band       : f x f valid means of the band's OWN rows (the band must start at a
+ *                            global row that is a multiple of 16); flags_dev[k] = level k holds a void
+ *                            cell (the enclosed-void fill needs the whole grid; see sharding.py).
+ *   fsg_grid_mean_band     : NaN-aware box ('reflect') / sigma-1 Gaussian ('nearest') mean of a window
+ *                            of grid rows; the edge rules act at the GLOBAL grid edges (gh rows).
+ *   fsg_topousm_fused_band : the fused pass for global rows [out_row0, +out_rows) given DEM rows with a
+ *                            fused-halo on each side and, per non-fused term, a window of its mean grid.
+ * A band pipeline reproduces the whole-raster result bit for bit. */
+int fsg_topousm_plan(const int32_t* radii_host, int n_radii, double pixel_size, int32_t* kind_host,
+                     int32_t* factor_host, int32_t* size_host, int32_t* fused_halo_host);
+int fsg_pyramid_band(const float* dem, int64_t rows, int64_t W, int64_t ld, const int32_t* factors_host,
+                     int n_levels, float* const* grids_host, int32_t* flags_dev, void* stream);
+size_t fsg_grid_mean_band_workspace_bytes(int64_t out_rows, int64_t gw);
+int fsg_grid_mean_band(const float* src, int64_t src_row0, int64_t src_rows, int64_t gh, int64_t gw, int64_t ld,
+                       int size, int64_t out_row0, int64_t out_rows, float* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int fsg_topousm_fused_band(const float* dem, int64_t dem_row0, int64_t dem_rows, int64_t H, int64_t W, int64_t ld_in,
+                           void* out, int64_t out_row0, int64_t out_rows, int64_t ld_out,
+                           const int32_t* radii_host, const float* weights_host, int n_radii, double pixel_size,
+                           const float* const* term_grids_host, const int64_t* term_grow0_host,
+                           const int64_t* term_grows_host, double norm_scale, const fsg_encode* enc, void* stream);
+
+int fsg_grid_void_fill(float* grid, int64_t gh, int64_t gw, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- overview large-radius part (algorithms/_impl_topousm_fast.py:158-186,
  *      algorithms/_nan_utils.py:255-281): out = f32(w_large)*block - bilinear(field) */
 int fsg_topousm_large_part(const float* block, float* out, int64_t h, int64_t w, int64_t ld_in, int64_t ld_out,
@@ -168,6 +198,17 @@ size_t fsg_order_stats_workspace_bytes(void);
 int fsg_order_stats(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
                     const int64_t* ld_host, int n_chunks, int64_t rank, int take_abs, int finite_only,
                     double* result_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Staged selection for percentiles of a sample that is spread over several GPUs: per-rank key
+ * histograms (3 radix levels) and rank information, combined by the host with all-reduces
+ * (fujishadergpu_b200/core/sharding.py::distributed_percentile). */
+int fsg_key_histogram(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                      const int64_t* ld_host, int n_chunks, int level, uint32_t prefix, uint32_t mask, int take_abs,
+                      int finite_only, uint32_t* hist_dev, uint64_t* count_dev, void* stream);
+int fsg_key_rank_info(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                      const int64_t* ld_host, int n_chunks, uint32_t key, int take_abs, int finite_only,
+                      uint64_t* out_dev, void* stream);
+float fsg_key_to_float(uint32_t key, int take_abs);
 
 /* synthetic DEM generator used by bench/tests: eight sinusoid octaves +
  * hash noise, optional NoData wedge/ellipses; rows [row0,row0+rows) of an H x W raster. */

@@ -211,12 +211,9 @@ def gauss_taps(sigma: float, truncate: float = 4.0) -> np.ndarray:
 # --------------------------------------------------------------------------
 # a7 / a8 : decimate / upsample
 # --------------------------------------------------------------------------
-def decimate_valid_mean(a: np.ndarray, f: int) -> np.ndarray:
-    """algorithms/_nan_utils.py:604-668 -- f x f mean of finite members anchored at
-    (0,0), ragged edge NaN-padded, f32 sums; enclosed coarse voids (Gaussian
-    validity weight > 0.5) are filled, exterior voids stay NaN."""
-    if f <= 1:
-        return a
+def decimate_cells(a: np.ndarray, f: int) -> np.ndarray:
+    """First half of algorithms/_nan_utils.py:604-668 -- f x f mean of finite members anchored at (0,0),
+    ragged edge NaN-padded, f32 sums in NumPy's reduction order; all-NaN cells stay NaN."""
     f = int(f)
     h, w = a.shape
     oh, ow = max(1, (h + f - 1) // f), max(1, (w + f - 1) // f)
@@ -228,7 +225,12 @@ def decimate_valid_mean(a: np.ndarray, f: int) -> np.ndarray:
     cnt = fin.sum(axis=(1, 3), dtype=F32)
     tot = np.where(fin, cells, F32(0)).sum(axis=(1, 3), dtype=F32)
     with np.errstate(divide="ignore", invalid="ignore"):
-        coarse = np.where(cnt > 0, tot / np.maximum(cnt, F32(1)), F32(np.nan)).astype(F32)
+        return np.where(cnt > 0, tot / np.maximum(cnt, F32(1)), F32(np.nan)).astype(F32)
+
+
+def fill_enclosed_voids(coarse: np.ndarray) -> np.ndarray:
+    """Second half of algorithms/_nan_utils.py:604-668 -- enclosed coarse voids (Gaussian validity
+    weight > 0.5, sigma = max(1, min(h, w)/64)) are filled, exterior voids stay NaN."""
     void = np.isnan(coarse)
     if void.any():
         sig = max(1.0, float(min(coarse.shape)) / 64.0)
@@ -237,6 +239,13 @@ def decimate_valid_mean(a: np.ndarray, f: int) -> np.ndarray:
         enclosed = void & (sw > F32(0.5))
         coarse = np.where(enclosed, sv / np.maximum(sw, F32(1e-6)), coarse).astype(F32)
     return coarse.astype(F32)
+
+
+def decimate_valid_mean(a: np.ndarray, f: int) -> np.ndarray:
+    """algorithms/_nan_utils.py:604-668."""
+    if f <= 1:
+        return a
+    return fill_enclosed_voids(decimate_cells(a, f))
 
 
 def upsample_align_corners(a: np.ndarray, shape: Tuple[int, int]) -> np.ndarray:
