@@ -16,8 +16,9 @@ edge rules at the global raster edges): the result is bit-identical to one GPU p
 raster.  No collective touches image data except the point-to-point halo copies; the percentile of
 the statistics pre-pass is an exact distributed radix select (all-reduce of 2048-bin histograms).
 
-`backend` abstracts the compute stages so the host logic can be exercised on CPU (gloo) with a NumPy
-stand-in (tests/test_sharding_gloo.py); the product backend is CudaBackend (libfsg_b200).
+`backend` abstracts the compute stages so the host logic can be exercised on CPU (gloo) by tests that
+inject their own stand-in (tests/test_sharding_gloo.py); the product backend is CudaBackend
+(libfsg_b200) and there is no other one in this package.
 """
 from __future__ import annotations
 
@@ -47,7 +48,7 @@ def band_bounds(H: int, world: int, align: int = ALIGN) -> List[Tuple[int, int]]
 
 
 def mirror_need(lo: int, hi: int, n: int, reflect: bool) -> Tuple[int, int]:
-    """Rows of a length-n axis touched by indices [lo, hi] after mirroring (scipy 'reflect') or clamping."""
+    """Rows of a length-n axis touched by indices [lo, hi] after mirroring (edge-inclusive 'reflect') or clamping."""
     if n <= 0:
         return (0, 0)
     a, b = max(lo, 0), min(hi, n - 1)
@@ -283,7 +284,7 @@ def distributed_percentile(chunks, q: float, *, take_abs: bool, finite_only: boo
 # sharded statistics pre-pass (reference: algorithms/_norm_stats.py:176-298)
 # ------------------------------------------------------------------------------------------------
 def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, radii, weights, pixel_size=1.0,
-                          dist=None, grid: int = 3, block_fn=None) -> Optional[float]:
+                          dist=None, grid: int = 3, block_fn=None, select_fns=None) -> Optional[float]:
     """p99(|raw topousm_fast|) over the reference's stratified full-resolution windows.  Each window is
     evaluated whole by ONE rank (round-robin) after gathering its rows from the owning bands; the
     percentile over all windows is an exact distributed selection."""
@@ -333,36 +334,11 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
                 raw = raw[m:-m, m:-m]
             if raw.numel():
                 pooled.append(raw)
-    kw = {}
-    if band.device.type != "cuda":   # CPU (gloo) tests inject NumPy stand-ins for the three kernels
-        kw = _numpy_select_fns(pooled)
+    kw = select_fns(pooled) if select_fns is not None else {}   # tests inject stand-ins for the kernels
     s = distributed_percentile(pooled, 99.0, take_abs=True, finite_only=False, device=band.device, dist=dist, **kw)
     if not (s == s) or s <= 1e-9:
         return None
     return s
-
-
-def _numpy_select_fns(pooled):
-    """NumPy stand-ins for key_histogram / key_rank_info / key_to_float (host-logic tests on CPU)."""
-    vals = np.concatenate([np.abs(p.cpu().numpy().ravel()) for p in pooled]) if pooled else np.zeros(0, np.float32)
-    vals = vals[~np.isnan(vals)].astype(np.float32)
-    keys = vals.view(np.uint32).astype(np.int64)
-
-    def hist_fn(level, prefix, mask):
-        shift, bins = ((21, 2048), (10, 2048), (0, 1024))[level]
-        sel = keys[(keys & mask) == prefix]
-        h = np.bincount((sel >> shift) & (bins - 1), minlength=2048).astype(np.int64)
-        return torch.from_numpy(h), torch.tensor([keys.size], dtype=torch.int64)
-
-    def rank_info_fn(key):
-        le = int((keys <= key).sum())
-        gt = keys[keys > key]
-        return torch.tensor([le, int(gt.min()) if gt.size else 0xffffffff], dtype=torch.int64)
-
-    def key_to_float(key):
-        return float(np.array([key], dtype=np.uint32).view(np.float32)[0])
-
-    return dict(hist_fn=hist_fn, rank_info_fn=rank_info_fn, key_to_float=key_to_float)
 
 
 # ------------------------------------------------------------------------------------------------

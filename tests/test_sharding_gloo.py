@@ -109,6 +109,29 @@ class NumpyBackend:
         return res
 
 
+def _numpy_select_fns(pooled):
+    """NumPy stand-ins for key_histogram / key_rank_info / key_to_float (host-logic tests on CPU)."""
+    vals = np.concatenate([np.abs(p.cpu().numpy().ravel()) for p in pooled]) if pooled else np.zeros(0, np.float32)
+    vals = vals[~np.isnan(vals)].astype(np.float32)
+    keys = vals.view(np.uint32).astype(np.int64)
+
+    def hist_fn(level, prefix, mask):
+        shift, bins = ((21, 2048), (10, 2048), (0, 1024))[level]
+        sel = keys[(keys & mask) == prefix]
+        h = np.bincount((sel >> shift) & (bins - 1), minlength=2048).astype(np.int64)
+        return torch.from_numpy(h), torch.tensor([keys.size], dtype=torch.int64)
+
+    def rank_info_fn(key):
+        le = int((keys <= key).sum())
+        gt = keys[keys > key]
+        return torch.tensor([le, int(gt.min()) if gt.size else 0xffffffff], dtype=torch.int64)
+
+    def key_to_float(key):
+        return float(np.array([key], dtype=np.uint32).view(np.float32)[0])
+
+    return dict(hist_fn=hist_fn, rank_info_fn=rank_info_fn, key_to_float=key_to_float)
+
+
 def _worker(rank, world, port, dem_path, out_dir, radii, weights, with_stats):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -122,7 +145,8 @@ def _worker(rank, world, port, dem_path, out_dir, radii, weights, with_stats):
     scale = None
     if with_stats:
         scale = sh.sharded_topousm_scale(band, H, rank, world, radii=radii, weights=weights, dist=dist,
-                                         block_fn=lambda a: torch.from_numpy(orc.topousm_fast_block(a.numpy(), radii=radii, weights=weights)))
+                                         block_fn=lambda a: torch.from_numpy(orc.topousm_fast_block(a.numpy(), radii=radii, weights=weights)),
+                                         select_fns=_numpy_select_fns)
     out = sh.topousm_fast_sharded(band, H, rank, world, radii=radii, weights=weights, norm_scale=scale, dist=dist, backend=be)
     np.save(os.path.join(out_dir, f"out_{rank}.npy"), out.numpy())
     if rank == 0 and with_stats:
@@ -201,6 +225,6 @@ def test_distributed_percentile_single_process_matches_numpy():
     a = (rng.standard_normal(50001) * 5).astype(np.float32)
     a[::97] = np.nan
     chunks = [torch.from_numpy(a[:20000].reshape(100, 200)), torch.from_numpy(a[20000:].reshape(1, -1))]
-    fns = sh._numpy_select_fns(chunks)
+    fns = _numpy_select_fns(chunks)
     got = sh.distributed_percentile(chunks, 99.0, take_abs=True, finite_only=False, device="cpu", **fns)
     assert got == float(np.percentile(np.abs(a[~np.isnan(a)]), 99.0))
