@@ -254,6 +254,8 @@ def run_gpu_arm(a) -> None:
     # ---- e2e: host buffers through the public host API (uint8 result) ----
     e2e = None
     try:
+        if a.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
         from fujishadergpu_b200.core.tile_processor import HostTilePipeline
         del out
         torch.cuda.empty_cache()
@@ -311,6 +313,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
