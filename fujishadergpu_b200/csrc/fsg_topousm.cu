@@ -342,6 +342,7 @@ struct FusedParams {
   int norm_mode;   // 0 none, 1 divide by norm_scale, 2 zeros
   float norm_scale;
   EncodeDev enc;
+  int bulk_ok;     // v6: DEM rows are 16-byte aligned (base pointer and row stride) -> bulk async copies
 };
 
 __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
@@ -1085,6 +1086,10 @@ static size_t fused_smem_bytes(int R) {
   return nring * SWp * 4 + vp * 4 + align_up((size_t)FK_NB * SWp, 16);
 }
 
+}  // namespace fsg
+#include "fsg_topousm_v6.cuh"
+namespace fsg {
+
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
@@ -1128,7 +1133,12 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
   const bool fast_ok = H >= fused_R + 2 && W >= fused_R + 2 && W < (1 << 30) && !getenv("FSG_FORCE_GENERIC");
   const size_t smem_cap = 227 * 1024;
   int nb = 0;   // rows per batch of the fast kernel (0: general kernel)
-  if (fast_ok && fused_fast_smem_bytes<32>(fused_R, n_levels) <= smem_cap) nb = 32;
+  int n_fused = 0;
+  for (int i = 0; i < fp.n_terms; ++i) n_fused += fp.terms[i].kind == TERM_BOX_FUSED;
+  const bool v6_ok = fast_ok && fused_R <= 32 && n_levels <= V6_MAXLV && n_fused <= V6_MAXF && !getenv("FSG_FUSED_V5");
+  fp.bulk_ok = (((uintptr_t)fp.dem & 15) == 0 && fp.ld_in % 4 == 0 && !getenv("FSG_NO_BULK")) ? 1 : 0;
+  if (v6_ok) nb = 6;
+  else if (fast_ok && fused_fast_smem_bytes<32>(fused_R, n_levels) <= smem_cap) nb = 32;
   else if (fast_ok && fused_fast_smem_bytes<16>(fused_R, n_levels) <= smem_cap) nb = 16;
   // bands: few enough that the (2R+1)-row warm-up per band stays small, enough CTAs to fill 148 SMs
   const int64_t rows = fp.out_rows;
@@ -1146,11 +1156,14 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
   dim3 grid((unsigned)strips, (unsigned)bands);
   size_t smem = nb == 32 ? fused_fast_smem_bytes<32>(fused_R, n_levels)
                          : (nb == 16 ? fused_fast_smem_bytes<16>(fused_R, n_levels) : fused_smem_bytes(fused_R));
-  if (nb == 32) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (nb == 6) smem = V6Geom<32>::BYTES;
+  if (nb == 6) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v6<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (nb == 32) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (nb == 16) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int slot = prof_begin(PROF_TOPOUSM_FUSED, s);
-  if (nb == 32) fused_kernel_fast<32><<<grid, FK_THREADS, smem, s>>>(fp);
+  if (nb == 6) fused_kernel_v6<32><<<grid, FK_THREADS, smem, s>>>(fp);
+  else if (nb == 32) fused_kernel_fast<32><<<grid, FK_THREADS, smem, s>>>(fp);
   else if (nb == 16) fused_kernel_fast<16><<<grid, FK_THREADS, smem, s>>>(fp);
   else fused_kernel<<<grid, FK_THREADS, smem, s>>>(fp);
   prof_end(slot, s);
