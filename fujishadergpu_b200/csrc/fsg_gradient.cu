@@ -10,6 +10,8 @@
 // 2-px (hillshade/slope) or 3-px (curvature) halo is staged once in shared memory; curvature also
 // stages the first derivatives on tile+2.  Global traffic: one read of the DEM (+halo re-reads that
 // hit L2) and one write of the result -- 8 B/px (f32 out), 5 B/px (u8 out).
+#include <stdlib.h>
+
 #include "fsg_common.cuh"
 
 namespace fsg {
@@ -20,6 +22,7 @@ constexpr int G_THREADS = 256;
 
 struct AxisCoef {  // np.gradient(edge_order=2) coefficients for one axis, already f32
   float two_h;     // f32(2*h)           interior: (f[i+1]-f[i-1]) / two_h
+  float inv_two_h; // 1/two_h when two_h is a power of two (the division is then an exact multiply), else 0
   float a0, b0, c0;  // first sample:   a0*f0 + b0*f1 + c0*f2
   float a1, b1, c1;  // last sample:    a1*f[n-3] + b1*f[n-2] + c1*f[n-1]
 };
@@ -27,6 +30,8 @@ struct AxisCoef {  // np.gradient(edge_order=2) coefficients for one axis, alrea
 static AxisCoef make_axis(double h) {
   AxisCoef c;
   c.two_h = (float)(2.0 * h);
+  int ex = 0;
+  c.inv_two_h = (frexpf(fabsf(c.two_h), &ex) == 0.5f && ex > -100 && ex < 100) ? 1.0f / c.two_h : 0.f;
   c.a0 = (float)(-1.5 / h); c.b0 = (float)(2.0 / h); c.c0 = (float)(-0.5 / h);
   c.a1 = (float)(0.5 / h);  c.b1 = (float)(-2.0 / h); c.c1 = (float)(1.5 / h);
   return c;
@@ -47,7 +52,7 @@ struct GradParams {
 
 // NaN-aware sigma=1 Gaussian at one pixel (handle_nan_with_gaussian, mode='nearest'): separable,
 // axis 0 first, f64 accumulation in scipy's symmetric order, f32 between the passes.
-__device__ float gap_fill(const GradParams& p, int64_t gy, int64_t gx) {
+__device__ __noinline__ float gap_fill(const GradParams& p, int64_t gy, int64_t gx) {
   float colv[9], colw[9];
 #pragma unroll 1
   for (int k = 0; k < 9; ++k) {
@@ -94,20 +99,21 @@ __device__ __forceinline__ float deriv(const float* f, int s, int64_t g, int64_t
   return (f[s] - f[-s]) / c.two_h;
 }
 
-template <int CLASS>  // 0 hillshade, 1 slope, 2 curvature
-__global__ void __launch_bounds__(G_THREADS) grad_kernel(GradParams p) {
-  constexpr int HALO = (CLASS == 2) ? 3 : 2;
-  constexpr int FW = GT_W + 2 * HALO + 1;  // +1: odd stride, fewer bank conflicts
-  constexpr int FH = GT_H + 2 * HALO;
-  constexpr int DW = GT_W + 4 + 1;
-  constexpr int DH = GT_H + 4;
-  __shared__ float F[FH * FW];
-  __shared__ unsigned char M[GT_H * GT_W];
-  __shared__ float DY[(CLASS == 2) ? DH * DW : 1];
-  __shared__ float DX[(CLASS == 2) ? DH * DW : 1];
+template <int CLASS>
+struct TileGeom {
+  static constexpr int HALO = (CLASS == 2) ? 3 : 2;
+  static constexpr int FW = GT_W + 2 * HALO + 1;  // +1: odd stride, fewer bank conflicts
+  static constexpr int FH = GT_H + 2 * HALO;
+  static constexpr int DW = GT_W + 4 + 1;
+  static constexpr int DH = GT_H + 4;
+};
 
-  const int64_t ty0 = p.out_row0 + (int64_t)blockIdx.y * GT_H;  // global row of tile origin
-  const int64_t tx0 = (int64_t)blockIdx.x * GT_W;
+// one 64x32 output tile with origin (ty0, tx0); all G_THREADS threads of the CTA take part
+template <int CLASS>  // 0 hillshade, 1 slope, 2 curvature
+__device__ __forceinline__ void grad_tile(const GradParams& p, int64_t ty0, int64_t tx0, float* F, unsigned char* M,
+                                          float* DY, float* DX) {
+  constexpr int HALO = TileGeom<CLASS>::HALO, FW = TileGeom<CLASS>::FW, FH = TileGeom<CLASS>::FH;
+  constexpr int DW = TileGeom<CLASS>::DW, DH = TileGeom<CLASS>::DH;
   const int tid = threadIdx.x;
 
   // ---- stage gap-filled, scaled DEM ----
@@ -204,6 +210,188 @@ __global__ void __launch_bounds__(G_THREADS) grad_kernel(GradParams p) {
   }
 }
 
+template <int CLASS>
+__global__ void __launch_bounds__(G_THREADS) grad_kernel(const __grid_constant__ GradParams p) {
+  __shared__ float F[TileGeom<CLASS>::FH * TileGeom<CLASS>::FW];
+  __shared__ unsigned char M[GT_H * GT_W];
+  __shared__ float DY[(CLASS == 2) ? TileGeom<CLASS>::DH * TileGeom<CLASS>::DW : 1];
+  __shared__ float DX[(CLASS == 2) ? TileGeom<CLASS>::DH * TileGeom<CLASS>::DW : 1];
+  grad_tile<CLASS>(p, p.out_row0 + (int64_t)blockIdx.y * GT_H, (int64_t)blockIdx.x * GT_W, F, M, DY, DX);
+}
+
+// ------------------------------------------------------------------------------------------
+// Streaming variant for hillshade / slope (16-byte aligned rows).
+// A CTA owns 1024 columns x 64 rows.  A thread owns four adjacent columns and marches down the rows
+// with the previous, current and next row in registers plus three rows of loads in flight (float4
+// loads; the two horizontal neighbours outside its four columns are scalar loads that hit L1).  The hot
+// loop has no NaN / edge handling at all: a CTA that met a NaN anywhere in the rows it loaded redoes
+// its block with the tile routine above (gap fill), and raster-edge pixels are redone with the
+// one-sided np.gradient forms.  Arithmetic: the same op-for-op sequence as grad_tile (reference:
+// _nan_utils.py:50-74, _impl_hillshade.py:20-54, _impl_slope.py:19-35).
+// ------------------------------------------------------------------------------------------
+constexpr int GS_THREADS = G_THREADS;
+constexpr int GS_VEC = 4;
+constexpr int GS_COLS = GS_THREADS * GS_VEC;
+constexpr int GS_BAND = 64;
+constexpr int GS_RING = 6;   // rows in registers: previous, current, next + 3 rows of loads in flight
+static_assert(GS_COLS % GT_W == 0 && GS_BAND % GT_H == 0, "the NaN redo walks whole tiles");
+
+__device__ __forceinline__ float filled_at(const GradParams& p, int64_t gy, int64_t gx) {
+  int64_t by = gy - p.buf_row0;
+  by = by < 0 ? 0 : (by >= p.buf_rows ? p.buf_rows - 1 : by);
+  float v = __ldg(p.dem + by * p.ld_in + gx);
+  if (v != v) v = gap_fill(p, gy, gx);
+  return v * p.zscale;
+}
+
+__device__ __forceinline__ float central(float hi, float lo, const AxisCoef& c) {
+  float d = hi - lo;
+  return c.inv_two_h != 0.f ? d * c.inv_two_h : d / c.two_h;
+}
+
+template <int CLASS>
+__device__ __forceinline__ float grad_result(const GradParams& p, float dy, float dx) {
+  if (CLASS == 0) {
+    float e = dx * p.sgx, n = dy * p.sgy;
+    float norm = sqrtf((e * e + n * n) + 1.0f);
+    float hs = (((-e) * p.lx + (-n) * p.ly) + p.lz) / norm;
+    return fminf(fmaxf(hs, 0.f), 1.f);
+  } else {
+    float s = atanf(sqrtf(dx * dx + dy * dy));
+    if (p.sub == FSG_SLOPE_DEGREE) return s * (180.0f / 3.14159274101257324f);  // npy_rad2degf
+    if (p.sub == FSG_SLOPE_PERCENT) return tanf(s) * 100.f;
+    return s;
+  }
+}
+
+// one raster-edge pixel from global memory (one-sided second-order forms of np.gradient)
+template <int CLASS>
+__device__ __noinline__ void edge_px(const GradParams& p, int64_t gy, int64_t gx) {
+  float c0 = __ldg(p.dem + (gy - p.buf_row0) * p.ld_in + gx);
+  float res;
+  if (c0 != c0) {
+    res = nanf("");
+  } else {
+    float dy, dx;
+    if (gy == 0) dy = (p.y1.a0 * filled_at(p, 0, gx) + p.y1.b0 * filled_at(p, 1, gx)) + p.y1.c0 * filled_at(p, 2, gx);
+    else if (gy == p.H - 1)
+      dy = (p.y1.a1 * filled_at(p, p.H - 3, gx) + p.y1.b1 * filled_at(p, p.H - 2, gx)) + p.y1.c1 * filled_at(p, p.H - 1, gx);
+    else dy = (filled_at(p, gy + 1, gx) - filled_at(p, gy - 1, gx)) / p.y1.two_h;
+    if (gx == 0) dx = (p.x1.a0 * filled_at(p, gy, 0) + p.x1.b0 * filled_at(p, gy, 1)) + p.x1.c0 * filled_at(p, gy, 2);
+    else if (gx == p.W - 1)
+      dx = (p.x1.a1 * filled_at(p, gy, p.W - 3) + p.x1.b1 * filled_at(p, gy, p.W - 2)) + p.x1.c1 * filled_at(p, gy, p.W - 1);
+    else dx = (filled_at(p, gy, gx + 1) - filled_at(p, gy, gx - 1)) / p.x1.two_h;
+    res = grad_result<CLASS>(p, dy, dx);
+  }
+  store_out(p.out, (gy - p.out_row0) * p.ld_out + gx, res, p.enc);
+}
+
+struct GsRow {
+  float v[GS_VEC + 2];   // columns c-1 .. c+4
+};
+
+__device__ __forceinline__ void gs_issue(const GradParams& p, int64_t gy, int64_t c, GsRow& r) {
+  const float* row = p.dem + (gy - p.buf_row0) * p.ld_in;
+  if (c + GS_VEC <= p.W) {
+    float4 q = __ldg(reinterpret_cast<const float4*>(row + c));
+    r.v[1] = q.x; r.v[2] = q.y; r.v[3] = q.z; r.v[4] = q.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < GS_VEC; ++k) r.v[1 + k] = (c + k < p.W) ? __ldg(row + c + k) : 0.f;
+  }
+  r.v[0] = c > 0 ? __ldg(row + c - 1) : 0.f;
+  r.v[5] = c + GS_VEC < p.W ? __ldg(row + c + GS_VEC) : 0.f;
+}
+
+template <int CLASS>
+__global__ void __launch_bounds__(GS_THREADS, 3) grad_stream_kernel(const __grid_constant__ GradParams p) {
+  __shared__ float F[TileGeom<CLASS>::FH * TileGeom<CLASS>::FW];
+  __shared__ unsigned char M[GT_H * GT_W];
+  const int64_t cx0 = (int64_t)blockIdx.x * GS_COLS;
+  const int64_t c = cx0 + (int64_t)threadIdx.x * GS_VEC;
+  const int64_t y0 = p.out_row0 + (int64_t)blockIdx.y * GS_BAND;
+  const int64_t yend = p.out_row0 + p.out_rows;
+  const int64_t y1 = y0 + GS_BAND < yend ? y0 + GS_BAND : yend;
+  const int64_t last_needed = y1 < p.H ? y1 : p.H - 1;   // last row any pixel of the block reads
+  const bool live = c < p.W;
+  float nanprobe = 0.f;   // becomes NaN as soon as one loaded value is NaN (or +-Inf)
+  if (live) {
+    GsRow R[GS_RING];
+#pragma unroll
+    for (int s = 0; s < GS_RING; ++s) {
+#pragma unroll
+      for (int k = 0; k < GS_VEC + 2; ++k) R[s].v[k] = 0.f;
+    }
+    if (y0 > 0) gs_issue(p, y0 - 1, c, R[0]);
+#pragma unroll
+    for (int s = 1; s < GS_RING - 1; ++s)
+      if (y0 + s - 1 <= last_needed) gs_issue(p, y0 + s - 1, c, R[s]);
+    const bool vec_out = (p.ld_out % 4 == 0) && (c + GS_VEC <= p.W);
+    const bool scale = p.zscale != 1.0f;
+    for (int64_t yb = y0; yb < y1; yb += GS_RING) {
+#pragma unroll
+      for (int s = 0; s < GS_RING; ++s) {
+        const int64_t y = yb + s;
+        if (y < y1) {
+          GsRow& prev = R[s % GS_RING];
+          GsRow& cur = R[(s + 1) % GS_RING];
+          GsRow& next = R[(s + 2) % GS_RING];
+          if (y + GS_RING - 2 <= last_needed) gs_issue(p, y + GS_RING - 2, c, R[(s + GS_RING - 1) % GS_RING]);
+          float res[GS_VEC];
+#pragma unroll
+          for (int k = 0; k < GS_VEC; ++k) {
+            float up = prev.v[k + 1], dn = next.v[k + 1], lf = cur.v[k], rt = cur.v[k + 2];
+            if (scale) { up = up * p.zscale; dn = dn * p.zscale; lf = lf * p.zscale; rt = rt * p.zscale; }
+            float dy = central(dn, up, p.y1);
+            float dx = central(rt, lf, p.x1);
+            res[k] = grad_result<CLASS>(p, dy, dx);
+          }
+          nanprobe += ((cur.v[0] + cur.v[1]) + (cur.v[2] + cur.v[3])) + (cur.v[4] + cur.v[5]);
+          if (y == y0) nanprobe += ((prev.v[1] + prev.v[2]) + (prev.v[3] + prev.v[4]));
+          if (y == y1 - 1) nanprobe += ((next.v[1] + next.v[2]) + (next.v[3] + next.v[4]));
+          nanprobe *= 0.f;
+          const int64_t o = (y - p.out_row0) * p.ld_out + c;
+          if (vec_out && p.enc.kind == FSG_OUT_F32) {
+            *reinterpret_cast<float4*>((float*)p.out + o) = make_float4(res[0], res[1], res[2], res[3]);
+          } else if (vec_out && p.enc.kind == FSG_OUT_U8) {
+            uchar4 q = make_uchar4((unsigned char)(int)encode_dn(res[0], p.enc), (unsigned char)(int)encode_dn(res[1], p.enc),
+                                   (unsigned char)(int)encode_dn(res[2], p.enc), (unsigned char)(int)encode_dn(res[3], p.enc));
+            *reinterpret_cast<uchar4*>((uint8_t*)p.out + o) = q;
+          } else {
+#pragma unroll
+            for (int k = 0; k < GS_VEC; ++k)
+              if (c + k < p.W) store_out(p.out, o + k, res[k], p.enc);
+          }
+        }
+      }
+    }
+  }
+  // ---- cold paths ----
+  if (__syncthreads_or((int)(nanprobe != nanprobe))) {
+    // a NaN (NoData) somewhere in the rows this block loaded: redo the block tile by tile with gap fill
+    for (int64_t ty = y0; ty < y1; ty += GT_H) {
+      for (int64_t tx = cx0; tx < cx0 + GS_COLS && tx < p.W; tx += GT_W) {
+        __syncthreads();
+        grad_tile<CLASS>(p, ty, tx, F, M, nullptr, nullptr);
+      }
+    }
+    return;
+  }
+  if (!live) return;
+  if (y0 == 0) {
+    for (int k = 0; k < GS_VEC; ++k) if (c + k < p.W) edge_px<CLASS>(p, 0, c + k);
+  }
+  if (y1 == p.H && p.H > 1) {
+    for (int k = 0; k < GS_VEC; ++k) if (c + k < p.W) edge_px<CLASS>(p, p.H - 1, c + k);
+  }
+  if (c == 0) {
+    for (int64_t y = y0; y < y1; ++y) edge_px<CLASS>(p, y, 0);
+  }
+  if (c <= p.W - 1 && p.W - 1 < c + GS_VEC) {
+    for (int64_t y = y0; y < y1; ++y) edge_px<CLASS>(p, y, p.W - 1);
+  }
+}
+
 static int check_window(const fsg_window* w, int need_halo, const char* who) {
   if (!w) return fail(FSG_E_INVALID, "%s: window is NULL", who);
   if (w->H_global < 3 || w->W < 3)
@@ -236,7 +424,16 @@ static int run_grad(int cls, const float* dem, void* out, const fsg_window* win,
   dim3 grid((unsigned)((p.W + GT_W - 1) / GT_W), (unsigned)((p.out_rows + GT_H - 1) / GT_H));
   cudaStream_t s = (cudaStream_t)stream;
   int slot = prof_begin(PROF_GRADIENT, s);
-  if (cls == 0) grad_kernel<0><<<grid, G_THREADS, 0, s>>>(p);
+  // streaming kernel: aligned rows, whole buffer rows available for every row it touches
+  const bool stream_ok = cls != 2 && (((uintptr_t)p.dem & 15) == 0) && (p.ld_in % 4 == 0) &&
+                         (((uintptr_t)p.out & 15) == 0) && p.buf_row0 <= (p.out_row0 > 0 ? p.out_row0 - 1 : 0) &&
+                         p.buf_row0 + p.buf_rows >= (p.out_row0 + p.out_rows < p.H ? p.out_row0 + p.out_rows + 1 : p.H) &&
+                         !getenv("FSG_GRAD_TILED");
+  if (stream_ok) {
+    dim3 sgrid((unsigned)((p.W + GS_COLS - 1) / GS_COLS), (unsigned)((p.out_rows + GS_BAND - 1) / GS_BAND));
+    if (cls == 0) grad_stream_kernel<0><<<sgrid, GS_THREADS, 0, s>>>(p);
+    else grad_stream_kernel<1><<<sgrid, GS_THREADS, 0, s>>>(p);
+  } else if (cls == 0) grad_kernel<0><<<grid, G_THREADS, 0, s>>>(p);
   else if (cls == 1) grad_kernel<1><<<grid, G_THREADS, 0, s>>>(p);
   else grad_kernel<2><<<grid, G_THREADS, 0, s>>>(p);
   prof_end(slot, s);
