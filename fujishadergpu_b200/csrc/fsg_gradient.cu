@@ -91,12 +91,17 @@ __device__ __noinline__ float gap_fill(const GradParams& p, int64_t gy, int64_t 
   return fw > 0.f ? fv / fw : 0.f;
 }
 
+// x^1.5 for x >= 0 as x*sqrt(x): two correctly rounded ops (<= 1.5 ulp; the reference's powf is not
+// correctly rounded either) instead of the ~100-instruction powf
+__device__ __forceinline__ float pow15(float x) { return x * sqrtf(x); }
+
 // derivative along one axis of a shared-memory plane; `g` is the global index along the axis,
 // `n` the raster extent, `s` the element stride along that axis.
 __device__ __forceinline__ float deriv(const float* f, int s, int64_t g, int64_t n, const AxisCoef& c) {
   if (g == 0) return (c.a0 * f[0] + c.b0 * f[s]) + c.c0 * f[2 * s];
   if (g == n - 1) return (c.a1 * f[-2 * s] + c.b1 * f[-s]) + c.c1 * f[0];
-  return (f[s] - f[-s]) / c.two_h;
+  float d = f[s] - f[-s];
+  return c.inv_two_h != 0.f ? d * c.inv_two_h : d / c.two_h;   // exact reciprocal when 2h is a power of two
 }
 
 template <int CLASS>
@@ -189,7 +194,7 @@ __device__ __forceinline__ void grad_tile(const GradParams& p, int64_t ty0, int6
       if (p.sub == FSG_CURV_MEAN) {
         float pp = dx, q = dy, r = dxx, t = dyy;
         float s = (dxy + dyx) / 2.f;
-        float den = powf((1.f + pp * pp) + q * q, 1.5f);
+        float den = pow15((1.f + pp * pp) + q * q);
         float num = ((1.f + q * q) * r - ((2.f * pp) * q) * s) + (1.f + pp * pp) * t;
         k = (-num) / (2.f * den + 1e-10f);
       } else if (p.sub == FSG_CURV_GAUSSIAN) {
@@ -197,11 +202,11 @@ __device__ __forceinline__ void grad_tile(const GradParams& p, int64_t ty0, int6
         k = (dxx * dyy - dxy * dxy) / (b * b);
       } else if (p.sub == FSG_CURV_PLANFORM) {
         float num = ((dy * dy) * dxx - ((2.f * dx) * dy) * dxy) + (dx * dx) * dyy;
-        k = (-num) / (powf(dx * dx + dy * dy, 1.5f) + 1e-10f);
+        k = (-num) / (pow15(dx * dx + dy * dy) + 1e-10f);
       } else {
         float num = ((dx * dx) * dxx + ((2.f * dx) * dy) * dxy) + (dy * dy) * dyy;
         float g2 = dx * dx + dy * dy;
-        k = (-num) / (g2 * powf((1.f + dx * dx) + dy * dy, 1.5f) + 1e-10f);
+        k = (-num) / (g2 * pow15((1.f + dx * dx) + dy * dy) + 1e-10f);
       }
       float t = tanhf(k * 100.f);
       res = powf((t + 1.f) / 2.f, (float)(1 / 2.2));
@@ -233,7 +238,6 @@ constexpr int GS_THREADS = G_THREADS;
 constexpr int GS_VEC = 4;
 constexpr int GS_COLS = GS_THREADS * GS_VEC;
 constexpr int GS_BAND = 64;
-constexpr int GS_RING = 6;   // rows in registers: previous, current, next + 3 rows of loads in flight
 static_assert(GS_COLS % GT_W == 0 && GS_BAND % GT_H == 0, "the NaN redo walks whole tiles");
 
 __device__ __forceinline__ float filled_at(const GradParams& p, int64_t gy, int64_t gx) {
@@ -304,7 +308,7 @@ __device__ __forceinline__ void gs_issue(const GradParams& p, int64_t gy, int64_
 }
 
 template <int CLASS>
-__global__ void __launch_bounds__(GS_THREADS, 3) grad_stream_kernel(const __grid_constant__ GradParams p) {
+__global__ void __launch_bounds__(GS_THREADS, 4) grad_stream_kernel(const __grid_constant__ GradParams p) {
   __shared__ float F[TileGeom<CLASS>::FH * TileGeom<CLASS>::FW];
   __shared__ unsigned char M[GT_H * GT_W];
   const int64_t cx0 = (int64_t)blockIdx.x * GS_COLS;
@@ -316,55 +320,51 @@ __global__ void __launch_bounds__(GS_THREADS, 3) grad_stream_kernel(const __grid
   const bool live = c < p.W;
   float nanprobe = 0.f;   // becomes NaN as soon as one loaded value is NaN (or +-Inf)
   if (live) {
-    GsRow R[GS_RING];
+    // prev / cur / next are the rows of the stencil; q1..q3 are rows whose loads are still in flight.
+    // The rotation is done with register moves (one loop body: the 6x unrolled form thrashed the
+    // instruction cache).
+    GsRow prev, cur, next, q1, q2, q3;
 #pragma unroll
-    for (int s = 0; s < GS_RING; ++s) {
-#pragma unroll
-      for (int k = 0; k < GS_VEC + 2; ++k) R[s].v[k] = 0.f;
-    }
-    if (y0 > 0) gs_issue(p, y0 - 1, c, R[0]);
-#pragma unroll
-    for (int s = 1; s < GS_RING - 1; ++s)
-      if (y0 + s - 1 <= last_needed) gs_issue(p, y0 + s - 1, c, R[s]);
+    for (int k = 0; k < GS_VEC + 2; ++k) prev.v[k] = cur.v[k] = next.v[k] = q1.v[k] = q2.v[k] = q3.v[k] = 0.f;
+    if (y0 > 0) gs_issue(p, y0 - 1, c, prev);
+    gs_issue(p, y0, c, cur);
+    if (y0 + 1 <= last_needed) gs_issue(p, y0 + 1, c, next);
+    if (y0 + 2 <= last_needed) gs_issue(p, y0 + 2, c, q1);
+    if (y0 + 3 <= last_needed) gs_issue(p, y0 + 3, c, q2);
     const bool vec_out = (p.ld_out % 4 == 0) && (c + GS_VEC <= p.W);
     const bool scale = p.zscale != 1.0f;
-    for (int64_t yb = y0; yb < y1; yb += GS_RING) {
+    nanprobe += ((prev.v[1] + prev.v[2]) + (prev.v[3] + prev.v[4]));
+#pragma unroll 1
+    for (int64_t y = y0; y < y1; ++y) {
+      if (y + 4 <= last_needed) gs_issue(p, y + 4, c, q3);
+      float res[GS_VEC];
 #pragma unroll
-      for (int s = 0; s < GS_RING; ++s) {
-        const int64_t y = yb + s;
-        if (y < y1) {
-          GsRow& prev = R[s % GS_RING];
-          GsRow& cur = R[(s + 1) % GS_RING];
-          GsRow& next = R[(s + 2) % GS_RING];
-          if (y + GS_RING - 2 <= last_needed) gs_issue(p, y + GS_RING - 2, c, R[(s + GS_RING - 1) % GS_RING]);
-          float res[GS_VEC];
-#pragma unroll
-          for (int k = 0; k < GS_VEC; ++k) {
-            float up = prev.v[k + 1], dn = next.v[k + 1], lf = cur.v[k], rt = cur.v[k + 2];
-            if (scale) { up = up * p.zscale; dn = dn * p.zscale; lf = lf * p.zscale; rt = rt * p.zscale; }
-            float dy = central(dn, up, p.y1);
-            float dx = central(rt, lf, p.x1);
-            res[k] = grad_result<CLASS>(p, dy, dx);
-          }
-          nanprobe += ((cur.v[0] + cur.v[1]) + (cur.v[2] + cur.v[3])) + (cur.v[4] + cur.v[5]);
-          if (y == y0) nanprobe += ((prev.v[1] + prev.v[2]) + (prev.v[3] + prev.v[4]));
-          if (y == y1 - 1) nanprobe += ((next.v[1] + next.v[2]) + (next.v[3] + next.v[4]));
-          nanprobe *= 0.f;
-          const int64_t o = (y - p.out_row0) * p.ld_out + c;
-          if (vec_out && p.enc.kind == FSG_OUT_F32) {
-            *reinterpret_cast<float4*>((float*)p.out + o) = make_float4(res[0], res[1], res[2], res[3]);
-          } else if (vec_out && p.enc.kind == FSG_OUT_U8) {
-            uchar4 q = make_uchar4((unsigned char)(int)encode_dn(res[0], p.enc), (unsigned char)(int)encode_dn(res[1], p.enc),
-                                   (unsigned char)(int)encode_dn(res[2], p.enc), (unsigned char)(int)encode_dn(res[3], p.enc));
-            *reinterpret_cast<uchar4*>((uint8_t*)p.out + o) = q;
-          } else {
-#pragma unroll
-            for (int k = 0; k < GS_VEC; ++k)
-              if (c + k < p.W) store_out(p.out, o + k, res[k], p.enc);
-          }
-        }
+      for (int k = 0; k < GS_VEC; ++k) {
+        float up = prev.v[k + 1], dn = next.v[k + 1], lf = cur.v[k], rt = cur.v[k + 2];
+        if (scale) { up = up * p.zscale; dn = dn * p.zscale; lf = lf * p.zscale; rt = rt * p.zscale; }
+        float dy = central(dn, up, p.y1);
+        float dx = central(rt, lf, p.x1);
+        res[k] = grad_result<CLASS>(p, dy, dx);
       }
+      nanprobe += ((cur.v[0] + cur.v[1]) + (cur.v[2] + cur.v[3])) + (cur.v[4] + cur.v[5]);
+      nanprobe *= 0.f;
+      const int64_t o = (y - p.out_row0) * p.ld_out + c;
+      if (vec_out && p.enc.kind == FSG_OUT_F32) {
+        *reinterpret_cast<float4*>((float*)p.out + o) = make_float4(res[0], res[1], res[2], res[3]);
+      } else if (vec_out && p.enc.kind == FSG_OUT_U8) {
+        uchar4 q = make_uchar4((unsigned char)(int)encode_dn(res[0], p.enc), (unsigned char)(int)encode_dn(res[1], p.enc),
+                               (unsigned char)(int)encode_dn(res[2], p.enc), (unsigned char)(int)encode_dn(res[3], p.enc));
+        *reinterpret_cast<uchar4*>((uint8_t*)p.out + o) = q;
+      } else {
+#pragma unroll
+        for (int k = 0; k < GS_VEC; ++k)
+          if (c + k < p.W) store_out(p.out, o + k, res[k], p.enc);
+      }
+      prev = cur; cur = next; next = q1; q1 = q2; q2 = q3;
     }
+    // the row below the block (read as `next` of the last row) is `cur` after the final rotation
+    nanprobe += ((cur.v[1] + cur.v[2]) + (cur.v[3] + cur.v[4]));
+    nanprobe *= 0.f;
   }
   // ---- cold paths ----
   if (__syncthreads_or((int)(nanprobe != nanprobe))) {
