@@ -8,6 +8,7 @@ import logging
 from typing import Optional
 
 from .. import _device as _dev
+from .. import kernels as _k
 
 logger = logging.getLogger(__name__)
 
@@ -95,7 +96,9 @@ def compute_norm_stats_device(dem, algorithm: str, params: dict, *, grid: int = 
     pooled = []
     for wy0, wx0, tw, th in stratified_windows(W, H, by0, by1, bx0, bx1, grid=grid, tile=min(tile, max(W, H))):
         win = t[wy0:wy0 + th, wx0:wx0 + tw]
-        if float(torch.isfinite(win).float().mean()) < min_valid_frac:
+        # valid fraction of the window: one counting pass of the selection kernel (rank < 0 only counts)
+        _, _, n_valid = _k.order_stats([win], -1, take_abs=False, finite_only=True)
+        if n_valid < min_valid_frac * float(win.numel()):
             continue
         raw = _dev.as_tensor(block_func(win, **kw))
         m = int(min(margin, raw.shape[0] // 3, raw.shape[1] // 3))

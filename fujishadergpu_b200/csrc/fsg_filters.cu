@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(256) gauss_axis0_kernel(Grid g, const double* 
                                                           const int* run_flag, int64_t oy0, int64_t oh) {
   if (run_flag && *run_flag == 0) return;
   int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t yl = (int64_t)blockIdx.y + (int64_t)blockIdx.z * 32768;
-  if (x >= g.w || yl >= oh) return;
+  if (x >= g.w) return;
+  for (int64_t yl = blockIdx.y; yl < oh; yl += gridDim.y) {   // few CTAs: the flag check is the common case
   const int64_t y = oy0 + yl;
   auto at = [&](int64_t yy, double* ok) {
     float v = g.src[(clamp_index(yy, g.h) - g.row_off) * g.ld + x];
@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256) gauss_axis0_kernel(Grid g, const double* 
   }
   tv[yl * g.w + x] = (float)sv;
   tw[yl * g.w + x] = (float)sw;
+  }
 }
 
 __global__ void __launch_bounds__(256) gauss_axis1_kernel(const float* __restrict__ tv, const float* __restrict__ tw,
@@ -141,11 +142,11 @@ __global__ void __launch_bounds__(256) gauss_axis1_kernel(const float* __restric
                                                           int* still_nan) {
   if (run_flag && *run_flag == 0) return;
   int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t y = (int64_t)blockIdx.y + (int64_t)blockIdx.z * 32768;
-  if (x >= w || y >= h) return;
+  if (x >= w) return;
+  for (int64_t y = blockIdx.y; y < h; y += gridDim.y) {
   if (combine == COMBINE_VOIDFILL) {
     float cur = out[y * w + x];
-    if (cur == cur) return;  // only void cells are candidates
+    if (cur == cur) continue;  // only void cells are candidates
   }
   const float* rv = tv + y * w;
   const float* rw = tw + y * w;
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(256) gauss_axis1_kernel(const float* __restric
   } else {
     if (fw > 0.5f) out[y * w + x] = fv / fmaxf(fw, 1e-6f);
     else if (still_nan) *still_nan = 1;
+  }
   }
 }
 
@@ -204,7 +206,10 @@ int launch_gauss_taps(double sigma, int radius, double* taps_dev, cudaStream_t s
 int launch_gauss_axis0(const Grid& g, const double* taps_dev, int radius, float* tv, float* tw, const int* run_flag,
                        int64_t oy0, int64_t oh, cudaStream_t s) {
   if (oh <= 0) return FSG_OK;
-  dim3 grid((unsigned)((g.w + 255) / 256), (unsigned)(oh < 32768 ? oh : 32768), (unsigned)((oh + 32767) / 32768));
+  const int64_t gx = (g.w + 255) / 256;
+  int64_t gy = (148 * 16 + gx - 1) / gx;   // ~16 CTAs per SM in total, rows are strided over
+  if (gy > oh) gy = oh;
+  dim3 grid((unsigned)gx, (unsigned)gy);
   gauss_axis0_kernel<<<grid, 256, 0, s>>>(g, taps_dev, radius, tv, tw, run_flag, oy0, oh);
   FSG_LAUNCH_OK();
   return FSG_OK;
@@ -212,7 +217,10 @@ int launch_gauss_axis0(const Grid& g, const double* taps_dev, int radius, float*
 
 int launch_gauss_axis1(const float* tv, const float* tw, int64_t h, int64_t w, const double* taps_dev, int radius,
                        int combine, float* out, const int* run_flag, int* still_nan, cudaStream_t s) {
-  dim3 grid((unsigned)((w + 255) / 256), (unsigned)(h < 32768 ? h : 32768), (unsigned)((h + 32767) / 32768));
+  const int64_t gx = (w + 255) / 256;
+  int64_t gy = (148 * 16 + gx - 1) / gx;
+  if (gy > h) gy = h;
+  dim3 grid((unsigned)gx, (unsigned)gy);
   gauss_axis1_kernel<<<grid, 256, 0, s>>>(tv, tw, h, w, taps_dev, radius, combine, out, run_flag, still_nan);
   FSG_LAUNCH_OK();
   return FSG_OK;

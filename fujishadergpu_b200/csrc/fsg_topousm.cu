@@ -219,6 +219,34 @@ __device__ __forceinline__ void cell_reduce(const float* sm, int row0, int col0,
   *cnt = Cn;
 }
 
+// One cell ROW of a factor >= 8 cell (the pairwise row sum of cell_reduce): used by the two-stage path of
+// pyramid_kernel, where every (cell, row) pair is reduced by its own thread and the rows are then
+// added in order by one thread per cell -- same operation order, 16x more parallelism for f = 16.
+template <int F>
+__device__ __forceinline__ void row_reduce(const float* sm, int row, int col0, float* rs_out, float* rc_out) {
+  static_assert(F >= 8, "pairwise rows only");
+  float r[8], c[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float v = sm[py_idx(row, col0 + k)];
+    bool ok = isfinite(v);
+    r[k] = ok ? v : 0.f;
+    c[k] = ok ? 1.f : 0.f;
+  }
+#pragma unroll
+  for (int j = 8; j < F; j += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = sm[py_idx(row, col0 + j + k)];
+      bool ok = isfinite(v);
+      r[k] = r[k] + (ok ? v : 0.f);
+      c[k] = c[k] + (ok ? 1.f : 0.f);
+    }
+  }
+  *rs_out = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  *rc_out = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+}
+
 // Single-column coarse grid (W <= f): NumPy coalesces the two reduced axes into ONE contiguous run of
 // f*f elements and reduces it with its pairwise routine (n<8 sequential; n<=128: 8 lanes + tree;
 // n=256: two 128-element halves).
@@ -276,9 +304,38 @@ __global__ void __launch_bounds__(256) pyramid_kernel(PyramidParams p) {
     for (int k = 0; k < 4; ++k) sm[py_idx(r, c4 + k)] = v[k];
   }
   __syncthreads();
+  __shared__ float RS[PY_ROWS * PY_COLS / 8], RC[PY_ROWS * PY_COLS / 8];
   for (int lv = 0; lv < p.n_levels; ++lv) {
     const int f = p.f[lv];
     const int cells_x = PY_COLS / f, cells_y = PY_ROWS / f;
+    if (f >= 8 && p.gw[lv] != 1) {
+      // stage 1: one (cell, row) pair per thread; stage 2: rows added in order, one cell per thread
+      for (int it = tid; it < cells_x * PY_ROWS; it += 256) {
+        int row = it / cells_x, cx = it - row * cells_x;
+        float rs, rc;
+        if (f == 8) row_reduce<8>(sm, row, cx * 8, &rs, &rc);
+        else row_reduce<16>(sm, row, cx * 16, &rs, &rc);
+        RS[it] = rs;
+        RC[it] = rc;
+      }
+      __syncthreads();
+      for (int i = tid; i < cells_x * cells_y; i += 256) {
+        int cy = i / cells_x, cx = i - cy * cells_x;
+        int64_t oy = y0 / f + cy, ox = x0 / f + cx;
+        if (oy >= p.gh[lv] || ox >= p.gw[lv]) continue;
+        float tot = RS[(cy * f) * cells_x + cx], cnt = RC[(cy * f) * cells_x + cx];
+        for (int r = 1; r < f; ++r) {
+          tot = tot + RS[(cy * f + r) * cells_x + cx];
+          cnt = cnt + RC[(cy * f + r) * cells_x + cx];
+        }
+        float out;
+        if (cnt > 0.f) out = tot / fmaxf(cnt, 1.f);
+        else { out = qnan; p.flags[lv] = 1; }
+        p.grid[lv][oy * p.gw[lv] + ox] = out;
+      }
+      __syncthreads();
+      continue;
+    }
     for (int i = tid; i < cells_x * cells_y; i += 256) {
       int cy = i / cells_x, cx = i - cy * cells_x;
       int64_t oy = y0 / f + cy, ox = x0 / f + cx;
@@ -1140,15 +1197,22 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
   if (v6_ok) nb = 6;
   else if (fast_ok && fused_fast_smem_bytes<32>(fused_R, n_levels) <= smem_cap) nb = 32;
   else if (fast_ok && fused_fast_smem_bytes<16>(fused_R, n_levels) <= smem_cap) nb = 16;
-  // bands: few enough that the (2R+1)-row warm-up per band stays small, enough CTAs to fill 148 SMs
+  // bands: whole waves of CTAs (148 SMs, one CTA each) at the smallest cost = waves x (band rows + the
+  // (2R+1)-row warm-up every band pays)
   const int64_t rows = fp.out_rows;
   int64_t strips = (W + FK_TW - 1) / FK_TW;
-  int64_t want_bands = (rows + 1023) / 2048;
-  if (want_bands < 1) want_bands = 1;
-  const int64_t min_rows = 8 * (int64_t)(2 * fused_R + 1);
-  while (strips * want_bands < 148 * 6 && (rows + 2 * want_bands - 1) / (2 * want_bands) >= min_rows) want_bands *= 2;
-  int64_t band_rows = (rows + want_bands - 1) / want_bands;
-  band_rows = (band_rows + FK_NB - 1) / FK_NB * FK_NB;
+  int64_t band_rows = (rows + FK_NB - 1) / FK_NB * FK_NB;
+  {
+    double best = 1e300;
+    const int64_t max_bands = (rows + 4 * FK_NB - 1) / (4 * FK_NB) < 512 ? (rows + 4 * FK_NB - 1) / (4 * FK_NB) : 512;
+    for (int64_t b = 1; b <= (max_bands < 1 ? 1 : max_bands); ++b) {
+      int64_t br = ((rows + b - 1) / b + FK_NB - 1) / FK_NB * FK_NB;
+      int64_t nb_ = (rows + br - 1) / br;
+      int64_t waves = (strips * nb_ + 147) / 148;
+      double cost = (double)waves * (double)(br + 2 * fused_R + 1 + 24);   // +24: per-band set-up, in row units
+      if (cost < best - 1e-9) { best = cost; band_rows = br; }
+    }
+  }
   if (band_rows > (1 << 30)) band_rows = 1 << 30;
   fp.band_rows = (int)band_rows;
   int64_t bands = (rows + band_rows - 1) / band_rows;
