@@ -12,6 +12,8 @@
 // Traffic: the 80 gathers of a CTA tile are 80 shifted copies of the tile, served by L1/L2; DRAM sees
 // the DEM about once when CTAs sweep the raster in row-major order (a +-256-row band of a 32768-wide
 // raster is 67 MB < 126 MB L2).  Algorithmic bytes: 8 B/px.
+#include <stdlib.h>
+
 #include "fsg_common.cuh"
 
 namespace fsg {
@@ -32,6 +34,8 @@ struct OpenParams {
 struct OpenSample {
   short ox, oy;
   float dist;  // f32(max(hypot(ox*sx, oy*sy), 1e-9))
+  int off;     // oy * ld_in + ox (elements)
+  float rinv;  // f32(1 / dist): division by the constant distance = multiply + one FMA correction
 };
 
 // Passed BY VALUE as a kernel parameter (read through the constant bank, broadcast to the warp):
@@ -41,7 +45,13 @@ struct OpenTable {
   OpenSample s[OP_MAX_SAMPLES];
 };
 
-__global__ void __launch_bounds__(256) openness_kernel(OpenParams p, const __grid_constant__ OpenTable tab) {
+__global__ void __launch_bounds__(256) openness_kernel(OpenParams p, const __grid_constant__ OpenTable tab, int fast_halo) {
+  if (fast_halo >= 0) {   // interior 128 x 4 tiles are done by openness_interior_kernel
+    const int64_t tx0 = (int64_t)(blockIdx.x / 2) * 128, ty0 = p.out_row0 + (int64_t)blockIdx.y * 4;
+    if (tx0 >= fast_halo && tx0 + 128 + fast_halo <= p.W && ty0 >= fast_halo && ty0 + 4 + fast_halo <= p.H &&
+        ty0 + 4 <= p.out_row0 + p.out_rows)
+      return;
+  }
   const int64_t x = (int64_t)blockIdx.x * 64 + (threadIdx.x & 63);
   const int64_t y = p.out_row0 + (int64_t)blockIdx.y * 4 + (threadIdx.x >> 6);
   if (x >= p.W || y >= p.out_row0 + p.out_rows) return;
@@ -85,6 +95,77 @@ __global__ void __launch_bounds__(256) openness_kernel(OpenParams p, const __gri
   store_out(p.out, (y - p.out_row0) * p.ld_out + x, res, p.enc);
 }
 
+
+// Interior tiles (every sample of every pixel lies inside the raster): no bounds checks, linear sample
+// offsets, and (v - c) / dist evaluated as q = d*rinv corrected by one FMA residual step, which returns
+// the correctly rounded quotient (Markstein) -- the same f32 value as the IEEE division of the generic
+// kernel, at a third of the instructions.  Two pixels per thread for more loads in flight.
+template <bool NEG>
+__global__ void __launch_bounds__(256) openness_interior_kernel(const __grid_constant__ OpenParams p,
+                                                                const __grid_constant__ OpenTable tab, int halo) {
+  const int64_t x0 = (int64_t)blockIdx.x * 128, y0 = p.out_row0 + (int64_t)blockIdx.y * 4;
+  // tiles that touch the border band are left to openness_kernel (launched over the same grid)
+  const bool interior = x0 >= halo && x0 + 128 + halo <= p.W && y0 >= halo && y0 + 4 + halo <= p.H &&
+                        y0 + 4 <= p.out_row0 + p.out_rows;
+  if (!interior) return;
+  const int64_t x = x0 + (threadIdx.x & 63);     // this thread's pixels: x and x + 64 (coalesced warp loads)
+  const int64_t y = y0 + (threadIdx.x >> 6);
+  const float* pc = p.dem + (y - p.buf_row0) * p.ld_in + x;
+  const float c0 = __ldg(pc), c1 = __ldg(pc + 64);
+  const float half_pi = (float)(3.14159265358979323846 / 2);
+  const float start = NEG ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+  float asum0 = 0.f, acnt0 = 0.f, asum1 = 0.f, acnt1 = 0.f;
+  for (int d = 0; d < p.n_dirs; ++d) {
+    float e0 = start, e1 = start;
+    const int k1 = tab.dir_start[d + 1];
+#pragma unroll 5
+    for (int k = tab.dir_start[d]; k < k1; ++k) {
+      const OpenSample sm = tab.s[k];
+      const float v0 = __ldg(pc + sm.off), v1 = __ldg(pc + sm.off + 64);
+      const float d0 = v0 - c0, d1 = v1 - c1;
+      float q0 = d0 * sm.rinv, q1 = d1 * sm.rinv;
+      const float r0 = fmaf(-q0, sm.dist, d0), r1 = fmaf(-q1, sm.dist, d1);
+      q0 = (r0 == r0) ? fmaf(r0, sm.rinv, q0) : q0;   // residual is NaN only for infinite / NaN quotients
+      q1 = (r1 == r1) ? fmaf(r1, sm.rinv, q1) : q1;
+      // a NaN sample gives a NaN quotient, which fminf / fmaxf ignore: invalid samples drop out by themselves
+      e0 = NEG ? fminf(e0, q0) : fmaxf(e0, q0);
+      e1 = NEG ? fminf(e1, q1) : fmaxf(e1, q1);
+    }
+    if (e0 != start) {   // at least one valid sample in this direction
+      float a = atanf(e0);
+      a = NEG ? fminf(half_pi, a) : fmaxf(-half_pi, a);
+      asum0 = asum0 + (NEG ? half_pi + a : half_pi - a);
+      acnt0 = acnt0 + 1.f;
+    }
+    if (e1 != start) {
+      float a = atanf(e1);
+      a = NEG ? fminf(half_pi, a) : fmaxf(-half_pi, a);
+      asum1 = asum1 + (NEG ? half_pi + a : half_pi - a);
+      acnt1 = acnt1 + 1.f;
+    }
+  }
+  float res0, res1;
+  {
+    float o = asum0 / fmaxf(acnt0, 1.f);
+    o = o / half_pi;
+    o = fminf(fmaxf(o, 0.f), 1.f);
+    res0 = powf(o, (float)(1 / 2.2));
+    if (p.stretch) res0 = fmaxf((res0 - p.stretch_lo) / p.stretch_scale, 0.f);
+    if (c0 != c0) res0 = nanf("");
+  }
+  {
+    float o = asum1 / fmaxf(acnt1, 1.f);
+    o = o / half_pi;
+    o = fminf(fmaxf(o, 0.f), 1.f);
+    res1 = powf(o, (float)(1 / 2.2));
+    if (p.stretch) res1 = fmaxf((res1 - p.stretch_lo) / p.stretch_scale, 0.f);
+    if (c1 != c1) res1 = nanf("");
+  }
+  const int64_t o = (y - p.out_row0) * p.ld_out + x;
+  store_out(p.out, o, res0, p.enc);
+  store_out(p.out, o + 64, res1, p.enc);
+}
+
 static double py_round(double v) { return nearbyint(v); }  // half-to-even, like Python's round()
 
 static int run_openness(const float* dem, void* out, const fsg_window* win, int negative, int n_dirs,
@@ -108,7 +189,26 @@ static int run_openness(const float* dem, void* out, const fsg_window* win, int 
   if (p.out_rows == 0) return FSG_OK;
   dim3 grid((unsigned)((p.W + 63) / 64), (unsigned)((p.out_rows + 3) / 4));
   int slot = prof_begin(PROF_OPENNESS, (cudaStream_t)stream);
-  openness_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, tab);
+  // interior fast path: sample offsets fit in int32,
+  // the buffer holds every row a sample of an interior tile can touch
+  bool fast = (double)p.ld_in * (double)(D + 1) < 2.0e9 && p.buf_row0 <= (p.out_row0 - D > 0 ? p.out_row0 - D : 0) &&
+              p.buf_row0 + p.buf_rows >= (p.out_row0 + p.out_rows + D < p.H ? p.out_row0 + p.out_rows + D : p.H) &&
+              !getenv("FSG_OPENNESS_GENERIC");
+  if (fast) {
+    OpenTable t2 = tab;
+    const int ns = t2.dir_start[n_dirs];
+    for (int k = 0; k < ns; ++k) {
+      t2.s[k].off = (int)((int64_t)t2.s[k].oy * p.ld_in + t2.s[k].ox);
+      t2.s[k].rinv = 1.0f / t2.s[k].dist;
+    }
+    dim3 g2((unsigned)((p.W + 127) / 128), grid.y);
+    if (p.negative) openness_interior_kernel<true><<<g2, 256, 0, (cudaStream_t)stream>>>(p, t2, D);
+    else openness_interior_kernel<false><<<g2, 256, 0, (cudaStream_t)stream>>>(p, t2, D);
+    FSG_LAUNCH_OK();
+    openness_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, t2, D);
+  } else {
+    openness_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, tab, -1);
+  }
   prof_end(slot, (cudaStream_t)stream);
   FSG_LAUNCH_OK();
   return FSG_OK;
