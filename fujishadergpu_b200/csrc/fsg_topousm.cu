@@ -400,6 +400,7 @@ struct FusedParams {
   float norm_scale;
   EncodeDev enc;
   int bulk_ok;     // v6: DEM rows are 16-byte aligned (base pointer and row stride) -> bulk async copies
+  int out_vec_ok;  // v7: output rows allow 16-byte (f32) / 4-byte (u8) vector stores
 };
 
 __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
@@ -1145,6 +1146,7 @@ static size_t fused_smem_bytes(int R) {
 
 }  // namespace fsg
 #include "fsg_topousm_v6.cuh"
+#include "fsg_topousm_v7.cuh"
 namespace fsg {
 
 // ------------------------------------------------------------------------------------------
@@ -1194,25 +1196,31 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
   for (int i = 0; i < fp.n_terms; ++i) n_fused += fp.terms[i].kind == TERM_BOX_FUSED;
   const bool v6_ok = fast_ok && fused_R <= 32 && n_levels <= V6_MAXLV && n_fused <= V6_MAXF && !getenv("FSG_FUSED_V5");
   fp.bulk_ok = (((uintptr_t)fp.dem & 15) == 0 && fp.ld_in % 4 == 0 && !getenv("FSG_NO_BULK")) ? 1 : 0;
-  if (v6_ok) nb = 6;
+  // v7 (role-split pipeline) is bit-identical but measured 1.6x slower than v6 on B200 (10 warps per SM do not
+  // hide the latencies of either role, see profiles/): opt-in only
+  bool v7_ok = v6_ok && n_fused >= 1 && n_levels <= V7_MAXLV && getenv("FSG_FUSED_V7") != nullptr;
+  for (int l = 0; l < n_levels; ++l) v7_ok = v7_ok && fp.lvl_cscale[l] <= 0.25;   // decimation >= 4 (V7_KMAX cells)
+  {
+    const size_t esz = out_elem_size(fp.enc.kind);
+    const uintptr_t need = fp.enc.kind == FSG_OUT_F32 ? 15 : 3;
+    fp.out_vec_ok = (((uintptr_t)fp.out & need) == 0 && fp.ld_out % 4 == 0 && esz != 2) ? 1 : 0;
+  }
+  if (v7_ok) nb = 7;
+  else if (v6_ok) nb = 6;
   else if (fast_ok && fused_fast_smem_bytes<32>(fused_R, n_levels) <= smem_cap) nb = 32;
   else if (fast_ok && fused_fast_smem_bytes<16>(fused_R, n_levels) <= smem_cap) nb = 16;
-  // bands: whole waves of CTAs (148 SMs, one CTA each) at the smallest cost = waves x (band rows + the
-  // (2R+1)-row warm-up every band pays)
+  // bands: few enough that the (2R+1)-row warm-up per band stays small, enough CTAs (>= 6 per SM when the
+  // raster allows) that the slower edge strips and the SM-to-SM spread average out.  (A "fewest waves"
+  // model was tried and lost 25 %: one or two waves leave the chip waiting for the edge-strip CTAs.)
   const int64_t rows = fp.out_rows;
-  int64_t strips = (W + FK_TW - 1) / FK_TW;
-  int64_t band_rows = (rows + FK_NB - 1) / FK_NB * FK_NB;
-  {
-    double best = 1e300;
-    const int64_t max_bands = (rows + 4 * FK_NB - 1) / (4 * FK_NB) < 512 ? (rows + 4 * FK_NB - 1) / (4 * FK_NB) : 512;
-    for (int64_t b = 1; b <= (max_bands < 1 ? 1 : max_bands); ++b) {
-      int64_t br = ((rows + b - 1) / b + FK_NB - 1) / FK_NB * FK_NB;
-      int64_t nb_ = (rows + br - 1) / br;
-      int64_t waves = (strips * nb_ + 147) / 148;
-      double cost = (double)waves * (double)(br + 2 * fused_R + 1 + 24);   // +24: per-band set-up, in row units
-      if (cost < best - 1e-9) { best = cost; band_rows = br; }
-    }
-  }
+  const int tw = nb == 7 ? V7_TW : FK_TW;
+  int64_t strips = (W + tw - 1) / tw;
+  int64_t want_bands = (rows + 1023) / 2048;
+  if (want_bands < 1) want_bands = 1;
+  const int64_t min_rows = 8 * (int64_t)(2 * fused_R + 1);
+  while (strips * want_bands < 148 * 6 && (rows + 2 * want_bands - 1) / (2 * want_bands) >= min_rows) want_bands *= 2;
+  int64_t band_rows = (rows + want_bands - 1) / want_bands;
+  band_rows = (band_rows + FK_NB - 1) / FK_NB * FK_NB;
   if (band_rows > (1 << 30)) band_rows = 1 << 30;
   fp.band_rows = (int)band_rows;
   int64_t bands = (rows + band_rows - 1) / band_rows;
@@ -1221,12 +1229,15 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
   size_t smem = nb == 32 ? fused_fast_smem_bytes<32>(fused_R, n_levels)
                          : (nb == 16 ? fused_fast_smem_bytes<16>(fused_R, n_levels) : fused_smem_bytes(fused_R));
   if (nb == 6) smem = V6Geom<32>::BYTES;
-  if (nb == 6) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v6<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (nb == 7) smem = V7Geom<32>::BYTES;
+  if (nb == 7) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v7<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (nb == 6) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v6<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (nb == 32) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (nb == 16) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int slot = prof_begin(PROF_TOPOUSM_FUSED, s);
-  if (nb == 6) fused_kernel_v6<32><<<grid, FK_THREADS, smem, s>>>(fp);
+  if (nb == 7) fused_kernel_v7<32><<<grid, V7_THREADS, smem, s>>>(fp);
+  else if (nb == 6) fused_kernel_v6<32><<<grid, FK_THREADS, smem, s>>>(fp);
   else if (nb == 32) fused_kernel_fast<32><<<grid, FK_THREADS, smem, s>>>(fp);
   else if (nb == 16) fused_kernel_fast<16><<<grid, FK_THREADS, smem, s>>>(fp);
   else fused_kernel<<<grid, FK_THREADS, smem, s>>>(fp);

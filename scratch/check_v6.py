@@ -8,7 +8,7 @@ W6 = [32 / 63, 16 / 63, 8 / 63, 4 / 63, 2 / 63, 1 / 63]
 
 
 def run(d, radii, w, env, **kw):
-    for key in ("FSG_FORCE_GENERIC", "FSG_FUSED_V5", "FSG_NO_BULK"):
+    for key in ("FSG_FORCE_GENERIC", "FSG_FUSED_V5", "FSG_FUSED_V7", "FSG_NO_BULK"):
         os.environ.pop(key, None)
     for key in env:
         os.environ[key] = "1"
@@ -29,7 +29,7 @@ def same(a, b):
 
 
 fails = 0
-cases = [((1000, 1500), True), ((1000, 1500), False), ((3000, 2900), False), ((2051, 1797), True), ((4096, 4096), False),
+cases = [((64, 5000), True), ((40, 300), False), ((1000, 1500), True), ((1000, 1500), False), ((3000, 2900), False), ((2051, 1797), True), ((4096, 4096), False),
          ((700, 5000), True), ((5000, 300), False), ((129, 264 * 3), True), ((4096 + 17, 2048 + 5), True)]
 for shape, nod in cases:
     d = k.synth_dem(shape, seed=11 + shape[0], nodata=nod)
@@ -39,7 +39,7 @@ for shape, nod in cases:
     for radii, w in (([2, 8, 32, 128, 512, 2048], W6), ([2, 8, 32], [4 / 7, 2 / 7, 1 / 7]), ([128, 3, 17], [0.2, 0.5, 0.3]),
                      ([32], [1.0]), ([50, 2], [0.5, 0.5])):
         ref = run(d, radii, w, ["FSG_FORCE_GENERIC"])
-        for env in ([], ["FSG_NO_BULK"], ["FSG_FUSED_V5"]):
+        for env in ([], ["FSG_NO_BULK"], ["FSG_FUSED_V7"]):
             got = run(d, radii, w, env)
             ok, msg = same(ref, got)
             if not ok:
@@ -67,7 +67,7 @@ S = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 d = k.synth_dem((S, S))
 ws = torch.empty(max(256, k.topousm_fast_workspace_bytes((S, S), [2, 8, 32, 128, 512, 2048], 1.0)), dtype=torch.uint8, device="cuda")
 out = torch.empty((S, S), dtype=torch.float32, device="cuda")
-for name, env in (("v5", ["FSG_FUSED_V5"]), ("v6", []), ("v6 nobulk", ["FSG_NO_BULK"])):
+for name, env in (("v5", ["FSG_FUSED_V5"]), ("v6", []), ("v6 nobulk", ["FSG_NO_BULK"]), ("v7", ["FSG_FUSED_V7"])):
     for radii, w in (([2, 8, 32, 128, 512, 2048], W6), ([2, 8, 32], [4 / 7, 2 / 7, 1 / 7]), ([128, 512, 2048], [4 / 7, 2 / 7, 1 / 7]), ([2], [1.0])):
         run(d, radii, w, env, workspace=ws, out=out)
         k.profile_enable(True)
