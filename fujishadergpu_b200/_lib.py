@@ -61,6 +61,9 @@ _SIGNATURES = {
     "fsg_encode_f32": (_I, [_P, _P, _L, C.POINTER(Encode), _P]),
     "fsg_scale_f32": (_I, [_P, _P, _L, _D, _P]),
     "fsg_stretch_f32": (_I, [_P, _P, _L, _D, _D, _P]),
+    "fsg_gaussian_nan_workspace_bytes": (C.c_size_t, [_L, _L, _D]),
+    "fsg_gaussian_nan": (_I, [_P, _P, _L, _L, _L, _D, _P, C.c_size_t, _P]),
+    "fsg_combine_f32": (_I, [_P, _P, _L, _D, _I, _P]),
     "fsg_order_stats_workspace_bytes": (C.c_size_t, []),
     "fsg_order_stats": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, _L, _I, _I,
                              _P, _P, C.c_size_t, _P]),

@@ -99,6 +99,74 @@ def _upsample_to_shape(block, target_shape):
     return _dev.like_input(_k.upsample(block, target_shape), block)
 
 
+def handle_nan_with_gaussian(block, sigma: float, mode: str = "nearest"):
+    """reference :18-31 -- (smoothed, nan_mask); the NaN-aware Gaussian runs in libfsg_b200."""
+    import torch
+    if str(mode) != "nearest":
+        raise NotImplementedError("handle_nan_with_gaussian: only mode='nearest' is on the B200 path")
+    t = _dev.as_f32_2d(block)
+    return _dev.like_input(_k.gaussian_nan(t, float(sigma)), block), torch.isnan(t)
+
+
+def _smooth_for_radius(block, radius: float, *, pixel_size: float = 1.0, algorithm_name: str = "default"):
+    """reference :527-552 -- NaN-aware Gaussian smoothing controlled by the spatial radius
+    (sigma = max(0.5, r/2); decimate -> smooth -> zoom back for large radii)."""
+    r = max(1.0, float(radius))
+    if r <= 1.0:
+        return block
+    factor = _radius_to_downsample_factor(r, block_shape=tuple(block.shape), pixel_size=pixel_size,
+                                          algorithm_name=algorithm_name)
+    if factor <= 1:
+        return handle_nan_with_gaussian(block, sigma=max(0.5, r / 2.0), mode="nearest")[0]
+    reduced = _downsample_nan_aware(block, factor)
+    small = handle_nan_with_gaussian(reduced, sigma=max(0.5, (r / factor) / 2.0), mode="nearest")[0]
+    return _upsample_to_shape(small, tuple(block.shape))
+
+
+def large_radius_threshold(block, fallback: int) -> int:
+    """reference :219-228 with one block == one chunk: max(256, min(H, W) // 16)."""
+    try:
+        min_chunk = min(int(block.shape[0]), int(block.shape[1]))
+    except Exception:
+        min_chunk = int(fallback)
+    return int(max(256, int(min_chunk) // 16))
+
+
+def _accumulate(responses, weights32, first_mode: str):
+    import torch
+    acc = torch.empty_like(_dev.as_f32_2d(responses[0]))
+    for i, resp in enumerate(responses):
+        _k.combine(acc, _dev.as_f32_2d(resp), float(weights32[i]), first_mode if i == 0 else "add_weighted")
+    return acc
+
+
+def _combine_multiscale_dask(responses, *, weights=None, agg: str = "mean"):
+    """reference :182-213 on device blocks: stack / max / min / sum / weighted mean (weights cleaned and
+    L1-normalised in Python floats, each used as an f32 scalar) / plain mean."""
+    import torch
+    if not responses:
+        raise ValueError("responses must not be empty")
+    a = str(agg or "mean").lower()
+    if a == "stack":
+        return _dev.like_input(torch.stack([_dev.as_f32_2d(r) for r in responses], dim=0), responses[0])
+    if len(responses) == 1:
+        return responses[0]
+    if a in ("max", "min"):
+        acc = _dev.as_f32_2d(responses[0]).clone()
+        for r in responses[1:]:
+            _k.combine(acc, _dev.as_f32_2d(r), 1.0, a)
+        return _dev.like_input(acc, responses[0])
+    if a == "sum":   # da.sum over the stacked axis: pairwise only from 8 items on, i.e. in order here
+        return _dev.like_input(_accumulate(responses, [1.0] * len(responses), "copy"), responses[0])
+    if _weight_count_matches(weights, len(responses)):
+        clean = _clean_normalized_weights(weights)
+        if clean is not None:
+            return _dev.like_input(_accumulate(responses, [np.float32(w) for w in clean], "first_weighted"), responses[0])
+    # da.mean = sum / n
+    acc = _accumulate(responses, [1.0] * len(responses), "copy")
+    return _dev.like_input(_k.scale(acc, float(len(responses))), responses[0])
+
+
 def _bilinear_sample_coarse(coarse, r0: int, r1: int, c0: int, c1: int, full_h: int, full_w: int):
     """reference :255-281 (through the fused large-part kernel with w_large = 0 on a zero block)."""
     import torch
@@ -111,5 +179,6 @@ def _bilinear_sample_coarse(coarse, r0: int, r1: int, c0: int, c1: int, full_h: 
 __all__ = [
     "_radius_to_downsample_factor", "_resolve_spatial_radii_weights", "_normalize_spatial_radii",
     "_clean_normalized_weights", "_weight_count_matches", "_downsample_nan_aware", "_upsample_to_shape",
-    "_bilinear_sample_coarse",
+    "_bilinear_sample_coarse", "handle_nan_with_gaussian", "_smooth_for_radius", "large_radius_threshold",
+    "_combine_multiscale_dask",
 ]

@@ -22,11 +22,40 @@ def _merged_params(algo, params):
     return merged
 
 
+def _combine_direct(responses, *, weights=None, agg="mean"):
+    """reference :28-69 -- stack / max / min / sum / f32-normalised weighted mean / equal mean."""
+    import numpy as np
+    import torch
+    from .._nan_utils import _accumulate, _combine_multiscale_dask
+    if not responses:
+        raise ValueError("responses must not be empty")
+    a = str(agg or "mean").lower()
+    if a == "stack" or len(responses) == 1 or a in ("max", "min"):
+        return _combine_multiscale_dask(responses, agg=a)
+    if a == "sum":
+        return _dev.like_input(_accumulate(responses, [1.0] * len(responses), "first_from_zero"), responses[0])
+    if isinstance(weights, (list, tuple)) and len(weights) == len(responses):
+        w = np.asarray(weights, dtype=np.float32)
+        if np.isfinite(w).all() and float(w.sum()) > 0:
+            w = w / float(w.sum())
+            return _dev.like_input(_accumulate(responses, [float(x) for x in w], "first_weighted"), responses[0])
+    inv = np.float32(1.0 / float(len(responses)))
+    return _dev.like_input(_accumulate(responses, [float(inv)] * len(responses), "first_from_zero"), responses[0])
+
+
 def _direct_hillshade(block, p):
+    from .._impl_hillshade import compute_hillshade_spatial_block
     radii = p.get("radii", [1])
-    if isinstance(radii, (list, tuple)) and len(radii) > 1:
-        raise NotImplementedError("hillshade: multi-radius (spatial) tiles are not on the B200 path yet")
+    if not isinstance(radii, (list, tuple)) or len(radii) == 0:
+        radii = [1]
+    radii = [max(1.0, float(r)) for r in radii]
     z = p.get("z_factor", 1.0)
+    if bool(p.get("multiscale", False) or len(radii) > 1) and len(radii) > 1:   # reference :94-104
+        responses = [compute_hillshade_spatial_block(
+            block, azimuth=p.get("azimuth", Constants.DEFAULT_AZIMUTH), altitude=p.get("altitude", Constants.DEFAULT_ALTITUDE),
+            z_factor=1.0 if z is None else z, pixel_size=p.get("pixel_size", 1.0), pixel_scale_x=p.get("pixel_scale_x"),
+            pixel_scale_y=p.get("pixel_scale_y"), radius=float(r)) for r in radii]
+        return _combine_direct(responses, weights=p.get("weights"), agg=p.get("agg", "mean"))
     return _dev.like_input(_k.hillshade(
         block, azimuth=p.get("azimuth", Constants.DEFAULT_AZIMUTH), altitude=p.get("altitude", Constants.DEFAULT_ALTITUDE),
         z_factor=1.0 if z is None else z, pixel_size=p.get("pixel_size", 1.0),
@@ -75,7 +104,7 @@ _DIRECT = {
 def _process_direct(algo, class_name, dem_gpu, params):
     p = _merged_params(algo, params)
     if str(p.get("mode", "local")).lower() == "spatial" and class_name in _DIRECT:
-        return algo.process(dem_gpu, **p)   # raises NotImplementedError where 8f-next
+        return algo.process(dem_gpu, **p)   # the reference falls back to a single-chunk dask graph here (:340-346)
     if class_name in _DIRECT:
         return _DIRECT[class_name](dem_gpu, p)
     if class_name == "TopoUSMFastAlgorithm":

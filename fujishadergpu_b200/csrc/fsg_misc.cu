@@ -1,5 +1,5 @@
 // Elementwise helpers: integer encoding, normalise, display stretch, synthetic DEM generator.
-#include "fsg_common.cuh"
+#include "fsg_filters.cuh"
 
 namespace fsg {
 
@@ -78,6 +78,41 @@ __global__ void synth_kernel(float* out, int64_t H, int64_t W, int64_t row0, int
   }
 }
 
+// Gaussian taps computed on the HOST (glibc exp, like scipy's kernel) and handed over by value
+constexpr int TAPS_MAX = 448;
+struct TapsParam {
+  int n;
+  double w[TAPS_MAX];
+};
+__global__ void store_taps_kernel(const __grid_constant__ TapsParam tp, double* dst) {
+  for (int i = threadIdx.x; i < tp.n; i += blockDim.x) dst[i] = tp.w[i];
+}
+
+// _combine_direct (algorithms/tile/dask_bridge.py:28-69), one response at a time.
+// mode 0: acc = a*w            (first weighted response)
+//      1: acc = acc + a*w      (further responses; also the equal-weight mean with w = 1/n)
+//      2: acc = 0 + a*w        (first response of the equal-weight mean / sum: the reference starts from zeros)
+//      3: acc = np.maximum(acc, a)   4: acc = np.minimum(acc, a)   (NaN propagates like NumPy)
+//      5: acc = a
+__global__ void combine_kernel(const float* __restrict__ a, float* __restrict__ acc, int64_t n, float w, int mode) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += step) {
+    float v = a[i];
+    float r;
+    if (mode == 0) r = v * w;
+    else if (mode == 1) r = acc[i] + v * w;
+    else if (mode == 2) r = 0.f + v * w;
+    else if (mode == 5) r = v;
+    else {
+      float c = acc[i];
+      if (v != v || c != c) r = nanf("");
+      else r = mode == 3 ? fmaxf(c, v) : fminf(c, v);
+    }
+    acc[i] = r;
+  }
+}
+
 static int grid_for(int64_t n) {
   int64_t b = (n + 255) / 256;
   int64_t cap = 148 * 16;
@@ -114,6 +149,53 @@ int fsg_stretch_f32(const float* in, float* out, int64_t n, double lo, double sc
   if (!in || !out) return fail(FSG_E_INVALID, "fsg_stretch_f32: NULL argument");
   if (n <= 0) return FSG_OK;
   stretch_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(in, out, n, (float)lo, (float)scale);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+size_t fsg_gaussian_nan_workspace_bytes(int64_t H, int64_t W, double sigma) {
+  if (H < 1 || W < 1 || !(sigma > 0.0)) return 0;
+  int r = (int)(4.0 * sigma + 0.5);
+  size_t plane = ((size_t)H * (size_t)W * 4 + 255) / 256 * 256;
+  return 2 * plane + ((size_t)(r + 1) * 8 + 255) / 256 * 256;
+}
+
+/* handle_nan_with_gaussian(block, sigma, mode='nearest')[0]  (algorithms/_nan_utils.py:18-31) */
+int fsg_gaussian_nan(const float* in, float* out, int64_t H, int64_t W, int64_t ld_in, double sigma, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  using namespace fsg;
+  if (!in || !out || H < 1 || W < 1 || ld_in < W || !(sigma > 0.0))
+    return fail(FSG_E_INVALID, "fsg_gaussian_nan: bad argument");
+  size_t need = fsg_gaussian_nan_workspace_bytes(H, W, sigma);
+  if (!workspace || workspace_bytes < need)
+    return fail(FSG_E_WORKSPACE, "fsg_gaussian_nan: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t plane = ((size_t)H * (size_t)W * 4 + 255) / 256 * 256;
+  float* tv = (float*)workspace;
+  float* tw = (float*)((unsigned char*)workspace + plane);
+  double* taps = (double*)((unsigned char*)workspace + 2 * plane);
+  int radius = (int)(4.0 * sigma + 0.5);
+  int rc;
+  if (radius + 1 <= TAPS_MAX) {
+    TapsParam tp;
+    tp.n = radius + 1;
+    if (gauss_half_taps(sigma, tp.w, TAPS_MAX - 1) != radius) return fail(FSG_E_INVALID, "fsg_gaussian_nan: taps");
+    store_taps_kernel<<<1, 256, 0, s>>>(tp, taps);
+    FSG_LAUNCH_OK();
+  } else if ((rc = launch_gauss_taps(sigma, radius, taps, s))) {
+    return rc;
+  }
+  Grid g{in, H, W, ld_in};
+  if ((rc = launch_gauss_axis0(g, taps, radius, tv, tw, nullptr, 0, H, s))) return rc;
+  return launch_gauss_axis1(tv, tw, H, W, taps, radius, COMBINE_MEAN, out, nullptr, nullptr, s);
+}
+
+int fsg_combine_f32(const float* a, float* acc, int64_t n, double w, int mode, void* stream) {
+  using namespace fsg;
+  if (!a || !acc) return fail(FSG_E_INVALID, "fsg_combine_f32: NULL argument");
+  if (mode < 0 || mode > 5) return fail(FSG_E_INVALID, "fsg_combine_f32: unknown mode %d", mode);
+  if (n <= 0) return FSG_OK;
+  combine_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(a, acc, n, (float)w, mode);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }

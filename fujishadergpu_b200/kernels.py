@@ -235,6 +235,32 @@ def stretch(arr, lo: float, scale_value: float) -> torch.Tensor:
     return out
 
 
+def gaussian_nan(block, sigma: float) -> torch.Tensor:
+    """handle_nan_with_gaussian(block, sigma, mode='nearest')[0] (reference _nan_utils.py:18-31)."""
+    t = dev.as_f32_2d(block)
+    H, W = int(t.shape[0]), int(t.shape[1])
+    out = torch.empty((H, W), dtype=torch.float32, device=t.device)
+    lib = _lib.load()
+    need = int(lib.fsg_gaussian_nan_workspace_bytes(H, W, float(sigma)))
+    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=t.device)
+    check(lib.fsg_gaussian_nan(_ptr(t), _ptr(out), H, W, int(t.stride(0)), float(sigma), _ptr(ws), need,
+                               C.c_void_p(dev.stream_ptr(t))), "fsg_gaussian_nan")
+    return out
+
+
+_COMBINE_MODES = {"first_weighted": 0, "add_weighted": 1, "first_from_zero": 2, "max": 3, "min": 4, "copy": 5}
+
+
+def combine(acc, resp, w: float, mode: str) -> None:
+    """One step of the reference's response combiner (in place on `acc`)."""
+    a = dev.as_tensor(resp)
+    if not a.is_contiguous():
+        a = a.contiguous()
+    assert acc.is_contiguous() and acc.dtype == torch.float32 and a.dtype == torch.float32 and acc.numel() == a.numel()
+    check(_lib.load().fsg_combine_f32(_ptr(a), _ptr(acc), int(a.numel()), float(w), _COMBINE_MODES[mode],
+                                      C.c_void_p(dev.stream_ptr(a))), "fsg_combine_f32")
+
+
 def _pooled_views(chunks):
     views = [dev.as_tensor(c) for c in chunks]
     views = [v if v.ndim == 2 else v.reshape(1, -1) for v in views]

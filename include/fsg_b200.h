@@ -189,6 +189,17 @@ int fsg_encode_f32(const float* in, void* out, int64_t n, const fsg_encode* enc,
 int fsg_scale_f32(const float* in, float* out, int64_t n, double scale, void* stream);
 int fsg_stretch_f32(const float* in, float* out, int64_t n, double lo, double scale, void* stream);
 
+/* ---- spatial mode of the gradient family --------------------------------
+ * fsg_gaussian_nan : handle_nan_with_gaussian(block, sigma, mode='nearest')[0]
+ *                    (algorithms/_nan_utils.py:18-31; the smoothing of _smooth_for_radius, :527-552)
+ * fsg_combine_f32  : one step of _combine_direct (algorithms/tile/dask_bridge.py:28-69) /
+ *                    _combine_multiscale_dask (_nan_utils.py:182-213); mode 0 acc=a*w, 1 acc+=a*w,
+ *                    2 acc=0+a*w, 3 acc=maximum(acc,a), 4 acc=minimum(acc,a), 5 acc=a */
+size_t fsg_gaussian_nan_workspace_bytes(int64_t H, int64_t W, double sigma);
+int fsg_gaussian_nan(const float* in, float* out, int64_t H, int64_t W, int64_t ld_in, double sigma,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int fsg_combine_f32(const float* a, float* acc, int64_t n, double w, int mode, void* stream);
+
 size_t fsg_order_stats_workspace_bytes(void);
 /* Pooled order statistics over up to 16 2-D chunks (|x| first when take_abs != 0; samples are the
  * non-NaN, or with finite_only the finite, values).  rank < 0: count only.  Otherwise exact radix

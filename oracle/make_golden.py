@@ -78,6 +78,43 @@ def main(out_dir: str) -> None:
     params["hillshade__dense_az45_alt30_z2"] = dict(input="dense", kw=dict(azimuth=45, altitude=30, z_factor=2.0))
     save("gradient_family", params, **arrays)
 
+    # ---------------- gradient family, spatial mode (Gaussian scale space) ----------------
+    from FujiShaderGPU.algorithms.tile import dask_bridge as db
+    sdense = synth_dem(200, 240, seed=20261031)
+    sholes = synth_dem(200, 240, seed=20261032, nodata=True)
+    sholes[90:93, 100:140] = np.nan
+    arrays = {"sdense": sdense, "sholes": sholes}
+    params = {}
+    nup = dict(pixel_scale_x=1.0, pixel_scale_y=-1.0)
+    for key, dem in (("sdense", sdense), ("sholes", sholes)):
+        for r in (2.0, 8.0, 32.0, 64.0, 300.0):
+            nm_ = f"hillshade_r{int(r)}__{key}"
+            arrays[nm_] = hs.compute_hillshade_spatial_block(dem.copy(), radius=r, **nup)
+            params[nm_] = dict(input=key, algo="hillshade", kw=dict(radius=r, **nup))
+        for r in (3.0, 40.0):
+            nm_ = f"slope_r{int(r)}__{key}"
+            arrays[nm_] = sl.compute_slope_spatial_block(dem.copy(), radius=r, unit="degree", **nup)
+            params[nm_] = dict(input=key, algo="slope", kw=dict(radius=r, unit="degree", **nup))
+        for r in (4.0, 30.0):
+            nm_ = f"curvature_r{int(r)}__{key}"
+            sm_ = nu._smooth_for_radius(dem.copy(), r, pixel_size=1.0, algorithm_name="curvature")
+            arrays[nm_] = cv.compute_curvature_block(sm_, curvature_type="mean", **nup)
+            params[nm_] = dict(input=key, algo="curvature", kw=dict(radius=r, curvature_type="mean", **nup))
+        # the tile adapter's multi-radius hillshade (tile/dask_bridge.py:72-110) and its combiner (:28-69)
+        radii = [2, 8, 32, 64]
+        wts = sm.auto_spatial_weights(4)
+        resp = [hs.compute_hillshade_spatial_block(dem.copy(), radius=float(r), **nup) for r in radii]
+        arrays[f"hillshade_multi_weighted__{key}"] = db._combine_direct(resp, weights=wts, agg="mean")
+        params[f"hillshade_multi_weighted__{key}"] = dict(input=key, algo="hillshade_multi",
+                                                          kw=dict(radii=radii, weights=list(map(float, wts)), agg="mean", **nup))
+        arrays[f"hillshade_multi_max__{key}"] = db._combine_direct(resp, weights=None, agg="max")
+        params[f"hillshade_multi_max__{key}"] = dict(input=key, algo="hillshade_multi",
+                                                     kw=dict(radii=radii, weights=None, agg="max", **nup))
+        arrays[f"hillshade_multi_equal__{key}"] = db._combine_direct(resp, weights=None, agg="mean")
+        params[f"hillshade_multi_equal__{key}"] = dict(input=key, algo="hillshade_multi",
+                                                       kw=dict(radii=radii, weights=None, agg="mean", **nup))
+    save("spatial_gradient", params, **arrays)
+
     # ---------------- topousm_fast ----------------
     tdense = synth_dem(288, 240, seed=20261019)
     tholes = synth_dem(288, 240, seed=20261020, nodata=True)

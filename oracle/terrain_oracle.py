@@ -536,6 +536,87 @@ def curvature_block(dem, *, curvature_type="mean", pixel_size=1.0, pixel_scale_x
 # --------------------------------------------------------------------------
 # a17 / a18 : openness
 # --------------------------------------------------------------------------
+# --------------------------------------------------------------------------
+# 8f-1 : spatial mode of the gradient family (Gaussian scale space)
+# --------------------------------------------------------------------------
+def smooth_for_radius(dem, radius, *, pixel_size: float = 1.0, algorithm: str = "default") -> np.ndarray:
+    """algorithms/_nan_utils.py:527-552 -- NaN-aware Gaussian (sigma = max(0.5, r/2), 'nearest'),
+    evaluated on the decimated grid and zoomed back for large radii."""
+    a = np.asarray(dem, dtype=F32)
+    r = max(1.0, float(radius))
+    if r <= 1.0:
+        return a
+    f = decimation_factor(r, pixel_size=pixel_size, algorithm=algorithm)
+    if f <= 1:
+        return gauss_mean(a, max(0.5, r / 2.0), mode="nearest")
+    small = decimate_valid_mean(a, f)
+    sm = gauss_mean(small, max(0.5, (r / f) / 2.0), mode="nearest")
+    return upsample_align_corners(sm, a.shape)
+
+
+def hillshade_spatial_block(dem, *, radius=4.0, azimuth=AZIMUTH_DEFAULT, altitude=ALTITUDE_DEFAULT, z_factor=1.0,
+                            pixel_size=1.0, pixel_scale_x=None, pixel_scale_y=None) -> np.ndarray:
+    """algorithms/_impl_hillshade.py:57-67."""
+    sm = smooth_for_radius(dem, radius, pixel_size=pixel_size, algorithm="hillshade")
+    return hillshade_block(sm, azimuth=azimuth, altitude=altitude, z_factor=z_factor, pixel_size=pixel_size,
+                           pixel_scale_x=pixel_scale_x, pixel_scale_y=pixel_scale_y)
+
+
+def slope_spatial_block(dem, *, radius=4.0, unit="degree", pixel_size=1.0, pixel_scale_x=None,
+                        pixel_scale_y=None) -> np.ndarray:
+    """algorithms/_impl_slope.py:38-45."""
+    sm = smooth_for_radius(dem, radius, pixel_size=pixel_size, algorithm="slope")
+    return slope_block(sm, unit=unit, pixel_size=pixel_size, pixel_scale_x=pixel_scale_x, pixel_scale_y=pixel_scale_y)
+
+
+def curvature_spatial_block(dem, *, radius=4.0, curvature_type="mean", pixel_size=1.0, pixel_scale_x=None,
+                            pixel_scale_y=None) -> np.ndarray:
+    """algorithms/_impl_curvature.py:72-78."""
+    sm = smooth_for_radius(dem, radius, pixel_size=pixel_size, algorithm="curvature")
+    return curvature_block(sm, curvature_type=curvature_type, pixel_size=pixel_size, pixel_scale_x=pixel_scale_x,
+                           pixel_scale_y=pixel_scale_y)
+
+
+def combine_responses(responses, *, weights=None, agg: str = "mean") -> np.ndarray:
+    """algorithms/tile/dask_bridge.py:28-69 (_combine_direct): f32 weights normalised in f32, the sum
+    accumulated in list order, every product / sum an individually rounded f32 op."""
+    if not responses:
+        raise ValueError("responses must not be empty")
+    a = str(agg or "mean").lower()
+    if a == "stack":
+        return np.stack(responses, axis=0).astype(F32, copy=False)
+    if len(responses) == 1:
+        return responses[0]
+    if a == "max":
+        out = responses[0]
+        for it in responses[1:]:
+            out = np.maximum(out, it)
+        return out.astype(F32, copy=False)
+    if a == "min":
+        out = responses[0]
+        for it in responses[1:]:
+            out = np.minimum(out, it)
+        return out.astype(F32, copy=False)
+    if a == "sum":
+        out = np.zeros_like(responses[0], dtype=F32)
+        for it in responses:
+            out = out + it
+        return out.astype(F32, copy=False)
+    if isinstance(weights, (list, tuple)) and len(weights) == len(responses):
+        w = np.asarray(weights, dtype=F32)
+        if np.isfinite(w).all() and float(w.sum()) > 0:
+            w = w / float(w.sum())
+            out = responses[0] * F32(w[0])
+            for i in range(1, len(responses)):
+                out = out + responses[i] * F32(w[i])
+            return out.astype(F32, copy=False)
+    out = np.zeros_like(responses[0], dtype=F32)
+    inv = F32(1.0 / float(len(responses)))
+    for it in responses:
+        out = out + it * inv
+    return out.astype(F32, copy=False)
+
+
 def openness_offsets(num_directions: int, max_distance: int):
     """Ray sample offsets ``[(dir, ox, oy), ...]`` and the pad depth D
     (algorithms/_impl_openness.py:58-68, 96-100).  Python banker's ``round``."""

@@ -13,6 +13,31 @@ def _kw(d):
 
 
 # ---- gradient family -------------------------------------------------------
+def _spatial_oracle(dem, meta):
+    kw = dict(meta["kw"])
+    algo = meta["algo"]
+    if algo == "hillshade":
+        return orc.hillshade_spatial_block(dem, **kw)
+    if algo == "slope":
+        return orc.slope_spatial_block(dem, **kw)
+    if algo == "curvature":
+        return orc.curvature_spatial_block(dem, **kw)
+    radii, weights, agg = kw.pop("radii"), kw.pop("weights"), kw.pop("agg")
+    resp = [orc.hillshade_spatial_block(dem, radius=float(r), **kw) for r in radii]
+    return orc.combine_responses(resp, weights=weights, agg=agg)
+
+
+def test_spatial_gradient_matches_reference(golden, manifest):
+    """Gaussian scale-space ('--mode spatial') block functions and the tile combiner vs the reference."""
+    g = golden("spatial_gradient")
+    for name, meta in manifest["spatial_gradient"].items():
+        got = _spatial_oracle(g[meta["input"]], meta)
+        if meta["algo"].startswith("hillshade"):
+            assert_close_f32(got, g[name], rtol=0, atol=4e-7, what=name)   # f64-vs-f32 light vector of the shim
+        else:
+            assert np.array_equal(got, g[name], equal_nan=True), name
+
+
 def test_gradient_family_matches_reference(golden, manifest):
     g = golden("gradient_family")
     for name, meta in manifest["gradient_family"].items():
