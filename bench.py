@@ -298,7 +298,7 @@ def run_gpu_arm(a) -> None:
                    "main_pass_mpx_s": H * W / (main_ms * 1e-3) / 1e6,
                    "fused_kernel_ms": fused_ms, "scale_p99": float(st[0])},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "fsg::fused_kernel (main pass)", "peak_source": peak_src,
+                     "traffic": traffic, "kernel": "fsg::fused_kernel_v6<32> (main pass)", "peak_source": peak_src,
                      "algorithmic_bytes_per_px": ALGO_BYTES_PER_PX},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "fsg_topousm_fast_workspace_bytes": (C.c_size_t, [_L, _L, C.POINTER(C.c_int32), _I, _D]),
     "fsg_topousm_fast": (_I, [_P, _P, _L, _L, _L, _L, C.POINTER(C.c_int32), C.POINTER(C.c_float), _I,
                               _D, _D, C.POINTER(Encode), _P, C.c_size_t, _P]),
+    "fsg_topousm_fast_roi": (_I, [_P, _P, _L, _L, _L, _L, C.POINTER(C.c_int32), C.POINTER(C.c_float), _I,
+                                  _D, _D, C.POINTER(Encode), _P, C.c_size_t, _L, _L, _L, _L, _P]),
     "fsg_topousm_plan": (_I, [C.POINTER(C.c_int32), _I, _D, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "fsg_pyramid_band": (_I, [_P, _L, _L, _L, C.POINTER(C.c_int32), _I, C.POINTER(_P), _P, _P]),

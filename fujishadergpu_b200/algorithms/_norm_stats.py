@@ -100,8 +100,15 @@ def compute_norm_stats_device(dem, algorithm: str, params: dict, *, grid: int = 
         _, _, n_valid = _k.order_stats([win], -1, take_abs=False, finite_only=True)
         if n_valid < min_valid_frac * float(win.numel()):
             continue
-        raw = _dev.as_tensor(block_func(win, **kw))
-        m = int(min(margin, raw.shape[0] // 3, raw.shape[1] // 3))
+        m = int(min(margin, win.shape[0] // 3, win.shape[1] // 3))
+        if algorithm == "topousm_fast" and m > 0:
+            # same block function, same values: the kernel is only asked for the region the trim keeps
+            # (reference :275-277 computes the whole window and throws the margin away)
+            raw = _k.topousm_fast(win, radii=kw.get("radii") or [4, 16, 64], weights=kw.get("weights"),
+                                  pixel_size=kw.get("pixel_size", 1.0), norm_scale=None,
+                                  roi=(m, int(win.shape[0]) - 2 * m, m, int(win.shape[1]) - 2 * m))
+        else:
+            raw = _dev.as_tensor(block_func(win, **kw))
         if m > 0:
             raw = raw[m:-m, m:-m]
         if raw.numel():

@@ -401,6 +401,8 @@ struct FusedParams {
   EncodeDev enc;
   int bulk_ok;     // v6: DEM rows are 16-byte aligned (base pointer and row stride) -> bulk async copies
   int out_vec_ok;  // v7: output rows allow 16-byte (f32) / 4-byte (u8) vector stores
+  int strip0;      // first column strip to compute (region of interest; 0 for the whole width)
+  int64_t roi_col0, roi_cols;   // host side: requested output columns (0, W for the whole width)
 };
 
 __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
   unsigned char* cplane = reinterpret_cast<unsigned char*>(vplane + (size_t)FK_NB * SWp);  // FK_NB x SWp
 
   const int tid = threadIdx.x;
-  const int64_t x0 = (int64_t)blockIdx.x * FK_TW;       // first output column of the strip
+  const int64_t x0 = ((int64_t)blockIdx.x + p.strip0) * FK_TW;       // first output column of the strip
   const int64_t cs0 = x0 - R;                            // global column of strip slot 0
   const int64_t out_end = p.out_row0 + p.out_rows;
   const int64_t yb0 = p.out_row0 + (int64_t)blockIdx.y * p.band_rows;
@@ -778,7 +780,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
   const int tid = threadIdx.x;
   const int W = (int)p.W;
   const int64_t H = p.H;
-  const int x0 = blockIdx.x * FK_TW;
+  const int x0 = ((int)blockIdx.x + p.strip0) * FK_TW;
   const int cs0 = x0 - R;
   const int64_t out_end = p.out_row0 + p.out_rows;
   const int64_t yb0 = p.out_row0 + (int64_t)blockIdx.y * p.band_rows;
@@ -1215,6 +1217,12 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
   const int64_t rows = fp.out_rows;
   const int tw = nb == 7 ? V7_TW : FK_TW;
   int64_t strips = (W + tw - 1) / tw;
+  fp.strip0 = 0;
+  if (fp.roi_cols > 0 && fp.roi_cols < W) {   // only the strips that overlap the requested columns
+    const int64_t s_lo = fp.roi_col0 / tw, s_hi = (fp.roi_col0 + fp.roi_cols + tw - 1) / tw;
+    fp.strip0 = (int)s_lo;
+    strips = s_hi - s_lo;
+  }
   int64_t want_bands = (rows + 1023) / 2048;
   if (want_bands < 1) want_bands = 1;
   const int64_t min_rows = 8 * (int64_t)(2 * fused_R + 1);
@@ -1255,7 +1263,12 @@ static void set_norm(FusedParams& fp, double norm_scale) {
 
 static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_t ld_in, int64_t ld_out,
                        const int32_t* radii, const float* weights, int n, double pixel_size, double norm_scale,
-                       const fsg_encode* enc, void* ws, size_t ws_bytes, cudaStream_t s) {
+                       const fsg_encode* enc, void* ws, size_t ws_bytes, cudaStream_t s, int64_t roi_row0 = 0,
+                       int64_t roi_rows = -1, int64_t roi_col0 = 0, int64_t roi_cols = -1) {
+  if (roi_rows < 0) roi_rows = H;
+  if (roi_cols < 0) roi_cols = W;
+  if (roi_row0 < 0 || roi_col0 < 0 || roi_row0 + roi_rows > H || roi_col0 + roi_cols > W)
+    return fail(FSG_E_INVALID, "fsg_topousm_fast_roi: region of interest outside the raster");
   HostPlan plan;
   int rc = make_plan(H, W, radii, n, pixel_size, &plan);
   if (rc) return rc;
@@ -1293,7 +1306,9 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
 
   FusedParams fp{};
   fp.dem = dem; fp.out = out; fp.H = H; fp.W = W; fp.ld_in = ld_in; fp.ld_out = ld_out;
-  fp.dem_row0 = 0; fp.dem_rows = H; fp.out_row0 = 0; fp.out_rows = H;
+  fp.dem_row0 = 0; fp.dem_rows = H; fp.out_row0 = roi_row0; fp.out_rows = roi_rows;
+  fp.out = (unsigned char*)out + (size_t)roi_row0 * (size_t)ld_out * out_elem_size(enc ? enc->kind : FSG_OUT_F32);
+  fp.roi_col0 = roi_col0; fp.roi_cols = roi_cols;
   fp.n_terms = n;
   fp.enc = make_encode(enc);
   set_norm(fp, norm_scale);
@@ -1492,6 +1507,15 @@ size_t fsg_topousm_fast_workspace_bytes(int64_t H, int64_t W, const int32_t* rad
   fsg::HostPlan plan;
   if (fsg::make_plan(H, W, radii_host, n_radii, pixel_size, &plan)) return 0;
   return plan.total;
+}
+
+int fsg_topousm_fast_roi(const float* dem, void* out, int64_t H, int64_t W, int64_t ld_in, int64_t ld_out,
+                         const int32_t* radii_host, const float* weights_host, int n_radii, double pixel_size,
+                         double norm_scale, const fsg_encode* enc, void* workspace, size_t workspace_bytes,
+                         int64_t roi_row0, int64_t roi_rows, int64_t roi_col0, int64_t roi_cols, void* stream) {
+  if (!radii_host || !weights_host) return fsg::fail(FSG_E_INVALID, "fsg_topousm_fast_roi: radii/weights are NULL");
+  return fsg::run_topousm(dem, out, H, W, ld_in, ld_out, radii_host, weights_host, n_radii, pixel_size, norm_scale,
+                          enc, workspace, workspace_bytes, (cudaStream_t)stream, roi_row0, roi_rows, roi_col0, roi_cols);
 }
 
 int fsg_topousm_fast(const float* dem, void* out, int64_t H, int64_t W, int64_t ld_in, int64_t ld_out,

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(V7_THREADS, 1) fused_kernel_v7(FusedParams p) 
   const bool is_h = tid < V7_HT;
   const int W = (int)p.W;
   const int64_t H = p.H;
-  const int x0 = blockIdx.x * TW;
+  const int x0 = ((int)blockIdx.x + p.strip0) * TW;
   const int cs0 = x0 - RH;
   const int64_t out_end = p.out_row0 + p.out_rows;
   const int64_t yb0 = p.out_row0 + (int64_t)blockIdx.y * p.band_rows;

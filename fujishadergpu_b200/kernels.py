@@ -97,8 +97,10 @@ def topousm_fast_workspace_bytes(shape, radii, pixel_size=1.0) -> int:
 
 
 def topousm_fast(dem, *, radii, weights=None, pixel_size=1.0, norm_scale=None, output_dtype="float32",
-                 qp=None, workspace: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Whole pipeline for one block == whole raster.  norm_scale=None -> raw block output."""
+                 qp=None, workspace: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                 roi=None) -> torch.Tensor:
+    """Whole pipeline for one block == whole raster.  norm_scale=None -> raw block output.
+    roi = (row0, rows, col0, cols): only that region of `out` is guaranteed to be computed."""
     t = dev.as_f32_2d(dem)
     if radii is None or len(radii) == 0:
         raise ValueError("At least one radius value is required")
@@ -110,6 +112,14 @@ def topousm_fast(dem, *, radii, weights=None, pixel_size=1.0, norm_scale=None, o
     if out is None:
         out = dev.empty_out(t, t.shape, output_dtype)
     enc = make_encode(output_dtype, qp)
+    if roi is not None:
+        check(lib.fsg_topousm_fast_roi(_ptr(t), _ptr(out), int(t.shape[0]), int(t.shape[1]), int(t.stride(0)),
+                                       int(out.stride(0)), rr.ctypes.data_as(C.POINTER(C.c_int32)),
+                                       ww.ctypes.data_as(C.POINTER(C.c_float)), len(rr), float(pixel_size),
+                                       opt(norm_scale), C.byref(enc), _ptr(workspace),
+                                       workspace.numel() * workspace.element_size(), int(roi[0]), int(roi[1]),
+                                       int(roi[2]), int(roi[3]), C.c_void_p(dev.stream_ptr(t))), "fsg_topousm_fast_roi")
+        return out
     check(lib.fsg_topousm_fast(_ptr(t), _ptr(out), int(t.shape[0]), int(t.shape[1]), int(t.stride(0)),
                                int(out.stride(0)), rr.ctypes.data_as(C.POINTER(C.c_int32)),
                                ww.ctypes.data_as(C.POINTER(C.c_float)), len(rr), float(pixel_size), opt(norm_scale),

@@ -119,6 +119,15 @@ int fsg_topousm_fast(const float* dem, void* out, int64_t H, int64_t W, int64_t 
                      const int32_t* radii_host, const float* weights_host, int n_radii,
                      double pixel_size, double norm_scale, const fsg_encode* enc,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* Same pipeline, output restricted to a region of interest (the statistics pre-pass only needs the
+ * centre of each stratified window, algorithms/_norm_stats.py:275-277).  `out` is still the full
+ * H x W buffer; rows / column strips outside the region are left untouched (whole 264-column strips
+ * and whole rows are written, so a little more than the region may be filled). */
+int fsg_topousm_fast_roi(const float* dem, void* out, int64_t H, int64_t W, int64_t ld_in, int64_t ld_out,
+                         const int32_t* radii_host, const float* weights_host, int n_radii, double pixel_size,
+                         double norm_scale, const fsg_encode* enc, void* workspace, size_t workspace_bytes,
+                         int64_t roi_row0, int64_t roi_rows, int64_t roi_col0, int64_t roi_cols, void* stream);
+
 
 /* ---- row-band shards of topousm_fast (multi-GPU; one band of rows per GPU) ----------------------
  * The whole-raster pipeline above, cut into stages so that the host can exchange halo rows between
