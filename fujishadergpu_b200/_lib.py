@@ -69,6 +69,7 @@ _SIGNATURES = {
     "fsg_order_stats_workspace_bytes": (C.c_size_t, []),
     "fsg_order_stats": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, _L, _I, _I,
                              _P, _P, C.c_size_t, _P]),
+    "fsg_count_samples": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, _I, _P, _P]),
     "fsg_grid_void_fill": (_I, [_P, _L, _L, _P, C.c_size_t, _P]),
     "fsg_key_histogram": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, _I, C.c_uint32,
                                C.c_uint32, _I, _I, _P, _P, _P]),

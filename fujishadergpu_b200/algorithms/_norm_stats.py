@@ -94,11 +94,12 @@ def compute_norm_stats_device(dem, algorithm: str, params: dict, *, grid: int = 
     bx0, bx1 = int(cols.min()) * cov, min(W, (int(cols.max()) + 1) * cov)
 
     pooled = []
-    for wy0, wx0, tw, th in stratified_windows(W, H, by0, by1, bx0, bx1, grid=grid, tile=min(tile, max(W, H))):
-        win = t[wy0:wy0 + th, wx0:wx0 + tw]
-        # valid fraction of the window: one counting pass of the selection kernel (rank < 0 only counts)
-        _, _, n_valid = _k.order_stats([win], -1, take_abs=False, finite_only=True)
-        if n_valid < min_valid_frac * float(win.numel()):
+    wins = [t[wy0:wy0 + th, wx0:wx0 + tw]
+            for wy0, wx0, tw, th in stratified_windows(W, H, by0, by1, bx0, bx1, grid=grid, tile=min(tile, max(W, H)))]
+    # valid fraction of every window in one counting launch (one host sync instead of one per window)
+    n_valid = _k.count_samples(wins, finite_only=True) if wins else []
+    for win, nv in zip(wins, n_valid):
+        if nv < min_valid_frac * float(win.numel()):
             continue
         m = int(min(margin, win.shape[0] // 3, win.shape[1] // 3))
         if algorithm == "topousm_fast" and m > 0:

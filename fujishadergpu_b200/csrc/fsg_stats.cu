@@ -16,6 +16,7 @@ struct Chunks {
   const float* ptr[MAX_CHUNKS];
   int64_t rows[MAX_CHUNKS], cols[MAX_CHUNKS], ld[MAX_CHUNKS];
   int64_t start[MAX_CHUNKS + 1];  // prefix of rows*cols
+  int64_t rowstart[MAX_CHUNKS + 1];  // prefix of rows * ceil(cols / SCAN_TILE): (row, column tile) work items
   int n;
 };
 
@@ -45,12 +46,37 @@ __device__ __forceinline__ float key_value(unsigned int key, int take_abs) {
   return __uint_as_float(b);
 }
 
-__device__ __forceinline__ float fetch(const Chunks& c, int64_t i) {
-  int k = 0;
-  while (k + 1 < c.n && i >= c.start[k + 1]) ++k;
-  int64_t j = i - c.start[k];
-  int64_t r = j / c.cols[k], x = j - r * c.cols[k];
-  return c.ptr[k][r * c.ld[k] + x];
+
+// Visit every sample: CTAs stride over the rows of all chunks, the threads of a CTA over the columns of
+// a row (coalesced, no per-element division).  f(value, in_range) is called by ALL threads of the CTA
+// the same number of times, so warp-collective code is allowed inside.
+constexpr int SCAN_TILE = 2048;   // columns per (row, tile) work item
+template <typename F>
+__device__ __forceinline__ void scan_chunks(const Chunks& c, F f) {
+  const int64_t ntiles = c.rowstart[c.n];   // prefix of rows * tiles-per-row (see fill_chunks)
+  for (int64_t T = blockIdx.x; T < ntiles; T += gridDim.x) {
+    int k = 0;
+    while (k + 1 < c.n && T >= c.rowstart[k + 1]) ++k;
+    const int64_t cols = c.cols[k];
+    const int64_t tpr = (cols + SCAN_TILE - 1) / SCAN_TILE;
+    const int64_t t = T - c.rowstart[k];
+    const int64_t r = t / tpr, cb = (t - r * tpr) * SCAN_TILE;
+    const float* row = c.ptr[k] + r * c.ld[k];
+    const int64_t cend = cb + SCAN_TILE < cols ? cb + SCAN_TILE : cols;
+    for (int64_t x0 = cb; x0 < cend; x0 += blockDim.x) {
+      const int64_t x = x0 + threadIdx.x;
+      const bool in = x < cend;
+      f(in ? row[x] : 0.f, in);
+    }
+  }
+}
+
+// shared-memory histogram increment aggregated per warp: the keys of |x| cluster in a handful of bins
+// (same exponent), where plain atomics serialise 32-fold
+__device__ __forceinline__ void hist_add(unsigned int* sh, unsigned int bin, bool contrib) {
+  const unsigned int tag = contrib ? bin : 0xffffffffu;
+  const unsigned int m = __match_any_sync(0xffffffffu, tag);
+  if (contrib && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&sh[bin], (unsigned int)__popc(m));
 }
 
 // level: 0 -> bits 31..21 (2048 bins), 1 -> bits 20..10 (2048), 2 -> bits 9..0 (1024)
@@ -62,14 +88,13 @@ __global__ void __launch_bounds__(256) hist_kernel(Chunks c, int level, int take
   const unsigned int prefix = level ? st->prefix : 0u, mask = level ? st->mask : 0u;
   const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
   const unsigned int bins_mask = level == 2 ? 1023u : 2047u;
-  const int64_t total = c.start[c.n];
   unsigned long long local = 0;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    unsigned int key;
-    if (!sample_key(fetch(c, i), take_abs, finite_only, &key)) continue;
-    ++local;
-    if ((key & mask) == prefix) atomicAdd(&sh[(key >> shift) & bins_mask], 1u);
-  }
+  scan_chunks(c, [&](float v, bool in) {
+    unsigned int key = 0;
+    const bool ok = in && sample_key(v, take_abs, finite_only, &key);
+    local += ok;
+    hist_add(sh, (key >> shift) & bins_mask, ok && (key & mask) == prefix);
+  });
   __syncthreads();
   for (int i = threadIdx.x; i < 2048; i += 256)
     if (sh[i]) atomicAdd(&hist[i], sh[i]);
@@ -109,15 +134,15 @@ __global__ void pick_kernel(int level, SelState* st, unsigned int* hist, const u
 __global__ void __launch_bounds__(256) next_kernel(Chunks c, int take_abs, int finite_only, SelState* st) {
   if (st->n == 0) return;
   const unsigned int kk = st->key_k;
-  const int64_t total = c.start[c.n];
   unsigned long long le = 0;
   unsigned int mn = 0xffffffffu;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    unsigned int key;
-    if (!sample_key(fetch(c, i), take_abs, finite_only, &key)) continue;
-    if (key <= kk) ++le;
-    else if (key < mn) mn = key;
-  }
+  scan_chunks(c, [&](float v, bool in) {
+    unsigned int key = 0;
+    if (in && sample_key(v, take_abs, finite_only, &key)) {
+      if (key <= kk) ++le;
+      else if (key < mn) mn = key;
+    }
+  });
   for (int o = 16; o; o >>= 1) {
     le += __shfl_down_sync(0xffffffffu, le, o);
     unsigned int other = __shfl_down_sync(0xffffffffu, mn, o);
@@ -169,14 +194,13 @@ __global__ void __launch_bounds__(256) hist_kernel_v(Chunks c, int level, int ta
   __syncthreads();
   const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
   const unsigned int bins_mask = level == 2 ? 1023u : 2047u;
-  const int64_t total = c.start[c.n];
   unsigned long long local = 0;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    unsigned int key;
-    if (!sample_key(fetch(c, i), take_abs, finite_only, &key)) continue;
-    ++local;
-    if ((key & mask) == prefix) atomicAdd(&sh[(key >> shift) & bins_mask], 1u);
-  }
+  scan_chunks(c, [&](float v, bool in) {
+    unsigned int key = 0;
+    const bool ok = in && sample_key(v, take_abs, finite_only, &key);
+    local += ok;
+    hist_add(sh, (key >> shift) & bins_mask, ok && (key & mask) == prefix);
+  });
   __syncthreads();
   for (int i = threadIdx.x; i < 2048; i += 256)
     if (sh[i]) atomicAdd(&hist[i], sh[i]);
@@ -187,15 +211,15 @@ __global__ void __launch_bounds__(256) hist_kernel_v(Chunks c, int level, int ta
 __global__ void __launch_bounds__(256) rank_info_kernel(Chunks c, int take_abs, int finite_only, unsigned int kk,
                                                         unsigned long long* out) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { /* out[] is pre-set by init below */ }
-  const int64_t total = c.start[c.n];
   unsigned long long le = 0;
   unsigned int mn = 0xffffffffu;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    unsigned int key;
-    if (!sample_key(fetch(c, i), take_abs, finite_only, &key)) continue;
-    if (key <= kk) ++le;
-    else if (key < mn) mn = key;
-  }
+  scan_chunks(c, [&](float v, bool in) {
+    unsigned int key = 0;
+    if (in && sample_key(v, take_abs, finite_only, &key)) {
+      if (key <= kk) ++le;
+      else if (key < mn) mn = key;
+    }
+  });
   for (int o = 16; o; o >>= 1) {
     le += __shfl_down_sync(0xffffffffu, le, o);
     unsigned int other = __shfl_down_sync(0xffffffffu, mn, o);
@@ -204,6 +228,28 @@ __global__ void __launch_bounds__(256) rank_info_kernel(Chunks c, int take_abs, 
   if ((threadIdx.x & 31) == 0) {
     if (le) atomicAdd(&out[0], le);
     atomicMin(&out[1], (unsigned long long)mn);
+  }
+}
+
+// per-chunk sample counts (the statistics pre-pass checks the valid fraction of every window, _norm_stats.py:268-270)
+__global__ void __launch_bounds__(256) count_chunks_kernel(Chunks c, int finite_only, unsigned long long* counts) {
+  const int64_t ntiles = c.rowstart[c.n];
+  for (int64_t T = blockIdx.x; T < ntiles; T += gridDim.x) {
+    int k = 0;
+    while (k + 1 < c.n && T >= c.rowstart[k + 1]) ++k;
+    const int64_t cols = c.cols[k];
+    const int64_t tpr = (cols + SCAN_TILE - 1) / SCAN_TILE;
+    const int64_t t = T - c.rowstart[k];
+    const int64_t r = t / tpr, cb = (t - r * tpr) * SCAN_TILE;
+    const float* row = c.ptr[k] + r * c.ld[k];
+    const int64_t cend = cb + SCAN_TILE < cols ? cb + SCAN_TILE : cols;
+    unsigned int local = 0;
+    for (int64_t x = cb + threadIdx.x; x < cend; x += blockDim.x) {
+      float v = row[x];
+      local += finite_only ? (isfinite(v) ? 1u : 0u) : (v == v ? 1u : 0u);
+    }
+    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counts[k], (unsigned long long)local);
   }
 }
 
@@ -228,9 +274,11 @@ int fsg_order_stats(const float* const* chunks_host, const int64_t* rows_host, c
       return fail(FSG_E_INVALID, "fsg_order_stats: bad chunk %d", i);
     c.ptr[i] = chunks_host[i]; c.rows[i] = rows_host[i]; c.cols[i] = cols_host[i]; c.ld[i] = ld_host[i];
     c.start[i] = tot;
+    c.rowstart[i] = i == 0 ? 0 : c.rowstart[i - 1] + rows_host[i - 1] * ((cols_host[i - 1] + 2047) / 2048);
     tot += rows_host[i] * cols_host[i];
   }
   c.start[n_chunks] = tot;
+  c.rowstart[n_chunks] = n_chunks ? c.rowstart[n_chunks - 1] + rows_host[n_chunks - 1] * ((cols_host[n_chunks - 1] + 2047) / 2048) : 0;
   unsigned char* base = (unsigned char*)workspace;
   unsigned int* hist = (unsigned int*)base;
   unsigned long long* count = (unsigned long long*)(base + 2048 * 4);
@@ -284,9 +332,11 @@ int fsg_key_histogram(const float* const* chunks_host, const int64_t* rows_host,
   for (int i = 0; i < n_chunks; ++i) {
     c.ptr[i] = chunks_host[i]; c.rows[i] = rows_host[i]; c.cols[i] = cols_host[i]; c.ld[i] = ld_host[i];
     c.start[i] = tot;
+    c.rowstart[i] = i == 0 ? 0 : c.rowstart[i - 1] + rows_host[i - 1] * ((cols_host[i - 1] + 2047) / 2048);
     tot += rows_host[i] * cols_host[i];
   }
   c.start[n_chunks] = tot;
+  c.rowstart[n_chunks] = n_chunks ? c.rowstart[n_chunks - 1] + rows_host[n_chunks - 1] * ((cols_host[n_chunks - 1] + 2047) / 2048) : 0;
   if (tot == 0) return FSG_OK;
   int blocks = (int)((tot + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -308,15 +358,44 @@ int fsg_key_rank_info(const float* const* chunks_host, const int64_t* rows_host,
   for (int i = 0; i < n_chunks; ++i) {
     c.ptr[i] = chunks_host[i]; c.rows[i] = rows_host[i]; c.cols[i] = cols_host[i]; c.ld[i] = ld_host[i];
     c.start[i] = tot;
+    c.rowstart[i] = i == 0 ? 0 : c.rowstart[i - 1] + rows_host[i - 1] * ((cols_host[i - 1] + 2047) / 2048);
     tot += rows_host[i] * cols_host[i];
   }
   c.start[n_chunks] = tot;
+  c.rowstart[n_chunks] = n_chunks ? c.rowstart[n_chunks - 1] + rows_host[n_chunks - 1] * ((cols_host[n_chunks - 1] + 2047) / 2048) : 0;
   int blocks = (int)((tot + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   const unsigned long long init[2] = {0ull, 0xffffffffull};
   FSG_CUDA_OK(cudaMemcpyAsync(out_dev, init, sizeof(init), cudaMemcpyHostToDevice, s));
   rank_info_kernel<<<blocks, 256, 0, s>>>(c, take_abs, finite_only, key, (unsigned long long*)out_dev);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_count_samples(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                      const int64_t* ld_host, int n_chunks, int finite_only, uint64_t* counts_dev, void* stream) {
+  using namespace fsg;
+  if (n_chunks < 1 || n_chunks > MAX_CHUNKS || !counts_dev) return fail(FSG_E_INVALID, "fsg_count_samples: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  Chunks c{};
+  c.n = n_chunks;
+  int64_t tot = 0;
+  for (int i = 0; i < n_chunks; ++i) {
+    if (!chunks_host[i] || rows_host[i] < 0 || cols_host[i] < 0 || ld_host[i] < cols_host[i])
+      return fail(FSG_E_INVALID, "fsg_count_samples: bad chunk %d", i);
+    c.ptr[i] = chunks_host[i]; c.rows[i] = rows_host[i]; c.cols[i] = cols_host[i]; c.ld[i] = ld_host[i];
+    c.start[i] = tot;
+    c.rowstart[i] = i == 0 ? 0 : c.rowstart[i - 1] + rows_host[i - 1] * ((cols_host[i - 1] + 2047) / 2048);
+    tot += rows_host[i] * cols_host[i];
+  }
+  c.start[n_chunks] = tot;
+  c.rowstart[n_chunks] = c.rowstart[n_chunks - 1] + rows_host[n_chunks - 1] * ((cols_host[n_chunks - 1] + 2047) / 2048);
+  FSG_CUDA_OK(cudaMemsetAsync(counts_dev, 0, (size_t)n_chunks * sizeof(uint64_t), s));
+  if (tot == 0) return FSG_OK;
+  int64_t blocks = c.rowstart[n_chunks];
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  count_chunks_kernel<<<(int)blocks, 256, 0, s>>>(c, finite_only, (unsigned long long*)counts_dev);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }

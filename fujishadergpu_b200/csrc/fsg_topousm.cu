@@ -1227,6 +1227,9 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
   if (want_bands < 1) want_bands = 1;
   const int64_t min_rows = 8 * (int64_t)(2 * fused_R + 1);
   while (strips * want_bands < 148 * 6 && (rows + 2 * want_bands - 1) / (2 * want_bands) >= min_rows) want_bands *= 2;
+  // small launches (the statistics windows): filling the 148 SMs matters more than the warm-up rows
+  while (strips * want_bands < 148 && (rows + 2 * want_bands - 1) / (2 * want_bands) >= 3 * (int64_t)(2 * fused_R + 1))
+    want_bands *= 2;
   int64_t band_rows = (rows + want_bands - 1) / want_bands;
   band_rows = (band_rows + FK_NB - 1) / FK_NB * FK_NB;
   if (band_rows > (1 << 30)) band_rows = 1 << 30;

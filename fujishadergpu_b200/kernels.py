@@ -302,6 +302,25 @@ def order_stats(chunks: Sequence, rank: int, *, take_abs: bool, finite_only: boo
     return float(res[0]), float(res[1]), int(res[3])
 
 
+def count_samples(chunks: Sequence, *, finite_only: bool = True):
+    """Per-chunk counts of valid samples for up to 16 2-D device views (one launch, one host sync)."""
+    views = [dev.as_tensor(c) for c in chunks]
+    views = [v if (v.dtype == torch.float32 and v.stride(1) == 1) else v.to(torch.float32).contiguous() for v in views]
+    out = []
+    for i in range(0, len(views), 16):
+        part = views[i:i + 16]
+        n = len(part)
+        ptrs = (C.c_void_p * n)(*[v.data_ptr() for v in part])
+        rows = (C.c_int64 * n)(*[int(v.shape[0]) for v in part])
+        cols = (C.c_int64 * n)(*[int(v.shape[1]) for v in part])
+        lds = (C.c_int64 * n)(*[int(v.stride(0)) if v.shape[0] > 1 else int(v.shape[1]) for v in part])
+        counts = torch.empty(n, dtype=torch.int64, device=part[0].device)
+        check(_lib.load().fsg_count_samples(ptrs, rows, cols, lds, n, 1 if finite_only else 0, _ptr(counts),
+                                            C.c_void_p(dev.stream_ptr(part[0]))), "fsg_count_samples")
+        out.extend(int(x) for x in counts.cpu().tolist())
+    return out
+
+
 def percentile(chunks: Sequence, q: float, *, take_abs=False, finite_only=False) -> float:
     """np.percentile(sample, q) for an f32 sample (method 'linear'); NaN when the sample is empty.
     Index and interpolation arithmetic are NumPy's own f32 scalar ops

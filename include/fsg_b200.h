@@ -218,6 +218,11 @@ size_t fsg_order_stats_workspace_bytes(void);
 int fsg_order_stats(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
                     const int64_t* ld_host, int n_chunks, int64_t rank, int take_abs, int finite_only,
                     double* result_dev, void* workspace, size_t workspace_bytes, void* stream);
+/* Per-chunk counts of non-NaN (finite_only: finite) samples, counts_dev[n_chunks] (the statistics pre-pass
+ * skips windows with less than 2 % valid pixels, algorithms/_norm_stats.py:268-270). */
+int fsg_count_samples(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                      const int64_t* ld_host, int n_chunks, int finite_only, uint64_t* counts_dev, void* stream);
+
 
 /* Staged selection for percentiles of a sample that is spread over several GPUs: per-rank key
  * histograms (3 radix levels) and rank information, combined by the host with all-reduces
