@@ -317,10 +317,16 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
     by0, by1 = ymin * cov, min(H, (ymax + 1) * cov)
     bx0, bx1 = xmin * cov, min(W, (xmax + 1) * cov)
     wins = stratified_windows(W, H, by0, by1, bx0, bx1, grid=grid, tile=min(tile, max(W, H)))
+    trimmed_fn = None
     if block_fn is None:
         from .. import kernels as k
-        block_fn = lambda a: k.topousm_fast(a, radii=radii, weights=weights, pixel_size=pixel_size)
-    pooled = []
+
+        def trimmed_fn(a, m):   # the kernel is asked only for the region the trim keeps (same values)
+            raw = k.topousm_fast(a, radii=radii, weights=weights, pixel_size=pixel_size,
+                                 roi=(m, int(a.shape[0]) - 2 * m, m, int(a.shape[1]) - 2 * m) if m > 0 else None)
+            return raw[m:-m, m:-m] if m > 0 else raw
+    # 1. move every window's rows to its owner (round-robin) ...
+    mine = []
     for wi, (wy0, wx0, tw, th) in enumerate(wins):
         owner = wi % world
         need = [(0, 0)] * world
@@ -328,12 +334,19 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
         cols = band[:, wx0:wx0 + tw]
         win = exchange_rows(cols, own, need, rank, dist)
         if rank == owner:
+            mine.append(win)
+    # 2. ... then every rank evaluates its own windows, all ranks at the same time
+    pooled = []
+    for win in mine:
+        m = int(min(margin, win.shape[0] // 3, win.shape[1] // 3))
+        if trimmed_fn is not None:
+            raw = trimmed_fn(win, m)
+        else:
             raw = block_fn(win)
-            m = int(min(margin, raw.shape[0] // 3, raw.shape[1] // 3))
             if m > 0:
                 raw = raw[m:-m, m:-m]
-            if raw.numel():
-                pooled.append(raw)
+        if raw.numel():
+            pooled.append(raw)
     kw = select_fns(pooled) if select_fns is not None else {}   # tests inject stand-ins for the kernels
     s = distributed_percentile(pooled, 99.0, take_abs=True, finite_only=False, device=band.device, dist=dist, **kw)
     if not (s == s) or s <= 1e-9:
