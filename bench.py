@@ -184,7 +184,8 @@ def run_gpu_arm(a) -> None:
         dist.init_process_group("nccl", device_id=dev)
     if world > 1:
         from fujishadergpu_b200.core import sharding
-        return sharding.bench_sharded(a, dist, dev, METRIC, UNIT, RADII, _weights())
+        return sharding.bench_sharded(a, dist, dev, METRIC, UNIT, RADII, _weights(), clock_sampler=ClockSampler,
+                                      peak=measured_peak_gbs())
 
     S = int(a.size)
     H = W = S
@@ -256,11 +257,11 @@ def run_gpu_arm(a) -> None:
     try:
         if a.no_e2e:
             raise RuntimeError("skipped (--no-e2e)")
-        from fujishadergpu_b200.core.tile_processor import HostTilePipeline
+        from fujishadergpu_b200.core.tile_processor import StreamedTopoPipeline
         del out
         torch.cuda.empty_cache()
         e2e_side = S
-        pipe = HostTilePipeline((e2e_side, e2e_side), "topousm_fast", params, output_dtype="uint8", device=dev)
+        pipe = StreamedTopoPipeline((e2e_side, e2e_side), params, output_dtype="uint8", device=dev)
         hin = torch.empty((e2e_side, e2e_side), dtype=torch.float32, pin_memory=True)
         for r in range(0, e2e_side, 4096):
             hin[r:r + 4096].copy_(dem[r:r + 4096])
@@ -275,6 +276,7 @@ def run_gpu_arm(a) -> None:
         dt = (time.perf_counter() - t0) / n_e2e
         e2e = {"value": e2e_side * e2e_side / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
                "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": dt * 1e3, "output_dtype": "uint8",
+               "pipeline": "StreamedTopoPipeline: chunked H2D (stats-window rows first), per-chunk decimation, global scale while uploading, row bands + D2H overlapped",
                "steps": n_e2e}
         del pipe, hin, hout
     except Exception as exc:  # pinned allocation can fail on small hosts; say so instead of faking

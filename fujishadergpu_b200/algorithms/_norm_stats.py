@@ -62,8 +62,24 @@ def _norm_stat_window_geometry(algorithm: str, merged: dict, max_tile: int = 409
     return margin, max(min(2048, max(1, int(max_tile))), 4 * margin)
 
 
+def valid_bbox_host(host_arr, cov: Optional[int] = None):
+    """(by0, by1, bx0, bx1) of the valid data from a <= 512 px nearest overview of a HOST raster
+    (reference :254-264), or None when nothing is valid."""
+    import numpy as np
+    a = host_arr.numpy() if hasattr(host_arr, "numpy") else np.asarray(host_arr)
+    H, W = int(a.shape[0]), int(a.shape[1])
+    cov = max(1, max(W, H) // 512) if cov is None else int(cov)
+    ov = a[::cov, ::cov][: max(1, H // cov), : max(1, W // cov)]
+    ok = np.isfinite(ov)
+    if not ok.any():
+        return None
+    rows = np.nonzero(ok.any(axis=1))[0]
+    cols = np.nonzero(ok.any(axis=0))[0]
+    return (int(rows.min()) * cov, min(H, (int(rows.max()) + 1) * cov), int(cols.min()) * cov, min(W, (int(cols.max()) + 1) * cov))
+
+
 def compute_norm_stats_device(dem, algorithm: str, params: dict, *, grid: int = 3, max_tile: int = 4096,
-                              min_valid_frac: float = 0.02) -> Optional[tuple]:
+                              min_valid_frac: float = 0.02, bbox=None) -> Optional[tuple]:
     """Device-resident twin of _compute_norm_stats_tiled (reference :176-298)."""
     import inspect
     import torch
@@ -82,16 +98,19 @@ def compute_norm_stats_device(dem, algorithm: str, params: dict, *, grid: int = 
 
     t = _dev.as_f32_2d(dem)
     H, W = int(t.shape[0]), int(t.shape[1])
-    # coarse overview -> bounding box of valid data (reference :254-264; nearest-sampled <=512 px view)
-    cov = max(1, max(W, H) // 512)
-    ov = t[::cov, ::cov][: max(1, H // cov), : max(1, W // cov)]
-    ok = torch.isfinite(ov)
-    if not bool(ok.any()):
-        return None
-    rows = torch.nonzero(ok.any(dim=1)).flatten()
-    cols = torch.nonzero(ok.any(dim=0)).flatten()
-    by0, by1 = int(rows.min()) * cov, min(H, (int(rows.max()) + 1) * cov)
-    bx0, bx1 = int(cols.min()) * cov, min(W, (int(cols.max()) + 1) * cov)
+    if bbox is not None:
+        by0, by1, bx0, bx1 = [int(v) for v in bbox]
+    else:
+        # coarse overview -> bounding box of valid data (reference :254-264; nearest-sampled <=512 px view)
+        cov = max(1, max(W, H) // 512)
+        ov = t[::cov, ::cov][: max(1, H // cov), : max(1, W // cov)]
+        ok = torch.isfinite(ov)
+        if not bool(ok.any()):
+            return None
+        rows = torch.nonzero(ok.any(dim=1)).flatten()
+        cols = torch.nonzero(ok.any(dim=0)).flatten()
+        by0, by1 = int(rows.min()) * cov, min(H, (int(rows.max()) + 1) * cov)
+        bx0, bx1 = int(cols.min()) * cov, min(W, (int(cols.max()) + 1) * cov)
 
     pooled = []
     wins = [t[wy0:wy0 + th, wx0:wx0 + tw]
@@ -133,5 +152,5 @@ def inject_global_stats(dem, algorithm: str, params: dict) -> dict:
     return params
 
 
-__all__ = ["_NORM_STAT_SPECS", "stratified_windows", "_norm_stat_window_geometry", "compute_norm_stats_device",
+__all__ = ["_NORM_STAT_SPECS", "valid_bbox_host", "stratified_windows", "_norm_stat_window_geometry", "compute_norm_stats_device",
            "inject_global_stats"]

@@ -357,7 +357,7 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
 # ------------------------------------------------------------------------------------------------
 # bench driver for N > 1 (called from bench.py under torchrun)
 # ------------------------------------------------------------------------------------------------
-def bench_sharded(a, dist, dev, metric, unit, radii, weights):
+def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None, peak=None):
     import json
     import time
     from .. import kernels as k
@@ -381,12 +381,19 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights):
     dist.barrier()
     torch.cuda.synchronize()
     k.reset_launch_count()
+    sampler = clock_sampler(dev.index or 0) if (clock_sampler is not None and rank == 0) else None
+    if sampler is not None:
+        sampler.start()
+    k.profile_enable(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.steps):
         scale = step()
     ev1.record()
     torch.cuda.synchronize()
+    prof = k.profile_read()
+    k.profile_enable(False)
+    clocks = sampler.stop() if sampler is not None else None
     dist.barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -432,6 +439,16 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights):
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     if rank == 0:
         px = H * W
+        # roofline of the dominant kernel on rank 0: the fused full-resolution kernel over this rank's band
+        roofline = None
+        fused = sorted(ms_ for tag, ms_ in prof if tag == 1)
+        if fused and peak is not None:
+            main_fused = fused[-a.steps:]
+            fms = sum(main_fused) / len(main_fused)
+            ach = 8.0 * (r1 - r0) * W / (fms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "achieved": ach, "peak": peak[0], "unit": "GB/s", "frac": ach / peak[0],
+                        "traffic": None, "kernel": "fsg::fused_kernel_v6<32> (rank 0 band)", "peak_source": peak[1],
+                        "algorithmic_bytes_per_px": 8.0, "fused_kernel_ms": fms}
         line = {
             "metric": metric, "value": px / (ms_step * 1e-3) / 1e6, "unit": unit, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -442,7 +459,7 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights):
                        "l2_policy": "per-GPU band far larger than the 126 MB L2", "main_pass_ms": main_ms,
                        "stats_prepass_ms": ms_step - main_ms, "main_pass_mpx_s": px / (main_ms * 1e-3) / 1e6,
                        "scale_p99": scale, "band_rows": r1 - r0},
-            "roofline": None, "cpu_baseline": None,
+            "roofline": roofline, "cpu_baseline": None, "clocks": clocks,
             "e2e": {"value": px / float(dt.item()) / 1e6, "unit": unit, "h2d_bytes_per_step": px * 4,
                     "d2h_bytes_per_step": px, "ms_per_step": float(dt.item()) * 1e3, "output_dtype": "uint8"},
             "gpu_launches": int(launches.item()),

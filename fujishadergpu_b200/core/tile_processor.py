@@ -67,6 +67,160 @@ class HostTilePipeline:
         return host_out
 
 
+class StreamedTopoPipeline(HostTilePipeline):
+    """topousm_fast from host memory to host memory with the three engines overlapped: the raster is
+    uploaded in row chunks (the chunks the statistics windows need go first), every chunk is decimated as
+    soon as it lands, the global scale is computed while the rest is still in flight, and row bands run
+    through the band entry points (global coordinates -> bit-identical to the whole-raster call) as soon
+    as the rows and decimated rows they read are resident; each finished band goes back to the host on
+    a third stream while the next one computes.  (reference: the tile loop of
+    core/tile_processor.py:822-1024, where read, compute and write are strictly sequential per tile.)"""
+
+    def __init__(self, shape, params: dict, output_dtype: str = "uint8", device="cuda:0", chunk_rows: int = 4096):
+        super().__init__(shape, "topousm_fast", params, output_dtype, device, chunk_rows)
+        assert self.chunk_rows % 16 == 0, "chunks must hold whole decimation cells"
+        self.s_in = torch.cuda.Stream(device=self.device)
+        self.s_out = torch.cuda.Stream(device=self.device)
+        H, W = self.shape
+        plan = _k.topousm_plan(self.params["radii"], self.params.get("pixel_size", 1.0))
+        self.kinds, self.factors, self.sizes, self.R = plan["kind"], plan["factor"], plan["size"], plan["fused_halo"]
+        self.levels = sorted({self.factors[i] for i in range(len(self.kinds)) if self.kinds[i] == 1})
+        self.full = {f: torch.empty(((H + f - 1) // f, (W + f - 1) // f), dtype=torch.float32, device=self.device)
+                     for f in self.levels}
+        self.flags = torch.zeros(16, dtype=torch.int32, device=self.device)
+
+    def _band_need(self, r0: int, r1: int):
+        """DEM rows [lo, hi) a band reads directly or through its decimated means."""
+        from . import sharding as sh
+        H = self.shape[0]
+        n = len(self.kinds)
+        halo = max([self.R] + [4 if self.sizes[i] == 0 else self.sizes[i] // 2 for i in range(n) if self.kinds[i] == 2])
+        lo, hi = sh.mirror_need(r0 - halo, r1 - 1 + halo, H, True)
+        for i in range(n):
+            if self.kinds[i] != 1:
+                continue
+            f = self.factors[i]
+            gh = (H + f - 1) // f
+            rs = (gh - 1) / (H - 1) if H > 1 else 1.0
+            mlo = int(np.floor(r0 * rs)); mhi = min(gh - 1, int(np.floor((r1 - 1) * rs)) + 1)
+            reach = 4 if self.sizes[i] == 0 else self.sizes[i] // 2
+            glo, ghi = sh.mirror_need(mlo - reach, mhi + reach, gh, True)
+            lo, hi = min(lo, glo * f), max(hi, min(H, ghi * f))
+        return lo, hi
+
+    def _whole(self, host_out, radii, weights, px, scale):
+        H, C = self.shape[0], self.chunk_rows
+        cur = torch.cuda.current_stream(self.device)
+        _k.topousm_fast(self.dev_in, radii=radii, weights=weights, pixel_size=px, norm_scale=scale,
+                        output_dtype=self.output_dtype, qp=self.qp, workspace=self.workspace, out=self.dev_out)
+        for r in range(0, H, C):
+            host_out[r:r + C].copy_(self.dev_out[r:r + C], non_blocking=True)
+        cur.synchronize()
+        return host_out
+
+    def _band(self, r0: int, r1: int, radii, weights, px, scale):
+        from . import sharding as sh
+        H = self.shape[0]
+        n = len(self.kinds)
+        halo = max([self.R] + [4 if self.sizes[i] == 0 else self.sizes[i] // 2 for i in range(n) if self.kinds[i] == 2])
+        lo, hi = sh.mirror_need(r0 - halo, r1 - 1 + halo, H, True)
+        dem_ext = self.dev_in[lo:hi]
+        grids, grow0 = [None] * n, [0] * n
+        for i in range(n):
+            if self.kinds[i] == 1:
+                f = self.factors[i]
+                gh = (H + f - 1) // f
+                rs = (gh - 1) / (H - 1) if H > 1 else 1.0
+                mlo = int(np.floor(r0 * rs)); mhi = min(gh - 1, int(np.floor((r1 - 1) * rs)) + 1)
+                reach = 4 if self.sizes[i] == 0 else self.sizes[i] // 2
+                glo, ghi = sh.mirror_need(mlo - reach, mhi + reach, gh, True)
+                grids[i] = _k.grid_mean_band(self.full[f][glo:ghi], glo, gh, self.sizes[i], mlo, mhi - mlo + 1)
+                grow0[i] = mlo
+            elif self.kinds[i] == 2:
+                grids[i] = _k.grid_mean_band(dem_ext, lo, H, self.sizes[i], r0, r1 - r0)
+                grow0[i] = r0
+        _k.topousm_fused_band(dem_ext, lo, H, r0, r1 - r0, radii=radii, weights=weights, pixel_size=px,
+                              term_grids=grids, term_grow0=grow0, norm_scale=scale, output_dtype=self.output_dtype,
+                              qp=self.qp, out=self.dev_out[r0:r1])
+
+    def run(self, host_in: torch.Tensor, host_out: torch.Tensor) -> torch.Tensor:
+        from ..algorithms._norm_stats import (_norm_stat_window_geometry, compute_norm_stats_device, stratified_windows,
+                                              valid_bbox_host)
+        H, W = self.shape
+        C = self.chunk_rows
+        p = dict(self.params)
+        radii, weights, px = p["radii"], p.get("weights"), p.get("pixel_size", 1.0)
+        cur = torch.cuda.current_stream(self.device)
+        nchunks = (H + C - 1) // C
+        # valid-data bounding box from a host-side <= 512 px overview -> the windows of the statistics pre-pass;
+        # their chunks are uploaded first
+        scale = float(p["global_stats"][0]) if p.get("global_stats") else None
+        bbox = valid_bbox_host(host_in) if scale is None else None
+        first = []
+        if scale is None and bbox is not None:
+            _margin, tile = _norm_stat_window_geometry("topousm_fast", p)
+            wins = stratified_windows(W, H, bbox[0], bbox[1], bbox[2], bbox[3], grid=3, tile=min(tile, max(W, H)))
+            first = sorted({c for (wy0, _wx0, _tw, th) in wins
+                            for c in range(wy0 // C, min(nchunks, (wy0 + th - 1) // C + 1))})
+        order = first + [c for c in range(nchunks) if c not in set(first)]
+        self.s_in.wait_stream(cur)
+        ev = [None] * nchunks
+        with torch.cuda.stream(self.s_in):
+            for c in order:
+                a, b = c * C, min(H, (c + 1) * C)
+                self.dev_in[a:b].copy_(host_in[a:b], non_blocking=True)
+                ev[c] = torch.cuda.Event()
+                ev[c].record(self.s_in)
+        bands = [(r0, min(H, r0 + C)) for r0 in range(0, H, C)]
+        needs = []
+        for (r0, r1) in bands:
+            lo, hi = self._band_need(r0, r1)
+            needs.append(set(range(lo // C, min(nchunks, (hi - 1) // C + 1))))
+        pending = list(range(len(bands)))
+        landed = set()
+        self.flags.zero_()
+
+        def launch_ready():
+            for bi in list(pending):
+                if needs[bi] <= landed:
+                    r0, r1 = bands[bi]
+                    self._band(r0, r1, radii, weights, px, scale)
+                    e = torch.cuda.Event()
+                    e.record(cur)
+                    self.s_out.wait_event(e)
+                    with torch.cuda.stream(self.s_out):
+                        host_out[r0:r1].copy_(self.dev_out[r0:r1], non_blocking=True)
+                    pending.remove(bi)
+
+        for k_, c in enumerate(order):
+            a, b = c * C, min(H, (c + 1) * C)
+            cur.wait_event(ev[c])
+            if self.levels:   # decimate the chunk as it lands (cells never straddle chunks: C % 16 == 0)
+                grids, fl = _k.pyramid_band(self.dev_in[a:b], self.levels)
+                for f, g in zip(self.levels, grids):
+                    self.full[f][a // f:a // f + g.shape[0]].copy_(g)
+                self.flags[: len(self.levels)] |= fl
+            landed.add(c)
+            if scale is None and k_ + 1 >= len(first):
+                # every row the windows read is on the device: global scale now, while the uploads keep running
+                st = compute_norm_stats_device(self.dev_in, "topousm_fast", p, bbox=bbox) if bbox is not None else None
+                scale = float(st[0]) if st else 1.0
+            if scale is not None:
+                launch_ready()
+        if scale is None:
+            scale = 1.0
+        launch_ready()
+        assert not pending
+        if self.levels and bool(self.flags[: len(self.levels)].any()):
+            # a decimated cell without any valid pixel: the enclosed-void fill spans 1/16 of the raster side, so
+            # this (rare, NoData-heavy) case is redone with the whole-raster call
+            self.s_out.synchronize()
+            return self._whole(host_out, radii, weights, px, scale)
+        self.s_out.synchronize()
+        cur.synchronize()
+        return host_out
+
+
 def process_host_raster(dem_host: np.ndarray, algorithm: str, params: dict, output_dtype: str = "float32",
                         nodata: Optional[float] = None, device="cuda:0") -> np.ndarray:
     """Convenience wrapper: NumPy in, NumPy out (pins temporary buffers)."""
