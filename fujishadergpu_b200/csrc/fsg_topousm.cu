@@ -1207,7 +1207,11 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
     const uintptr_t need = fp.enc.kind == FSG_OUT_F32 ? 15 : 3;
     fp.out_vec_ok = (((uintptr_t)fp.out & need) == 0 && fp.ld_out % 4 == 0 && esz != 2) ? 1 : 0;
   }
+  // v6 geometry B (640 threads, 12-pixel segments) needs decimation >= 4 for its coarse cell slots
+  bool v6b_ok = v6_ok && getenv("FSG_V6_CFGB") != nullptr;
+  for (int l = 0; l < n_levels; ++l) v6b_ok = v6b_ok && fp.lvl_cscale[l] <= 0.25;
   if (v7_ok) nb = 7;
+  else if (v6b_ok) nb = 62;
   else if (v6_ok) nb = 6;
   else if (fast_ok && fused_fast_smem_bytes<32>(fused_R, n_levels) <= smem_cap) nb = 32;
   else if (fast_ok && fused_fast_smem_bytes<16>(fused_R, n_levels) <= smem_cap) nb = 16;
@@ -1215,7 +1219,7 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
   // raster allows) that the slower edge strips and the SM-to-SM spread average out.  (A "fewest waves"
   // model was tried and lost 25 %: one or two waves leave the chip waiting for the edge-strip CTAs.)
   const int64_t rows = fp.out_rows;
-  const int tw = nb == 7 ? V7_TW : FK_TW;
+  const int tw = nb == 7 ? V7_TW : (nb == 62 ? V6CfgB::TW : FK_TW);
   int64_t strips = (W + tw - 1) / tw;
   fp.strip0 = 0;
   if (fp.roi_cols > 0 && fp.roi_cols < W) {   // only the strips that overlap the requested columns
@@ -1239,16 +1243,19 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
   dim3 grid((unsigned)strips, (unsigned)bands);
   size_t smem = nb == 32 ? fused_fast_smem_bytes<32>(fused_R, n_levels)
                          : (nb == 16 ? fused_fast_smem_bytes<16>(fused_R, n_levels) : fused_smem_bytes(fused_R));
-  if (nb == 6) smem = V6Geom<32>::BYTES;
+  if (nb == 6) smem = V6Geom<32, V6CfgA>::BYTES;
+  if (nb == 62) smem = V6Geom<32, V6CfgB>::BYTES;
   if (nb == 7) smem = V7Geom<32>::BYTES;
   if (nb == 7) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v7<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else if (nb == 6) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v6<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (nb == 6) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v6<32, V6CfgA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (nb == 62) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v6<32, V6CfgB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (nb == 32) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (nb == 16) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int slot = prof_begin(PROF_TOPOUSM_FUSED, s);
   if (nb == 7) fused_kernel_v7<32><<<grid, V7_THREADS, smem, s>>>(fp);
-  else if (nb == 6) fused_kernel_v6<32><<<grid, FK_THREADS, smem, s>>>(fp);
+  else if (nb == 6) fused_kernel_v6<32, V6CfgA><<<grid, V6Geom<32, V6CfgA>::THREADS, smem, s>>>(fp);
+  else if (nb == 62) fused_kernel_v6<32, V6CfgB><<<grid, V6Geom<32, V6CfgB>::THREADS, smem, s>>>(fp);
   else if (nb == 32) fused_kernel_fast<32><<<grid, FK_THREADS, smem, s>>>(fp);
   else if (nb == 16) fused_kernel_fast<16><<<grid, FK_THREADS, smem, s>>>(fp);
   else fused_kernel<<<grid, FK_THREADS, smem, s>>>(fp);

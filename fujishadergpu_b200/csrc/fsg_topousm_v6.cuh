@@ -19,15 +19,19 @@
 
 namespace fsg {
 
-constexpr int V6_NB = 32;
-constexpr int V6_SEG = 24;
-constexpr int V6_NSEG = FK_THREADS / V6_NB;   // 11
+constexpr int V6_NB = 32;                     // rows per batch (lanes of a warp = the 32 rows in the horizontal pass)
 constexpr int V6_MAXF = 4;                    // fused radii with register-resident window sums
 constexpr int V6_MAXLV = 3;                   // pyramid levels with a column table in shared memory
-constexpr int V6_CG = 8;                      // coarse terms: pixels per rounding-boundary check
+constexpr int V6_CG = 8;                      // coarse terms: pixels per rounding-boundary check (v7)
 constexpr unsigned V6_GUARD = 1024u;          // ... and the guard band in f64 ulps (see the coarse term)
-constexpr int V6_KMAX = V6_SEG / 2 + 2;       // coarse cells a 24-pixel segment can touch (factor 2)
-static_assert(V6_SEG * V6_NSEG == FK_TW, "segments must tile the strip");
+
+// Launch geometry: strip width TW, pixels per horizontal thread SEG (threads = 32 rows x TW/SEG segments),
+// smallest decimation factor the coarse cell slots are sized for.
+//   V6CfgA: 264 columns, 24-pixel segments, 352 threads (11 warps, 168 registers)
+//   V6CfgB: 240 columns, 12-pixel segments, 640 threads (20 warps, <= 102 registers): more warps to hide
+//           latency, at the price of twice the window-start work per pixel
+struct V6CfgA { static constexpr int TW = 264, SEG = 24, FMIN = 2; };
+struct V6CfgB { static constexpr int TW = 240, SEG = 12, FMIN = 4; };
 
 struct V6ColEntry {   // per (level, strip column): zoom fraction and byte offset of the coarse cell slot
   double tc;
@@ -35,9 +39,12 @@ struct V6ColEntry {   // per (level, strip column): zoom fraction and byte offse
   int pad;
 };
 
-template <int RH>
+template <int RH, typename CFG>
 struct V6Geom {
-  static constexpr int SW = FK_TW + 2 * RH;                       // strip width incl. halo
+  static constexpr int TW = CFG::TW, SEG = CFG::SEG, NSEG = TW / SEG, THREADS = NSEG * V6_NB;
+  static constexpr int KMAX = SEG / CFG::FMIN + 2;   // coarse cells a segment can touch
+  static_assert(SEG * NSEG == TW && SEG % 4 == 0, "segments must tile the strip");
+  static constexpr int SW = TW + 2 * RH;                       // strip width incl. halo
   static constexpr int RS = ((SW / 4) % 2 == 1) ? SW : SW + 4;    // ring row stride (floats): RS/4 odd -> LDS.128 by rows is conflict-free
   static constexpr int PS = SW | 1;                               // plane row stride (doubles): odd -> LDS.64 by rows is conflict-free
   static constexpr int NRING = V6_NB + 2 * RH + 1;
@@ -45,9 +52,10 @@ struct V6Geom {
   static constexpr size_t PLANE_BYTES = (size_t)V6_NB * PS * 8;
   static constexpr size_t OFF_SLOT = OFF_PLANE + PLANE_BYTES;
   static constexpr size_t OFF_TC = (OFF_SLOT + (size_t)(NRING + 1) * 4 + 15) / 16 * 16;
-  static constexpr size_t OFF_BAR = OFF_TC + (size_t)V6_MAXLV * FK_TW * sizeof(V6ColEntry);
+  static constexpr size_t OFF_BAR = OFF_TC + (size_t)V6_MAXLV * TW * sizeof(V6ColEntry);
   static constexpr size_t BYTES = OFF_BAR + 16;
-  static_assert((size_t)V6_NSEG * V6_KMAX * 32 * 16 <= PLANE_BYTES, "coarse cell slots must fit in the plane region");
+  static_assert(THREADS >= SW, "one vertical thread per strip column");
+  static_assert((size_t)NSEG * KMAX * 32 * 16 <= PLANE_BYTES, "coarse cell slots must fit in the plane region");
   static_assert(RS % 4 == 0 && SW % 4 == 0, "rows must be whole 16-byte groups");
 };
 
@@ -81,10 +89,11 @@ __device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void* src, uns
 // scarce resource of this kernel)
 __device__ __forceinline__ double v6_round_f32(double q) { return round_to_f32_grid(q); }
 
-template <int RH>
-__global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_v6(FusedParams p) {
-  using G = V6Geom<RH>;
-  constexpr int NB = V6_NB, SEG = V6_SEG, SW = G::SW, RS = G::RS, PS = G::PS, NRING = G::NRING;
+template <int RH, typename CFG>
+__global__ void __launch_bounds__(V6Geom<RH, CFG>::THREADS, 1) fused_kernel_v6(FusedParams p) {
+  using G = V6Geom<RH, CFG>;
+  constexpr int NB = V6_NB, SEG = G::SEG, SW = G::SW, RS = G::RS, PS = G::PS, NRING = G::NRING;
+  constexpr int FK_TW = G::TW, FK_THREADS = G::THREADS, V6_KMAX = G::KMAX;   // (shadow the v5 constants)
   extern __shared__ __align__(16) unsigned char smraw[];
   float* ring = reinterpret_cast<float*>(smraw);
   double* plane64 = reinterpret_cast<double*>(smraw + G::OFF_PLANE);
@@ -465,11 +474,13 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_v6(FusedParams p) 
             // ulps of a rounding boundary (bit pattern x..x1000...0 in the low 29 bits).  Those pixels
             // (about 4e-6 of them) are recomputed with the four-tap form, group by group.
 #pragma unroll
-            for (int g = 0; g < SEG; g += V6_CG) {
-              double m64[V6_CG];
+            constexpr int CG = SEG % 8 == 0 ? 8 : 4;   // pixels per rounding-boundary check
+#pragma unroll
+            for (int g = 0; g < SEG; g += CG) {
+              double m64[CG];
               unsigned risk = 0xffffffffu;
 #pragma unroll
-              for (int u = 0; u < V6_CG; ++u) {
+              for (int u = 0; u < CG; ++u) {
                 const V6ColEntry e = ce[g + u];
                 const double2 ad = *reinterpret_cast<const double2*>(cellb + e.koff);
                 m64[u] = fma(e.tc, ad.y, ad.x);
@@ -478,7 +489,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_v6(FusedParams p) 
               }
               if (risk < (2u * V6_GUARD) << 3) {
 #pragma unroll
-                for (int u = 0; u < V6_CG; ++u) {
+                for (int u = 0; u < CG; ++u) {
                   const V6ColEntry e = ce[g + u];
                   int ca = c0 + e.koff / (32 * 16);
                   int cb = ca + 1 < gwm1 ? ca + 1 : gwm1;
@@ -493,7 +504,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_v6(FusedParams p) 
                 }
               }
 #pragma unroll
-              for (int u = 0; u < V6_CG; ++u) {
+              for (int u = 0; u < CG; ++u) {
                 float mean = (float)m64[u];
                 acc[g + u] = acc[g + u] + wgt * (xr[g + u] - mean);
               }

@@ -8,7 +8,7 @@ W6 = [32 / 63, 16 / 63, 8 / 63, 4 / 63, 2 / 63, 1 / 63]
 
 
 def run(d, radii, w, env, **kw):
-    for key in ("FSG_FORCE_GENERIC", "FSG_FUSED_V5", "FSG_FUSED_V7", "FSG_NO_BULK"):
+    for key in ("FSG_FORCE_GENERIC", "FSG_FUSED_V5", "FSG_FUSED_V7", "FSG_NO_BULK", "FSG_V6_CFGB"):
         os.environ.pop(key, None)
     for key in env:
         os.environ[key] = "1"
@@ -39,7 +39,7 @@ for shape, nod in cases:
     for radii, w in (([2, 8, 32, 128, 512, 2048], W6), ([2, 8, 32], [4 / 7, 2 / 7, 1 / 7]), ([128, 3, 17], [0.2, 0.5, 0.3]),
                      ([32], [1.0]), ([50, 2], [0.5, 0.5])):
         ref = run(d, radii, w, ["FSG_FORCE_GENERIC"])
-        for env in ([], ["FSG_NO_BULK"], ["FSG_FUSED_V7"]):
+        for env in ([], ["FSG_V6_CFGB"], ["FSG_V6_CFGB", "FSG_NO_BULK"]):
             got = run(d, radii, w, env)
             ok, msg = same(ref, got)
             if not ok:
@@ -67,7 +67,7 @@ S = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 d = k.synth_dem((S, S))
 ws = torch.empty(max(256, k.topousm_fast_workspace_bytes((S, S), [2, 8, 32, 128, 512, 2048], 1.0)), dtype=torch.uint8, device="cuda")
 out = torch.empty((S, S), dtype=torch.float32, device="cuda")
-for name, env in (("v5", ["FSG_FUSED_V5"]), ("v6", []), ("v6 nobulk", ["FSG_NO_BULK"]), ("v7", ["FSG_FUSED_V7"])):
+for name, env in (("v5", ["FSG_FUSED_V5"]), ("v6", []), ("v6 cfgB", ["FSG_V6_CFGB"]), ("v7", ["FSG_FUSED_V7"])):
     for radii, w in (([2, 8, 32, 128, 512, 2048], W6), ([2, 8, 32], [4 / 7, 2 / 7, 1 / 7]), ([128, 512, 2048], [4 / 7, 2 / 7, 1 / 7]), ([2], [1.0])):
         run(d, radii, w, env, workspace=ws, out=out)
         k.profile_enable(True)
