@@ -18,11 +18,43 @@ __global__ void __launch_bounds__(128) box_axis0_kernel(Grid g, int size, float*
   const float nf = (float)size;
   double s = 0.0;
   int cnt = 0;
-  for (int k = -lo; k <= hi; ++k) {
-    float v = g.src[(reflect_index(y0 + k, g.h) - g.row_off) * g.ld + x];
-    bool ok = v == v;
-    s += ok ? (double)v : 0.0;
-    cnt += ok;
+  const bool interior = y0 - lo >= 0 && y1 + hi < g.h;
+  if (interior) {
+    const float* pk = g.src + (y0 - lo - g.row_off) * g.ld + x;
+    double s1 = 0.0;
+    for (int k = 0; k < size; ++k) {      // exact sums: two accumulators, association free
+      float v = *pk;
+      bool ok = v == v;
+      if (k & 1) s1 += ok ? (double)v : 0.0;
+      else s += ok ? (double)v : 0.0;
+      cnt += ok;
+      pk += g.ld;
+    }
+    s += s1;
+  } else {
+    for (int k = -lo; k <= hi; ++k) {
+      float v = g.src[(reflect_index(y0 + k, g.h) - g.row_off) * g.ld + x];
+      bool ok = v == v;
+      s += ok ? (double)v : 0.0;
+      cnt += ok;
+    }
+  }
+  if (interior) {
+    // interior chunk: no mirroring, plain row pointers
+    const float* pin = g.src + (y0 + hi + 1 - g.row_off) * g.ld + x;
+    const float* pout = g.src + (y0 - lo - g.row_off) * g.ld + x;
+    float* pv = tv + (y0 - oy0) * g.w + x;
+    float* pw = tw + (y0 - oy0) * g.w + x;
+    for (int64_t y = y0; y < y1; ++y) {
+      *pv = (float)div_by_count(s, n, inv);
+      *pw = (float)cnt / nf;
+      float vin = *pin, vout = *pout;
+      bool oin = vin == vin, oout = vout == vout;
+      s += (oin ? (double)vin : 0.0) - (oout ? (double)vout : 0.0);
+      cnt += (int)oin - (int)oout;
+      pin += g.ld; pout += g.ld; pv += g.w; pw += g.w;
+    }
+    return;
   }
   for (int64_t y = y0; y < y1; ++y) {
     tv[(y - oy0) * g.w + x] = (float)div_by_count(s, n, inv);
@@ -49,17 +81,22 @@ __global__ void __launch_bounds__(256) box_axis1_kernel(const float* __restrict_
   const int64_t y0 = (int64_t)blockIdx.y * RT;
   const int lo = size / 2;
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < RT * span; idx += 256) {
-    int r = idx / span, c = idx - r * span;
-    int64_t gy = y0 + r;
-    float a = 0.f, b = 0.f;
-    if (gy < h) {
-      int64_t gx = reflect_index(x0 - lo + c, w);
-      a = tv[gy * w + gx];
-      b = tw[gy * w + gx];
+  const bool interior_x = x0 - lo >= 0 && x0 - lo + span <= w;
+  for (int r = tid / 32; r < RT; r += 8) {       // one warp per tile row, lanes over the columns
+    const int64_t gy = y0 + r;
+    const bool row_ok = gy < h;
+    const float* rv = tv + gy * w;
+    const float* rw = tw + gy * w;
+    for (int c = tid & 31; c < span; c += 32) {
+      float a = 0.f, b = 0.f;
+      if (row_ok) {
+        int64_t gx = interior_x ? x0 - lo + c : reflect_index(x0 - lo + c, w);
+        a = rv[gx];
+        b = rw[gx];
+      }
+      sv_p[r * P + c] = a;
+      sw_p[r * P + c] = b;
     }
-    sv_p[r * P + c] = a;
-    sw_p[r * P + c] = b;
   }
   __syncthreads();
   constexpr int NSEG = 256 / RT;

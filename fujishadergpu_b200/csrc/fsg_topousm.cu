@@ -156,7 +156,7 @@ static int make_plan(int64_t H, int64_t W, const int32_t* radii, int n, double p
 // ------------------------------------------------------------------------------------------
 constexpr int PY_ROWS = 16;
 constexpr int PY_COLS = 512;
-constexpr int PY_STRIDE = PY_COLS + PY_COLS / 16;  // +1 pad per 16 columns
+constexpr int PY_STRIDE = PY_COLS + 4;  // 16-byte aligned rows; +4 words: 128-bit loads by rows (factor 16) are conflict free
 
 struct PyramidParams {
   const float* dem;
@@ -169,7 +169,7 @@ struct PyramidParams {
   int* flags;  // flags[k] = level k has a void (all-NaN) cell
 };
 
-__device__ __forceinline__ int py_idx(int row, int col) { return row * PY_STRIDE + col + (col >> 4); }
+__device__ __forceinline__ int py_idx(int row, int col) { return row * PY_STRIDE + col; }
 
 // One cell: `sum(axis=(1,3), dtype=float32)` of NumPy = per cell row a pairwise row sum
 // (n<8: sequential; n>=8: 8 lanes then ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))), rows added in order.
@@ -217,6 +217,44 @@ __device__ __forceinline__ void cell_reduce(const float* sm, int row0, int col0,
   }
   *tot = T;
   *cnt = Cn;
+}
+
+// 128-bit variants for the two factors the reference's rule produces at 1 m pixels (4 and 16): same
+// operation order as cell_reduce<4> / row_reduce<16>, a quarter of the shared-memory instructions.
+__device__ __forceinline__ void fin4(const float4 q, float* v, float* c) {
+  const float x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    bool ok = isfinite(x[k]);
+    v[k] = ok ? x[k] : 0.f;
+    c[k] = ok ? 1.f : 0.f;
+  }
+}
+__device__ __forceinline__ void cell4_vec(const float* sm, int row0, int col0, float* tot, float* cnt) {
+  float T = 0.f, Cn = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v[4], c[4];
+    fin4(*reinterpret_cast<const float4*>(sm + py_idx(row0 + i, col0)), v, c);
+    float rs = ((v[0] + v[1]) + v[2]) + v[3];   // n < 8: sequential
+    float rc = ((c[0] + c[1]) + c[2]) + c[3];
+    if (i == 0) { T = rs; Cn = rc; } else { T = T + rs; Cn = Cn + rc; }
+  }
+  *tot = T;
+  *cnt = Cn;
+}
+__device__ __forceinline__ void row16_vec(const float* sm, int row, int col0, float* rs_out, float* rc_out) {
+  float r[8], c[8], v[4], w[4];
+  fin4(*reinterpret_cast<const float4*>(sm + py_idx(row, col0)), r, c);
+  fin4(*reinterpret_cast<const float4*>(sm + py_idx(row, col0 + 4)), r + 4, c + 4);
+  fin4(*reinterpret_cast<const float4*>(sm + py_idx(row, col0 + 8)), v, w);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { r[k] = r[k] + v[k]; c[k] = c[k] + w[k]; }
+  fin4(*reinterpret_cast<const float4*>(sm + py_idx(row, col0 + 12)), v, w);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { r[4 + k] = r[4 + k] + v[k]; c[4 + k] = c[4 + k] + w[k]; }
+  *rs_out = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  *rc_out = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
 }
 
 // One cell ROW of a factor >= 8 cell (the pairwise row sum of cell_reduce): used by the two-stage path of
@@ -279,7 +317,7 @@ __device__ void cell_reduce_contig(const float* sm, int f, int row0, int col0, f
 }
 
 __global__ void __launch_bounds__(256) pyramid_kernel(PyramidParams p) {
-  __shared__ float sm[PY_ROWS * PY_STRIDE];
+  __shared__ __align__(16) float sm[PY_ROWS * PY_STRIDE];
   const int64_t x0 = (int64_t)blockIdx.x * PY_COLS;
   const int64_t y0 = (int64_t)blockIdx.y * PY_ROWS;
   const int tid = threadIdx.x;
@@ -300,8 +338,7 @@ __global__ void __launch_bounds__(256) pyramid_kernel(PyramidParams p) {
           if (gx + k < p.W) v[k] = src[k];
       }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) sm[py_idx(r, c4 + k)] = v[k];
+    *reinterpret_cast<float4*>(sm + py_idx(r, c4)) = make_float4(v[0], v[1], v[2], v[3]);
   }
   __syncthreads();
   __shared__ float RS[PY_ROWS * PY_COLS / 8], RC[PY_ROWS * PY_COLS / 8];
@@ -310,13 +347,23 @@ __global__ void __launch_bounds__(256) pyramid_kernel(PyramidParams p) {
     const int cells_x = PY_COLS / f, cells_y = PY_ROWS / f;
     if (f >= 8 && p.gw[lv] != 1) {
       // stage 1: one (cell, row) pair per thread; stage 2: rows added in order, one cell per thread
-      for (int it = tid; it < cells_x * PY_ROWS; it += 256) {
-        int row = it / cells_x, cx = it - row * cells_x;
-        float rs, rc;
-        if (f == 8) row_reduce<8>(sm, row, cx * 8, &rs, &rc);
-        else row_reduce<16>(sm, row, cx * 16, &rs, &rc);
-        RS[it] = rs;
-        RC[it] = rc;
+      if (f == 16) {
+        // lanes = the 16 rows of two adjacent cells: rows are 516 words apart -> conflict-free LDS.128
+        for (int cx = tid / PY_ROWS; cx < cells_x; cx += 256 / PY_ROWS) {
+          const int row = tid % PY_ROWS;
+          float rs, rc;
+          row16_vec(sm, row, cx * 16, &rs, &rc);
+          RS[row * cells_x + cx] = rs;
+          RC[row * cells_x + cx] = rc;
+        }
+      } else {
+        for (int it = tid; it < cells_x * PY_ROWS; it += 256) {
+          int row = it / cells_x, cx = it - row * cells_x;
+          float rs, rc;
+          row_reduce<8>(sm, row, cx * 8, &rs, &rc);
+          RS[it] = rs;
+          RC[it] = rc;
+        }
       }
       __syncthreads();
       for (int i = tid; i < cells_x * cells_y; i += 256) {
@@ -343,7 +390,7 @@ __global__ void __launch_bounds__(256) pyramid_kernel(PyramidParams p) {
       float tot, cnt;
       if (p.gw[lv] == 1) cell_reduce_contig(sm, f, cy * f, cx * f, &tot, &cnt);
       else if (f == 2) cell_reduce<2>(sm, cy * 2, cx * 2, &tot, &cnt);
-      else if (f == 4) cell_reduce<4>(sm, cy * 4, cx * 4, &tot, &cnt);
+      else if (f == 4) cell4_vec(sm, cy * 4, cx * 4, &tot, &cnt);
       else if (f == 8) cell_reduce<8>(sm, cy * 8, cx * 8, &tot, &cnt);
       else cell_reduce<16>(sm, cy * 16, cx * 16, &tot, &cnt);
       float out;
