@@ -45,7 +45,22 @@ __global__ void __launch_bounds__(128) box_axis0_kernel(Grid g, int size, float*
     const float* pout = g.src + (y0 - lo - g.row_off) * g.ld + x;
     float* pv = tv + (y0 - oy0) * g.w + x;
     float* pw = tw + (y0 - oy0) * g.w + x;
-    for (int64_t y = y0; y < y1; ++y) {
+    int64_t y = y0;
+    for (; y + 4 <= y1; y += 4) {     // four rows of loads in flight
+      float vi[4], vo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { vi[k] = pin[k * g.ld]; vo[k] = pout[k * g.ld]; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        pv[k * g.w] = (float)div_by_count(s, n, inv);
+        pw[k * g.w] = (float)cnt / nf;
+        bool oin = vi[k] == vi[k], oout = vo[k] == vo[k];
+        s += (oin ? (double)vi[k] : 0.0) - (oout ? (double)vo[k] : 0.0);
+        cnt += (int)oin - (int)oout;
+      }
+      pin += 4 * g.ld; pout += 4 * g.ld; pv += 4 * g.w; pw += 4 * g.w;
+    }
+    for (; y < y1; ++y) {
       *pv = (float)div_by_count(s, n, inv);
       *pw = (float)cnt / nf;
       float vin = *pin, vout = *pout;
@@ -87,15 +102,28 @@ __global__ void __launch_bounds__(256) box_axis1_kernel(const float* __restrict_
     const bool row_ok = gy < h;
     const float* rv = tv + gy * w;
     const float* rw = tw + gy * w;
-    for (int c = tid & 31; c < span; c += 32) {
-      float a = 0.f, b = 0.f;
-      if (row_ok) {
-        int64_t gx = interior_x ? x0 - lo + c : reflect_index(x0 - lo + c, w);
-        a = rv[gx];
-        b = rw[gx];
+    if (row_ok && interior_x) {
+      const float* pa = rv + x0 - lo;
+      const float* pb = rw + x0 - lo;
+      int c = tid & 31;
+      for (; c + 96 < span; c += 128) {   // eight loads in flight per lane
+        float a0 = pa[c], a1 = pa[c + 32], a2 = pa[c + 64], a3 = pa[c + 96];
+        float b0 = pb[c], b1 = pb[c + 32], b2 = pb[c + 64], b3 = pb[c + 96];
+        sv_p[r * P + c] = a0; sv_p[r * P + c + 32] = a1; sv_p[r * P + c + 64] = a2; sv_p[r * P + c + 96] = a3;
+        sw_p[r * P + c] = b0; sw_p[r * P + c + 32] = b1; sw_p[r * P + c + 64] = b2; sw_p[r * P + c + 96] = b3;
       }
-      sv_p[r * P + c] = a;
-      sw_p[r * P + c] = b;
+      for (; c < span; c += 32) { sv_p[r * P + c] = pa[c]; sw_p[r * P + c] = pb[c]; }
+    } else {
+      for (int c = tid & 31; c < span; c += 32) {
+        float a = 0.f, b = 0.f;
+        if (row_ok) {
+          int64_t gx = reflect_index(x0 - lo + c, w);
+          a = rv[gx];
+          b = rw[gx];
+        }
+        sv_p[r * P + c] = a;
+        sw_p[r * P + c] = b;
+      }
     }
   }
   __syncthreads();

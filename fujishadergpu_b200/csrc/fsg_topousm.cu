@@ -323,22 +323,42 @@ __global__ void __launch_bounds__(256) pyramid_kernel(PyramidParams p) {
   const int tid = threadIdx.x;
   const float qnan = nanf("");
   // coalesced load, ragged edge -> NaN (the reference NaN-pads before reshaping)
-  for (int i = tid; i < PY_ROWS * (PY_COLS / 4); i += 256) {
-    int r = i / (PY_COLS / 4), c4 = (i - r * (PY_COLS / 4)) * 4;
-    int64_t gy = y0 + r, gx = x0 + c4;
-    float v[4] = {qnan, qnan, qnan, qnan};
-    if (gy < p.H) {
-      const float* src = p.dem + gy * p.ld + gx;
-      if (gx + 3 < p.W && ((((uintptr_t)src) & 15) == 0)) {
-        float4 q = *reinterpret_cast<const float4*>(src);
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-      } else {
+  const bool tile_fast = y0 + PY_ROWS <= p.H && x0 + PY_COLS <= p.W && (p.ld % 4 == 0) &&
+                         ((((uintptr_t)p.dem) & 15) == 0);
+  if (tile_fast) {
+    // whole, aligned tile: all eight 16-byte loads of a thread are issued before the first store
+    constexpr int NL = PY_ROWS * (PY_COLS / 4) / 256;
+    float4 q[NL];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (gx + k < p.W) v[k] = src[k];
-      }
+    for (int k = 0; k < NL; ++k) {
+      const int i = tid + k * 256;
+      const int r = i / (PY_COLS / 4), c4 = (i - r * (PY_COLS / 4)) * 4;
+      q[k] = __ldg(reinterpret_cast<const float4*>(p.dem + (y0 + r) * p.ld + x0 + c4));
     }
-    *reinterpret_cast<float4*>(sm + py_idx(r, c4)) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+      const int i = tid + k * 256;
+      const int r = i / (PY_COLS / 4), c4 = (i - r * (PY_COLS / 4)) * 4;
+      *reinterpret_cast<float4*>(sm + py_idx(r, c4)) = q[k];
+    }
+  } else {
+    for (int i = tid; i < PY_ROWS * (PY_COLS / 4); i += 256) {
+      int r = i / (PY_COLS / 4), c4 = (i - r * (PY_COLS / 4)) * 4;
+      int64_t gy = y0 + r, gx = x0 + c4;
+      float v[4] = {qnan, qnan, qnan, qnan};
+      if (gy < p.H) {
+        const float* src = p.dem + gy * p.ld + gx;
+        if (gx + 3 < p.W && ((((uintptr_t)src) & 15) == 0)) {
+          float4 q = *reinterpret_cast<const float4*>(src);
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (gx + k < p.W) v[k] = src[k];
+        }
+      }
+      *reinterpret_cast<float4*>(sm + py_idx(r, c4)) = make_float4(v[0], v[1], v[2], v[3]);
+    }
   }
   __syncthreads();
   __shared__ float RS[PY_ROWS * PY_COLS / 8], RC[PY_ROWS * PY_COLS / 8];
