@@ -8,11 +8,11 @@ constexpr int A1_CW = 256;     // output columns per CTA in the axis-1 pass
 
 // ---------------------------------------------------------------- box, axis 0 (running sums)
 __global__ void __launch_bounds__(128) box_axis0_kernel(Grid g, int size, float* __restrict__ tv, float* __restrict__ tw,
-                                                        int64_t oy0, int64_t oh) {
+                                                        int64_t oy0, int64_t oh, int chunk) {
   int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= g.w) return;
-  int64_t y0 = oy0 + (int64_t)blockIdx.y * A0_CHUNK;
-  int64_t y1 = y0 + A0_CHUNK < oy0 + oh ? y0 + A0_CHUNK : oy0 + oh;
+  int64_t y0 = oy0 + (int64_t)blockIdx.y * chunk;
+  int64_t y1 = y0 + chunk < oy0 + oh ? y0 + chunk : oy0 + oh;
   const int lo = size / 2, hi = size - 1 - lo;
   const double n = (double)size, inv = 1.0 / n;
   const float nf = (float)size;
@@ -234,8 +234,15 @@ __global__ void __launch_bounds__(256) gauss_axis1_kernel(const float* __restric
 // ---------------------------------------------------------------- launchers
 int launch_box_axis0(const Grid& g, int size, float* tv, float* tw, int64_t oy0, int64_t oh, cudaStream_t s) {
   if (oh <= 0) return FSG_OK;
-  dim3 grid((unsigned)((g.w + 127) / 128), (unsigned)((oh + A0_CHUNK - 1) / A0_CHUNK));
-  box_axis0_kernel<<<grid, 128, 0, s>>>(g, size, tv, tw, oy0, oh);
+  // rows per thread: 128 on big grids (the window start costs `size` loads per chunk), fewer on small grids so
+  // that at least ~2 CTAs per SM exist
+  const int64_t gx = (g.w + 127) / 128;
+  int64_t want_y = (148 * 2 + gx - 1) / gx;
+  int64_t chunk = (oh + want_y - 1) / want_y;
+  if (chunk > A0_CHUNK) chunk = A0_CHUNK;
+  if (chunk < 16) chunk = 16;
+  dim3 grid((unsigned)gx, (unsigned)((oh + chunk - 1) / chunk));
+  box_axis0_kernel<<<grid, 128, 0, s>>>(g, size, tv, tw, oy0, oh, (int)chunk);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }

@@ -63,10 +63,17 @@ __device__ __forceinline__ void scan_chunks(const Chunks& c, F f) {
     const int64_t r = t / tpr, cb = (t - r * tpr) * SCAN_TILE;
     const float* row = c.ptr[k] + r * c.ld[k];
     const int64_t cend = cb + SCAN_TILE < cols ? cb + SCAN_TILE : cols;
-    for (int64_t x0 = cb; x0 < cend; x0 += blockDim.x) {
-      const int64_t x = x0 + threadIdx.x;
-      const bool in = x < cend;
-      f(in ? row[x] : 0.f, in);
+    constexpr int NL = SCAN_TILE / 256;      // all loads of the tile in flight before the first use
+    float v[NL];
+#pragma unroll
+    for (int q = 0; q < NL; ++q) {
+      const int64_t x = cb + (int64_t)q * 256 + threadIdx.x;
+      v[q] = x < cend ? row[x] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < NL; ++q) {
+      const int64_t x = cb + (int64_t)q * 256 + threadIdx.x;
+      f(v[q], x < cend);
     }
   }
 }
@@ -244,10 +251,15 @@ __global__ void __launch_bounds__(256) count_chunks_kernel(Chunks c, int finite_
     const float* row = c.ptr[k] + r * c.ld[k];
     const int64_t cend = cb + SCAN_TILE < cols ? cb + SCAN_TILE : cols;
     unsigned int local = 0;
-    for (int64_t x = cb + threadIdx.x; x < cend; x += blockDim.x) {
-      float v = row[x];
-      local += finite_only ? (isfinite(v) ? 1u : 0u) : (v == v ? 1u : 0u);
+    constexpr int NL = SCAN_TILE / 256;
+    float v[NL];
+#pragma unroll
+    for (int q = 0; q < NL; ++q) {
+      const int64_t x = cb + (int64_t)q * 256 + threadIdx.x;
+      v[q] = x < cend ? row[x] : nanf("");
     }
+#pragma unroll
+    for (int q = 0; q < NL; ++q) local += finite_only ? (isfinite(v[q]) ? 1u : 0u) : (v[q] == v[q] ? 1u : 0u);
     for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counts[k], (unsigned long long)local);
   }
