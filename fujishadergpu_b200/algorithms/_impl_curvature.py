@@ -4,7 +4,7 @@ from __future__ import annotations
 from .. import kernels as _k
 from .. import _device as _dev
 from ._base import DaskAlgorithm
-from ._impl_hillshade import _check_radii_direct
+from ._impl_hillshade import spatial_responses
 from ._nan_utils import _combine_multiscale_dask, _resolve_spatial_radii_weights, _smooth_for_radius
 
 
@@ -34,8 +34,9 @@ class CurvatureAlgorithm(DaskAlgorithm):
             if hasattr(gpu_arr, "map_overlap"):
                 raise NotImplementedError("curvature: spatial mode takes a device block, not a dask array, on the B200 path")
             radii, weights = _resolve_spatial_radii_weights(params.get("radii"), params.get("weights", None), kw["pixel_size"])
-            _check_radii_direct("curvature", gpu_arr, radii)
-            responses = [compute_curvature_spatial_block(gpu_arr, radius=float(r), **kw) for r in radii]
+            responses = spatial_responses(gpu_arr, radii, params, block_fn=compute_curvature_spatial_block,
+                                          depth_for_scale=lambda rr: max(3, int(float(rr) * 2 + 2)),
+                                          curvature_type=kw["curvature_type"])
             return _combine_multiscale_dask(responses, weights=weights, agg=params.get("agg", "mean"))
         if hasattr(gpu_arr, "map_overlap"):
             return gpu_arr.map_overlap(compute_curvature_block, depth=2, boundary="reflect", dtype="float32", **kw)

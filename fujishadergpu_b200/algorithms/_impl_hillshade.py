@@ -5,7 +5,8 @@ from __future__ import annotations
 from .. import kernels as _k
 from .. import _device as _dev
 from ._base import Constants, DaskAlgorithm
-from ._nan_utils import _resolve_spatial_radii_weights, _smooth_for_radius, large_radius_threshold
+from ._nan_utils import (_resolve_spatial_radii_weights, _smooth_for_radius, large_radius_threshold,
+                         multiscale_response_fields)
 
 
 def compute_hillshade_block(block, *, azimuth=Constants.DEFAULT_AZIMUTH, altitude=Constants.DEFAULT_ALTITUDE,
@@ -24,15 +25,17 @@ def compute_hillshade_spatial_block(block, *, azimuth=Constants.DEFAULT_AZIMUTH,
                                    pixel_size=pixel_size, pixel_scale_x=pixel_scale_x, pixel_scale_y=pixel_scale_y)
 
 
-def _check_radii_direct(name: str, block, radii) -> None:
-    """Radii above the large-radius threshold take the reference's overview path (a global <= 2048 px
-    overview sampled per block), which is not on the B200 path yet."""
+def spatial_responses(block, radii, params, *, block_fn, depth_for_scale, **block_kwargs) -> list:
+    """Per-radius responses of a spatial-mode algorithm: radii above the large-radius threshold
+    max(256, min(H, W) // 16) are computed on a coarsened copy and sampled back (reference
+    _nan_utils.py:441-524 through HillshadeAlgorithm.process :103-113 and its slope / curvature twins)."""
     thr = large_radius_threshold(block, fallback=int(max(radii)) if radii else 64)
-    big = [r for r in radii if int(round(float(r))) > thr]
-    if big:
-        raise NotImplementedError(
-            f"{name}: spatial radii {big} exceed the large-radius threshold {thr} of this raster; the overview "
-            "path for them is not part of the B200 hot path yet (SURVEY.md section 8f rank 2)")
+    return multiscale_response_fields(
+        block, [float(r) for r in radii], block_fn=block_fn, radius_kw="radius", depth_for_scale=depth_for_scale,
+        is_large=lambda rr: int(round(float(rr))) > thr, pixel_size=params.get("pixel_size", 1.0),
+        pixel_scale_x=params.get("pixel_scale_x"), pixel_scale_y=params.get("pixel_scale_y"),
+        coarse_dem=params.get("_overview_coarse_dem"), coarse_decimation=params.get("_overview_decimation"),
+        **block_kwargs)
 
 
 def _weighted_f32(responses, weights):
@@ -75,8 +78,9 @@ class HillshadeAlgorithm(DaskAlgorithm):
         if mode == "spatial" or (multiscale and len(radii) > 1):
             if hasattr(gpu_arr, "map_overlap"):
                 raise NotImplementedError("hillshade: spatial mode takes a device block, not a dask array, on the B200 path")
-            _check_radii_direct("hillshade", gpu_arr, radii)
-            results = [compute_hillshade_spatial_block(gpu_arr, radius=float(r), **kw) for r in radii]
+            results = spatial_responses(gpu_arr, radii, params, block_fn=compute_hillshade_spatial_block,
+                                        depth_for_scale=lambda rr: max(2, int(float(rr) * 2 + 1)),
+                                        azimuth=kw["azimuth"], altitude=kw["altitude"], z_factor=kw["z_factor"])
             if agg == "stack":
                 return _combine_multiscale_dask(results, agg="stack")
             if agg == "mean":

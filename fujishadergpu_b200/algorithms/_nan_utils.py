@@ -132,6 +132,96 @@ def large_radius_threshold(block, fallback: int) -> int:
     return int(max(256, int(min_chunk) // 16))
 
 
+def coarsen_factor_for_shape(shape, coarse_max: int = 2048) -> int:
+    """reference :231-236 -- power-of-two decimation so the longest side is <= coarse_max."""
+    longest = max(int(shape[0]), int(shape[1]))
+    if longest <= int(coarse_max):
+        return 1
+    return 1 << int(np.ceil(np.log2(longest / float(coarse_max))))
+
+
+def _symmetric_pad(t, depth: int):
+    """dask map_overlap(boundary='reflect') on a single chunk: edge-inclusive mirror padding."""
+    import torch
+    ri = torch.from_numpy(np.pad(np.arange(int(t.shape[0])), depth, mode="symmetric")).to(t.device)
+    ci = torch.from_numpy(np.pad(np.arange(int(t.shape[1])), depth, mode="symmetric")).to(t.device)
+    return t.index_select(0, ri).index_select(1, ci).contiguous()
+
+
+def coarse_large_radius_response(block, *, block_fn, radius_kw: str, radius: float, factor: int, depth_for_radius,
+                                 pixel_size: float = 1.0, pixel_scale_x=None, pixel_scale_y=None,
+                                 coarse_cache: Optional[dict] = None, coarse_dem=None, coarse_decimation=None,
+                                 **block_kwargs):
+    """reference :329-438 with one block == the whole raster: the response of a large radius is computed on a
+    coarsened DEM (the injected overview when the host provides one, else the F x F NaN-aware block mean with
+    the ragged edge trimmed, as da.coarsen(nanmean, trim_excess=True)), with radius and pixel sizes scaled by
+    the factor, and sampled back bilinearly at pixel centres; NoData is restored from the DEM."""
+    import torch
+    t = _dev.as_f32_2d(block)
+    H, W = int(t.shape[0]), int(t.shape[1])
+    kw = dict(block_kwargs)
+    kw.pop("grad_stats_map", None)
+    if coarse_dem is not None and coarse_decimation is not None:
+        fac = float(coarse_decimation)
+        kw[radius_kw] = max(1, int(round(float(radius) / fac)))
+        kw["pixel_size"] = float(pixel_size) * fac
+        if pixel_scale_x is not None:
+            kw["pixel_scale_x"] = float(pixel_scale_x) * fac
+        if pixel_scale_y is not None:
+            kw["pixel_scale_y"] = float(pixel_scale_y) * fac
+        coarse_resp = _dev.as_f32_2d(block_fn(coarse_dem, **kw))
+    else:
+        F = int(factor)
+        if F not in (2, 4, 8, 16):
+            raise NotImplementedError(
+                f"large spatial radius {radius}: coarsening factor {F} (raster longer than 32768 px) is not on the "
+                "B200 path; pass the host's overview as _overview_coarse_dem / _overview_decimation")
+        if coarse_cache is not None and "coarse" in coarse_cache:
+            coarse = coarse_cache["coarse"]
+        else:
+            hc, wc = H // F, W // F
+            coarse = _k.pyramid_band(t[: hc * F, : wc * F], [F])[0][0]     # block mean of the valid members, no void fill
+            if coarse_cache is not None:
+                coarse_cache["coarse"] = coarse
+        r_coarse = max(1, int(round(float(radius) / float(F))))
+        kw[radius_kw] = r_coarse
+        kw["pixel_size"] = float(pixel_size) * float(F)
+        if pixel_scale_x is not None:
+            kw["pixel_scale_x"] = float(pixel_scale_x) * float(F)
+        if pixel_scale_y is not None:
+            kw["pixel_scale_y"] = float(pixel_scale_y) * float(F)
+        d = int(depth_for_radius(r_coarse))
+        padded = _symmetric_pad(coarse, d)
+        resp = _dev.as_f32_2d(block_fn(padded, **kw))
+        coarse_resp = resp[d:d + coarse.shape[0], d:d + coarse.shape[1]].contiguous()
+    up = _dev.as_f32_2d(_bilinear_sample_coarse(coarse_resp, 0, H, 0, W, H, W))
+    return _dev.like_input(torch.where(torch.isnan(t), torch.full_like(up, float("nan")), up), block)
+
+
+def multiscale_response_fields(block, scales, *, block_fn, depth_for_scale, radius_kw: str = "scale", is_large=None,
+                               pixel_size: float = 1.0, pixel_scale_x=None, pixel_scale_y=None,
+                               coarse_dem=None, coarse_decimation=None, max_depth: int = 150, **block_kwargs) -> list:
+    """reference :441-524 -- one response per scale; a large scale goes through the coarse path when the raster
+    is longer than 2048 px (coarsening factor > 1) or the host injected an overview."""
+    F = coarsen_factor_for_shape(tuple(block.shape))
+    cache: dict = {}
+    out = []
+    for s in scales:
+        sv = float(s)
+        d = int(depth_for_scale(sv))
+        large = is_large(sv) if is_large is not None else (d > int(max_depth))
+        if large and (F > 1 or (coarse_dem is not None and coarse_decimation is not None)):
+            out.append(coarse_large_radius_response(
+                block, block_fn=block_fn, radius_kw=radius_kw, radius=sv, factor=F,
+                depth_for_radius=lambda sc: max(1, int(depth_for_scale(sc))), pixel_size=pixel_size,
+                pixel_scale_x=pixel_scale_x, pixel_scale_y=pixel_scale_y, coarse_cache=cache, coarse_dem=coarse_dem,
+                coarse_decimation=coarse_decimation, **block_kwargs))
+        else:
+            out.append(block_fn(block, pixel_size=pixel_size, pixel_scale_x=pixel_scale_x, pixel_scale_y=pixel_scale_y,
+                                **{radius_kw: sv}, **block_kwargs))
+    return out
+
+
 def _accumulate(responses, weights32, first_mode: str):
     import torch
     acc = torch.empty_like(_dev.as_f32_2d(responses[0]))
@@ -180,5 +270,6 @@ __all__ = [
     "_radius_to_downsample_factor", "_resolve_spatial_radii_weights", "_normalize_spatial_radii",
     "_clean_normalized_weights", "_weight_count_matches", "_downsample_nan_aware", "_upsample_to_shape",
     "_bilinear_sample_coarse", "handle_nan_with_gaussian", "_smooth_for_radius", "large_radius_threshold",
-    "_combine_multiscale_dask",
+    "_combine_multiscale_dask", "coarsen_factor_for_shape", "coarse_large_radius_response",
+    "multiscale_response_fields",
 ]

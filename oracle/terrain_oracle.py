@@ -577,6 +577,40 @@ def curvature_spatial_block(dem, *, radius=4.0, curvature_type="mean", pixel_siz
                            pixel_scale_y=pixel_scale_y)
 
 
+def coarsen_factor(shape, coarse_max: int = 2048) -> int:
+    """algorithms/_nan_utils.py:231-236."""
+    longest = max(int(shape[0]), int(shape[1]))
+    if longest <= int(coarse_max):
+        return 1
+    return 1 << int(np.ceil(np.log2(longest / float(coarse_max))))
+
+
+def large_radius_response(dem, radius, factor: int, block_fn, depth: int, *, pixel_size=1.0, pixel_scale_x=None,
+                          pixel_scale_y=None, **kw) -> np.ndarray:
+    """algorithms/_nan_utils.py:329-438 for a single-chunk raster without an injected overview: da.coarsen with
+    nanmean over factor x factor blocks (ragged edge trimmed), block function with map_overlap(depth,
+    boundary='reflect') on the coarse array, pixel-centre bilinear sampling back, NoData restored."""
+    a = np.asarray(dem, dtype=F32)
+    H, W = a.shape
+    F = int(factor)
+    hc, wc = H // F, W // F
+    cells = a[: hc * F, : wc * F].reshape(hc, F, wc, F)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            coarse = np.nanmean(cells, axis=(1, 3)).astype(F32)
+    r_c = max(1, int(round(float(radius) / float(F))))
+    d = int(depth(r_c))
+    padded = np.pad(coarse, d, mode="symmetric")
+    resp = block_fn(padded, radius=r_c, pixel_size=float(pixel_size) * F,
+                    pixel_scale_x=None if pixel_scale_x is None else float(pixel_scale_x) * F,
+                    pixel_scale_y=None if pixel_scale_y is None else float(pixel_scale_y) * F, **kw)
+    resp = np.ascontiguousarray(resp[d:d + hc, d:d + wc], dtype=F32)
+    up = sample_overview_field(resp, 0, H, 0, W, H, W)
+    return np.where(np.isnan(a), F32(np.nan), up).astype(F32)
+
+
 def combine_responses(responses, *, weights=None, agg: str = "mean") -> np.ndarray:
     """algorithms/tile/dask_bridge.py:28-69 (_combine_direct): f32 weights normalised in f32, the sum
     accumulated in list order, every product / sum an individually rounded f32 op."""

@@ -108,8 +108,38 @@ def test_spatial_mode_algorithm_classes_vs_oracle():
     want = orc.combine_responses(resp, weights=w, agg="mean")
     got = _np(ALGORITHMS["hillshade"].process(d, mode="spatial", radii=radii, weights=None, **kw))
     assert_close_f32(got, want, what="hillshade spatial")
-    with pytest.raises(NotImplementedError):
-        ALGORITHMS["hillshade"].process(d, mode="spatial", radii=[2, 2048], **kw)   # overview path: 8f rank 2
+
+
+def test_spatial_mode_large_radius_coarse_path_vs_oracle():
+    """Radii above max(256, min(H,W)//16) on a raster longer than 2048 px: coarsened DEM, block function on the
+    reflect-padded coarse array, pixel-centre bilinear sampling back (reference _nan_utils.py:329-438)."""
+    from fujishadergpu_b200.algorithms.dask_registry import ALGORITHMS
+    dem = orc.synth_dem(2600, 3000, seed=43, nodata=True)
+    d = _cuda(dem)
+    kw = dict(pixel_scale_x=1.0, pixel_scale_y=-1.0, pixel_size=1.0)
+    radii, w = [8, 300], [0.5, 0.5]
+    F = orc.coarsen_factor(dem.shape)
+    assert F == 2
+    # hillshade: f32-normalised weights
+    big = orc.large_radius_response(dem, 300.0, F, orc.hillshade_spatial_block, lambda rc: max(2, int(rc * 2 + 1)), **kw)
+    small = orc.hillshade_spatial_block(dem, radius=8.0, **kw)
+    want = orc.combine_responses([small, big], weights=w, agg="mean")
+    got = _np(ALGORITHMS["hillshade"].process(d, mode="spatial", radii=radii, weights=w, **kw))
+    assert_close_f32(got, want, rtol=1e-5, atol=2e-6, what="hillshade spatial, large radius")
+    # slope: python-float weights
+    big = orc.large_radius_response(dem, 300.0, F, orc.slope_spatial_block, lambda rc: max(2, int(rc * 2 + 1)),
+                                    unit="degree", **kw)
+    small = orc.slope_spatial_block(dem, radius=8.0, unit="degree", **kw)
+    want = small * np.float32(0.5) + big * np.float32(0.5)
+    got = _np(ALGORITHMS["slope"].process(d, mode="spatial", radii=radii, weights=w, unit="degree", **kw))
+    assert_close_f32(got, want, rtol=1e-5, atol=2e-5, what="slope spatial, large radius")
+    # an injected overview (what the reference's orchestration passes) is used as given
+    ov = _cuda(orc.synth_dem(650, 750, seed=44))
+    got = ALGORITHMS["hillshade"].process(d, mode="spatial", radii=[300], weights=[1.0], _overview_coarse_dem=ov,
+                                          _overview_decimation=4.0, **kw)
+    resp = orc.hillshade_spatial_block(_np(ov), radius=75, pixel_size=4.0, pixel_scale_x=4.0, pixel_scale_y=-4.0)
+    want = np.where(np.isnan(dem), np.float32(np.nan), orc.sample_overview_field(resp, 0, 2600, 0, 3000, 2600, 3000))
+    assert_close_f32(_np(got), want, rtol=1e-5, atol=2e-6, what="hillshade spatial, injected overview")
 
 
 def test_gradient_family_large_vs_oracle():
