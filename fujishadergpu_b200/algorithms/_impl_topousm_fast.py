@@ -41,6 +41,27 @@ def split_radii_by_threshold(radii, weights, threshold):
     return near_r, near_w, far_r, far_w
 
 
+def compute_topousm_fast_large_coarse_field(coarse_dem, *, large_radii, large_weights, decimation: float):
+    """reference :133-155 -- Sum_i w_i * mean_{r_i}(coarse_dem) on the overview grid (NaN-aware box, 'reflect';
+    sigma-1 Gaussian when the scaled radius is <= 1), accumulated in list order in f32."""
+    import torch
+    t = _dev.as_f32_2d(coarse_dem)
+    gh = int(t.shape[0])
+    field = None
+    for r, w in zip(large_radii, large_weights):
+        r_coarse = max(1, int(round(float(r) / max(float(decimation), 1.0))))
+        size = 0 if r_coarse <= 1 else 2 * r_coarse + 1      # size 0 = sigma-1 Gaussian, 'nearest'
+        mean_c = _k.grid_mean_band(t, 0, gh, size, 0, gh)
+        if field is None:
+            field = torch.empty_like(mean_c)
+            _k.combine(field, mean_c, float(w), "first_weighted")
+        else:
+            _k.combine(field, mean_c, float(w), "add_weighted")
+    if field is None:
+        raise ValueError("large_radii must not be empty")
+    return _dev.like_input(field, coarse_dem)
+
+
 def _topousm_fast_add_large_block(block, *, coarse_field, w_large, off_r, off_c, full_h, full_w, block_info=None):
     """reference :158-186 -- W_large*block - bilinear(field) at the block's global position."""
     if block_info is not None and block_info.get(0) is not None:
@@ -91,7 +112,9 @@ class TopoUSMFastAlgorithm(DaskAlgorithm):
             raw = _k.topousm_large_part(t, coarse_field, w_large=w_large, off_r=off_r, off_c=off_c,
                                         full_h=full_h, full_w=full_w)
             if small_r:
-                raw = _k.topousm_fast(t, radii=small_r, weights=small_w, pixel_size=pixel_size, norm_scale=None) + raw
+                small = _k.topousm_fast(t, radii=small_r, weights=small_w, pixel_size=pixel_size, norm_scale=None)
+                _k.combine(small, raw, 1.0, "add_weighted")     # small + large (reference :299-303)
+                raw = small
             if not stats_ok:
                 stats = topousm_fast_stat_func(raw)
             return apply_global_normalization(_dev.like_input(raw, gpu_arr), topousm_fast_norm_func, stats)

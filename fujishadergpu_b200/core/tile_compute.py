@@ -73,3 +73,52 @@ def run_tile_algorithm(algo_instance, algorithm: str, dem_gpu, sigma: float, mul
                 params[key] = algo_params[key]
         return algo_instance.process(dem_gpu, **params)
     return algo_instance.process(dem_gpu, **{"sigma": sigma, "pixel_size": pixel_size, **algo_params})
+
+
+def _nodata_is_nan(nodata) -> bool:
+    try:
+        return nodata is not None and float(nodata) != float(nodata)
+    except (TypeError, ValueError):
+        return False
+
+
+def build_nodata_mask(data, nodata):
+    """reference core/tile_processor.py:185-196 (_build_nodata_mask): numeric NoData (|x - nodata| <= 1e-6) and NaN
+    cells are both NoData; returns a bool array of the input's kind (NumPy in, NumPy out; device in, device out)."""
+    if nodata is None:
+        return None
+    import numpy as np
+    if isinstance(data, np.ndarray):
+        if _nodata_is_nan(nodata):
+            return np.isnan(data)
+        return np.isclose(data, float(nodata), rtol=0.0, atol=1e-6) | np.isnan(data)
+    import torch
+    from .. import _device as _dev
+    t = _dev.as_tensor(data)
+    if _nodata_is_nan(nodata):
+        return torch.isnan(t)
+    return ((t - float(nodata)).abs() <= 1e-6) | torch.isnan(t)
+
+
+def apply_nodata_mask(result_gpu, mask_nodata, nodata):
+    """reference :132-152 -- write the NoData value back over the masked pixels (2-D, HxWxC and CxHxW results)."""
+    if mask_nodata is None:
+        return result_gpu
+    import torch
+    from .. import _device as _dev
+    res = _dev.as_tensor(result_gpu)
+    mask = torch.as_tensor(mask_nodata, device=res.device).to(torch.bool)
+    fill = float(nodata) if nodata is not None else 0.0
+    if res.ndim == 2:
+        res[mask] = fill
+    elif res.ndim == 3:
+        if tuple(res.shape[:2]) == tuple(mask.shape):
+            res[mask, :] = fill
+        elif tuple(res.shape[-2:]) == tuple(mask.shape):
+            res[:, mask] = fill
+        else:
+            raise ValueError(f"Unsupported result/mask shapes for nodata masking: result={tuple(res.shape)}, "
+                             f"mask={tuple(mask.shape)}")
+    else:
+        raise ValueError(f"Unsupported result ndim for nodata masking: {res.ndim}")
+    return result_gpu

@@ -273,6 +273,31 @@ def test_topousm_tiny_and_ragged_rasters_vs_oracle():
         _topo_close(got, want, scale, f"{shape} {radii}")
 
 
+def test_topousm_overview_large_field_and_nodata_mask():
+    """compute_topousm_fast_large_coarse_field (reference _impl_topousm_fast.py:133-155) and the NoData re-mask
+    helpers (core/tile_compute.py:132-152, core/tile_processor.py:185-196)."""
+    from fujishadergpu_b200.algorithms._impl_topousm_fast import compute_topousm_fast_large_coarse_field
+    from fujishadergpu_b200.core.tile_compute import apply_nodata_mask, build_nodata_mask
+    coarse = orc.synth_dem(300, 260, seed=51, nodata=True)
+    kw = dict(large_radii=[512, 2048, 3], large_weights=[0.2, 0.1, 0.05], decimation=16.0)
+    want = orc.topousm_large_field(coarse, **kw)
+    got = _np(compute_topousm_fast_large_coarse_field(_cuda(coarse), **kw))
+    assert np.array_equal(got, want), np.abs(got - want).max()
+    dem = orc.synth_dem(64, 80, seed=52)
+    dem[3, 4] = -9999.0
+    dem[10, 11] = np.nan
+    mask = build_nodata_mask(dem, -9999.0)
+    assert mask[3, 4] and mask[10, 11] and mask.sum() == 2
+    dmask = build_nodata_mask(_cuda(dem), -9999.0)
+    assert np.array_equal(_np(dmask), mask)
+    res = torch.ones((64, 80), device="cuda")
+    apply_nodata_mask(res, mask, float("nan"))
+    assert np.array_equal(np.isnan(_np(res)), mask)
+    stack = torch.ones((3, 64, 80), device="cuda")
+    apply_nodata_mask(stack, dmask, 0.0)
+    assert float(stack[:, 3, 4].abs().sum()) == 0.0 and float(stack.sum()) == 3 * (64 * 80 - 2)
+
+
 def test_topousm_weights_length_mismatch_raises():
     from fujishadergpu_b200.algorithms._impl_topousm_fast import compute_topousm_fast_efficient_block
     with pytest.raises(ValueError):
