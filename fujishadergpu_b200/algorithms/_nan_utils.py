@@ -99,6 +99,23 @@ def _upsample_to_shape(block, target_shape):
     return _dev.like_input(_k.upsample(block, target_shape), block)
 
 
+def handle_nan_with_uniform(block, size: int, mode: str = "reflect"):
+    """reference :34-47 -- (NaN-aware box mean, nan_mask); runs in libfsg_b200 (exact window sums)."""
+    import torch
+    if str(mode) != "reflect":
+        raise NotImplementedError("handle_nan_with_uniform: only mode='reflect' is on the B200 path")
+    t = _dev.as_f32_2d(block)
+    gh = int(t.shape[0])
+    return _dev.like_input(_k.grid_mean_band(t, 0, gh, int(size), 0, gh), block), torch.isnan(t)
+
+
+def restore_nan(result, nan_mask):
+    """reference :701-705 -- in-place result[mask] = NaN."""
+    r = _dev.as_tensor(result)
+    r[_dev.as_tensor(nan_mask).to(r.device)] = float("nan")
+    return result
+
+
 def handle_nan_with_gaussian(block, sigma: float, mode: str = "nearest"):
     """reference :18-31 -- (smoothed, nan_mask); the NaN-aware Gaussian runs in libfsg_b200."""
     import torch
@@ -269,7 +286,7 @@ def _bilinear_sample_coarse(coarse, r0: int, r1: int, c0: int, c1: int, full_h: 
 __all__ = [
     "_radius_to_downsample_factor", "_resolve_spatial_radii_weights", "_normalize_spatial_radii",
     "_clean_normalized_weights", "_weight_count_matches", "_downsample_nan_aware", "_upsample_to_shape",
-    "_bilinear_sample_coarse", "handle_nan_with_gaussian", "_smooth_for_radius", "large_radius_threshold",
+    "_bilinear_sample_coarse", "handle_nan_with_uniform", "restore_nan", "handle_nan_with_gaussian", "_smooth_for_radius", "large_radius_threshold",
     "_combine_multiscale_dask", "coarsen_factor_for_shape", "coarse_large_radius_response",
     "multiscale_response_fields",
 ]

@@ -15,6 +15,56 @@ from ..io.output_encoding import quantize_params, resolve_output_range
 
 _TORCH_DT = {"float32": torch.float32, "int16": torch.int16, "uint8": torch.uint8}
 
+# reference core/tile_processor.py:64-87 -- canonical name -> tile class (the five on the B200 path)
+DEFAULT_ALGORITHMS = {
+    "topousm_fast": "TopoUSMFastAlgorithm", "hillshade": "HillshadeAlgorithm", "slope": "SlopeAlgorithm",
+    "curvature": "CurvatureAlgorithm", "openness": "OpennessAlgorithm",
+}
+SPATIAL_TILE_ALGORITHMS = {"hillshade", "slope", "curvature", "openness"}
+
+
+def _required_padding_for_algorithm(algorithm: str, algo_params: dict, sigma: float, pixel_size: float,
+                                    target_distances=None, tile_size: int = 1024) -> int:
+    """reference core/tile_processor.py:207-383 for the hot-path algorithms: halo (pixels, rounded up to 32) a tile
+    needs so that its core equals the whole-raster result.  topousm_fast: max radius + 16; spatial mode of the
+    Gaussian-smoothing algorithms: 2 R + 2 over the radii at or below the large-radius threshold
+    max(256, tile_size // 16) (larger ones come from the overview); openness spatial: R + 16."""
+    import math
+    from .tile_compute import _normalize_topousm_fast_radii_and_weights
+    try:
+        base = int(math.ceil(max(float(sigma), 0.0) * 5.0))
+    except Exception:
+        base = 32
+    required = max(32, base)
+    mode = str(algo_params.get("mode", "spatial")).lower()
+    overview_active = mode == "spatial" and bool(algo_params.get("radii")) and algorithm != "topousm_fast"
+    thr_switch = max(256, int(tile_size) // 16)
+    if algorithm == "topousm_fast":
+        radii, _ = _normalize_topousm_fast_radii_and_weights(
+            target_distances=target_distances, weights=algo_params.get("weights"), pixel_size=pixel_size,
+            manual_radii=algo_params.get("radii"), manual_weights=algo_params.get("weights"))
+        if radii:
+            required = max(required, int(max(radii) + 16))
+    if mode == "spatial" and algorithm in SPATIAL_TILE_ALGORITHMS:
+        radii = algo_params.get("radii")
+        if not radii:
+            from ..algorithms.common.spatial_mode import auto_spatial_radii
+            radii = auto_spatial_radii(None)
+        try:
+            radii_f = [float(r) for r in radii if float(r) > 0]
+            if overview_active:
+                small = [r for r in radii_f if int(round(r)) <= thr_switch] or [min(radii_f)]
+                max_radius = int(round(max(small)))
+            else:
+                max_radius = max(int(round(r)) for r in radii_f)
+        except Exception:
+            max_radius = 32
+        if algorithm == "openness":
+            required = max(required, int(max_radius + 16))
+        else:
+            required = max(required, int(max_radius * 2 + 2))
+    return max(32, ((required + 31) // 32) * 32)
+
 
 class HostTilePipeline:
     """Re-usable device/host staging for repeated tiles of one shape (no allocation per call)."""

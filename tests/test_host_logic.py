@@ -139,3 +139,19 @@ def test_percentile_host_arithmetic_equals_numpy():
             if gamma >= 0.5:
                 out = hi - d * (1 - gamma)
             assert float(out) == float(np.percentile(a, q)), (n, q)
+
+
+def test_tile_padding_rules():
+    """reference core/tile_processor.py:207-383 (hot-path algorithms), values worked from the reference's rules."""
+    from fujishadergpu_b200.core.tile_processor import DEFAULT_ALGORITHMS, _required_padding_for_algorithm as pad
+    assert set(DEFAULT_ALGORITHMS) == {"topousm_fast", "hillshade", "slope", "curvature", "openness"}
+    ladder = [2, 8, 32, 128, 512, 2048]
+    assert pad("topousm_fast", {"radii": ladder, "mode": "spatial"}, 1.0, 1.0) == 2080          # 2048 + 16 -> 32-aligned
+    assert pad("topousm_fast", {"radii": [1], "mode": "local"}, 1.0, 1.0) == 32
+    assert pad("hillshade", {"mode": "local"}, 1.0, 1.0) == 32
+    # spatial: 2R + 2 over the radii below the overview threshold max(256, tile // 16)
+    assert pad("hillshade", {"mode": "spatial", "radii": ladder}, 1.0, 1.0, tile_size=1024) == 288   # R = 128 -> 258
+    assert pad("slope", {"mode": "spatial", "radii": ladder}, 1.0, 1.0, tile_size=16384) == 1056     # thr 1024, R = 512
+    assert pad("curvature", {"mode": "spatial", "radii": None}, 1.0, 1.0) == 4128                    # auto ladder, no overview
+    assert pad("openness", {"mode": "spatial", "radii": [256]}, 1.0, 1.0) == 288                     # R + 16
+    assert pad("hillshade", {"mode": "local"}, 20.0, 1.0) == 128                                     # 5 sigma
