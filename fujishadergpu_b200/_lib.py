@@ -76,6 +76,13 @@ _SIGNATURES = {
     "fsg_key_rank_info": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, C.c_uint32, _I, _I,
                                _P, _P]),
     "fsg_key_to_float": (C.c_float, [C.c_uint32, _I]),
+    "fsg_select_exchange_words": (C.c_size_t, []),
+    "fsg_select_workspace_bytes": (C.c_size_t, []),
+    "fsg_select_begin": (_I, [_P, C.c_size_t, _P]),
+    "fsg_select_hist": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, _I, _I, _I, _P, _P]),
+    "fsg_select_pick": (_I, [_I, C.c_float, _P, _P]),
+    "fsg_select_next": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, _I, _I, _P, _P]),
+    "fsg_select_finish": (_I, [_P, _I, _P, _P]),
     "fsg_synth_dem": (_I, [_P, _L, _L, _L, _L, _L, C.c_uint64, _I, _P]),
 }
 

@@ -70,14 +70,22 @@ def _overlap(a, b):
 
 
 def exchange_rows(local: torch.Tensor, own: Sequence[Tuple[int, int]], need: Sequence[Tuple[int, int]], rank: int,
-                  dist=None) -> torch.Tensor:
+                  dist=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Every rank holds rows own[rank] of a global 2-D array and wants rows need[rank]; returns the
-    tensor covering need[rank].  Point-to-point only (NCCL send/recv over NVLink, or gloo on CPU)."""
+    tensor covering need[rank].  Point-to-point only (NCCL send/recv over NVLink, or gloo on CPU).
+    `out`: caller's buffer for need[rank]; when `local` already is the matching slice of `out` (a band kept
+    inside its halo buffer, see haloed_band) the own rows are not copied, only the halo rows arrive."""
     lo, hi = need[rank]
-    out = torch.empty((max(0, hi - lo),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if out is None:
+        out = torch.empty((max(0, hi - lo),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    else:
+        assert tuple(out.shape) == (max(0, hi - lo),) + tuple(local.shape[1:]) and out.dtype == local.dtype
     mine = _overlap(own[rank], need[rank])
     if mine:
-        out[mine[0] - lo:mine[1] - lo].copy_(local[mine[0] - own[rank][0]:mine[1] - own[rank][0]])
+        dst = out[mine[0] - lo:mine[1] - lo]
+        src = local[mine[0] - own[rank][0]:mine[1] - own[rank][0]]
+        if not (dst.data_ptr() == src.data_ptr() and dst.stride() == src.stride()):
+            dst.copy_(src)
     ops, keep = [], []
     world = len(own)
     if dist is not None and world > 1:
@@ -127,11 +135,35 @@ class CudaBackend:
 # ------------------------------------------------------------------------------------------------
 # sharded topousm_fast
 # ------------------------------------------------------------------------------------------------
+def dem_halo_rows(H: int, world: int, rank: int, radii, pixel_size=1.0, backend=None) -> Tuple[int, int]:
+    """Global rows [lo, hi) of the DEM the fused pass of `rank` reads (own band + mirrored halo)."""
+    backend = backend or CudaBackend()
+    plan = backend.plan(radii, pixel_size)
+    kinds, sizes = plan["kind"], plan["size"]
+    halo = plan["fused_halo"]
+    for i in range(len(kinds)):
+        if kinds[i] == 2:
+            halo = max(halo, 4 if sizes[i] == 0 else sizes[i] // 2)
+    a, b = band_bounds(H, world)[rank]
+    return mirror_need(a - halo, b - 1 + halo, H, reflect=True) if b > a else (0, 0)
+
+
+def haloed_band(H: int, W: int, world: int, rank: int, radii, pixel_size=1.0, device="cuda", backend=None):
+    """(ext, band): `ext` holds the rows dem_halo_rows() names, `band` is the view of this rank's own rows inside
+    it.  A loader that writes its rows into `band` and passes `dem_ext=ext` to topousm_fast_sharded spares the
+    per-call copy of the band into a halo buffer (2 x band bytes of HBM traffic per step)."""
+    lo, hi = dem_halo_rows(H, world, rank, radii, pixel_size, backend)
+    a, b = band_bounds(H, world)[rank]
+    ext = torch.empty((hi - lo, W), dtype=torch.float32, device=device)
+    return ext, ext[a - lo:b - lo]
+
+
 def topousm_fast_sharded(band: torch.Tensor, H: int, rank: int, world: int, *, radii, weights=None, pixel_size=1.0,
                          norm_scale=None, output_dtype="float32", qp=None, dist=None, backend=None,
-                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                         out: Optional[torch.Tensor] = None, dem_ext: Optional[torch.Tensor] = None) -> torch.Tensor:
     """`band` = this rank's rows band_bounds(H, world)[rank] of the H x W raster (f32, NaN = NoData).
-    Returns the same rows of the topousm_fast result (normalised by norm_scale when given)."""
+    Returns the same rows of the topousm_fast result (normalised by norm_scale when given).
+    dem_ext: optional halo buffer from haloed_band() that already contains `band` (no copy of the own rows)."""
     backend = backend or CudaBackend()
     W = int(band.shape[1])
     own = band_bounds(H, world)
@@ -153,7 +185,7 @@ def topousm_fast_sharded(band: torch.Tensor, H: int, rank: int, world: int, *, r
             dem_need.append((lo, hi))
         else:
             dem_need.append((0, 0))
-    dem_ext = exchange_rows(band, own, dem_need, rank, dist)
+    dem_ext = exchange_rows(band, own, dem_need, rank, dist, out=dem_ext)
     dem_row0 = dem_need[rank][0]
 
     # ---- 2. pyramid levels of the own rows, halo rows of each level, coarse means
@@ -234,12 +266,17 @@ def distributed_percentile(chunks, q: float, *, take_abs: bool, finite_only: boo
                            hist_fn=None, rank_info_fn=None, key_to_float=None) -> float:
     """np.percentile over the union of every rank's `chunks`; all ranks return the same float.
     Exact: 3-level radix select on order-preserving keys, histograms summed with all_reduce."""
+    multi = dist is not None and dist.is_initialized() and dist.get_world_size() > 1
     if hist_fn is None:
+        # product path: the selection state stays on the device, the host only enqueues the stages and the
+        # all-reduces of the exchange area (one host synchronisation per percentile instead of six)
         from .. import kernels as k
-        hist_fn = lambda lvl, pre, msk: k.key_histogram(chunks, lvl, pre, msk, take_abs=take_abs,
-                                                        finite_only=finite_only, device=device)
-        rank_info_fn = lambda key: k.key_rank_info(chunks, key, take_abs=take_abs, finite_only=finite_only, device=device)
-        key_to_float = lambda key: k.key_to_float(key, take_abs)
+
+        def all_reduce(t, op):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MIN)
+
+        return k.staged_percentile(chunks, q, take_abs=take_abs, finite_only=finite_only, device=device,
+                                   all_reduce=all_reduce if multi else None)
 
     def allsum(t):
         if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
@@ -366,13 +403,15 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
     H = W = S
     own = band_bounds(H, world)
     r0, r1 = own[rank]
-    band = k.synth_dem((r1 - r0, W), seed=20261017 + 2, device=dev, row0=r0, h_global=H)
+    ext, band = haloed_band(H, W, world, rank, radii, device=dev)   # the band lives inside its halo buffer
+    k.synth_dem((r1 - r0, W), seed=20261017 + 2, device=dev, row0=r0, h_global=H, out=band)
     out = torch.empty((r1 - r0, W), dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
 
     def step():
         scale = sharded_topousm_scale(band, H, rank, world, radii=radii, weights=weights, dist=dist)
-        topousm_fast_sharded(band, H, rank, world, radii=radii, weights=weights, norm_scale=scale, dist=dist, out=out)
+        topousm_fast_sharded(band, H, rank, world, radii=radii, weights=weights, norm_scale=scale, dist=dist, out=out,
+                             dem_ext=ext)
         return scale
 
     for _ in range(a.warmup):
@@ -405,7 +444,8 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
     m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     m0.record()
     for _ in range(a.steps):
-        topousm_fast_sharded(band, H, rank, world, radii=radii, weights=weights, norm_scale=scale, dist=dist, out=out)
+        topousm_fast_sharded(band, H, rank, world, radii=radii, weights=weights, norm_scale=scale, dist=dist, out=out,
+                             dem_ext=ext)
     m1.record()
     torch.cuda.synchronize()
     mm = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device=dev)
@@ -417,14 +457,14 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
     hin = torch.empty((r1 - r0, W), dtype=torch.float32, pin_memory=True)
     hin.copy_(band)
     hout = torch.empty((r1 - r0, W), dtype=torch.uint8, pin_memory=True)
-    dband = torch.empty_like(band)
+    dext, dband = haloed_band(H, W, world, rank, radii, device=dev)
     out8 = torch.empty((r1 - r0, W), dtype=torch.uint8, device=dev)
 
     def e2e_step():
         dband.copy_(hin, non_blocking=True)
         sc = sharded_topousm_scale(dband, H, rank, world, radii=radii, weights=weights, dist=dist)
         topousm_fast_sharded(dband, H, rank, world, radii=radii, weights=weights, norm_scale=sc, dist=dist,
-                             output_dtype="uint8", qp=qp, out=out8)
+                             output_dtype="uint8", qp=qp, out=out8, dem_ext=dext)
         hout.copy_(out8, non_blocking=True)
         torch.cuda.synchronize()
 

@@ -265,6 +265,161 @@ __global__ void __launch_bounds__(256) count_chunks_kernel(Chunks c, int finite_
   }
 }
 
+// ---- device-staged selection (multi-GPU): the selection state never leaves the device ----------------
+// Exchange area `x` (int64, all-reduced by the host layer between the stages, stream-ordered):
+//   x[0..2047] histogram of the current radix level (SUM), x[2048] sample count (SUM, level 0),
+//   x[2049] #keys <= key_k (SUM), x[2050] smallest key > key_k (MIN)
+constexpr int SEL_X_COUNT = 2048, SEL_X_LE = 2049, SEL_X_NEXT = 2050, SEL_X_WORDS = 2056;
+
+__global__ void sel_begin_kernel(SelState* st, unsigned long long* x) {
+  for (int i = threadIdx.x; i < SEL_X_WORDS; i += blockDim.x) x[i] = i == SEL_X_NEXT ? 0xffffffffull : 0ull;
+  if (threadIdx.x == 0) {
+    memset(st, 0, sizeof(SelState));
+    st->key_next = 0xffffffffu;
+  }
+}
+
+__global__ void __launch_bounds__(256) sel_hist_kernel(Chunks c, int level, int take_abs, int finite_only,
+                                                       const SelState* st, unsigned long long* x) {
+  __shared__ unsigned int sh[2048];
+  for (int i = threadIdx.x; i < 2048; i += 256) sh[i] = 0;
+  __syncthreads();
+  if (level > 0 && st->n == 0) return;
+  const unsigned int prefix = level ? st->prefix : 0u, mask = level ? st->mask : 0u;
+  const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
+  const unsigned int bins_mask = level == 2 ? 1023u : 2047u;
+  unsigned long long local = 0;
+  scan_chunks(c, [&](float v, bool in) {
+    unsigned int key = 0;
+    const bool ok = in && sample_key(v, take_abs, finite_only, &key);
+    local += ok;
+    hist_add(sh, (key >> shift) & bins_mask, ok && (key & mask) == prefix);
+  });
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += 256)
+    if (sh[i]) atomicAdd(&x[i], (unsigned long long)sh[i]);
+  if (level == 0) {
+    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&x[SEL_X_COUNT], local);
+  }
+}
+
+// One warp: picks the bucket of the (all-reduced) histogram that holds the wanted rank and clears the
+// histogram for the next level.  Level 0 also derives the rank from the percentile the way NumPy does for an
+// f32 sample: virtual index (n-1)*f32(q/100) evaluated in f32, rank = floor (np.percentile, method 'linear').
+__global__ void sel_pick_kernel(int level, float q32, SelState* st, unsigned long long* x) {
+  const int lane = threadIdx.x & 31;
+  if (level == 0) {
+    if (lane == 0) {
+      st->n = x[SEL_X_COUNT];
+      st->prefix = 0; st->mask = 0;
+      if (st->n) {
+        const float vi = __fmul_rn(__ull2float_rn(st->n - 1ull), q32);
+        long long k = (long long)floorf(vi);
+        if (k < 0) k = 0;
+        if ((unsigned long long)k > st->n - 1ull) k = (long long)(st->n - 1ull);
+        st->rank = (unsigned long long)k;
+        st->out[2] = (double)k;
+      }
+    }
+    __syncwarp();
+  }
+  if (st->n == 0) {
+    for (int i = lane; i < 2048; i += 32) x[i] = 0ull;
+    return;
+  }
+  const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
+  const int bins = level == 2 ? 1024 : 2048;
+  const int per = bins / 32;
+  unsigned long long mine = 0;
+  for (int i = 0; i < per; ++i) mine += x[lane * per + i];
+  unsigned long long incl = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const unsigned long long excl = incl - mine;
+  const unsigned long long r = st->rank;
+  const bool holds = r >= excl && r < incl;
+  unsigned int ballot = __ballot_sync(0xffffffffu, holds);
+  int owner = ballot ? __ffs(ballot) - 1 : 31;   // rank beyond the total (cannot happen): last bucket
+  __syncwarp();
+  if (lane == owner) {
+    unsigned long long rr = r - excl;
+    int b = lane * per;
+    const int bend = b + per;
+    for (; b < bend; ++b) {
+      const unsigned long long h = x[b];
+      if (rr < h) break;
+      rr -= h;
+    }
+    if (b >= bend) { b = bend - 1; rr = 0; }
+    st->rank = rr;
+    st->prefix |= ((unsigned int)b) << shift;
+    st->mask |= ((unsigned int)(bins - 1)) << shift;
+    if (level == 2) st->key_k = st->prefix;
+  }
+  __syncwarp();
+  for (int i = lane; i < 2048; i += 32) x[i] = 0ull;
+}
+
+__global__ void __launch_bounds__(256) sel_next_kernel(Chunks c, int take_abs, int finite_only, const SelState* st,
+                                                       unsigned long long* x) {
+  if (st->n == 0) return;
+  const unsigned int kk = st->key_k;
+  unsigned long long le = 0;
+  unsigned int mn = 0xffffffffu;
+  scan_chunks(c, [&](float v, bool in) {
+    unsigned int key = 0;
+    if (in && sample_key(v, take_abs, finite_only, &key)) {
+      if (key <= kk) ++le;
+      else if (key < mn) mn = key;
+    }
+  });
+  for (int o = 16; o; o >>= 1) {
+    le += __shfl_down_sync(0xffffffffu, le, o);
+    unsigned int other = __shfl_down_sync(0xffffffffu, mn, o);
+    mn = other < mn ? other : mn;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (le) atomicAdd(&x[SEL_X_LE], le);
+    atomicMin(&x[SEL_X_NEXT], (unsigned long long)mn);
+  }
+}
+
+__global__ void sel_finish_kernel(const SelState* st, const unsigned long long* x, int take_abs, double* result) {
+  if (threadIdx.x != 0) return;
+  if (st->n == 0) {
+    result[0] = nan(""); result[1] = nan(""); result[2] = 0.0; result[3] = 0.0;
+    return;
+  }
+  const unsigned long long k = (unsigned long long)st->out[2];
+  const float ak = key_value(st->key_k, take_abs);
+  float ak1 = ak;
+  if (k + 1 < st->n && x[SEL_X_LE] < k + 2) ak1 = key_value((unsigned int)x[SEL_X_NEXT], take_abs);
+  result[0] = (double)ak;
+  result[1] = (double)ak1;
+  result[2] = st->out[2];
+  result[3] = (double)st->n;
+}
+
+static int fill_chunks(Chunks& c, const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                       const int64_t* ld_host, int n_chunks, int64_t* total) {
+  c.n = n_chunks;
+  int64_t tot = 0;
+  for (int i = 0; i < n_chunks; ++i) {
+    if (!chunks_host[i] || rows_host[i] < 0 || cols_host[i] < 0 || ld_host[i] < cols_host[i]) return -1;
+    c.ptr[i] = chunks_host[i]; c.rows[i] = rows_host[i]; c.cols[i] = cols_host[i]; c.ld[i] = ld_host[i];
+    c.start[i] = tot;
+    c.rowstart[i] = i == 0 ? 0 : c.rowstart[i - 1] + rows_host[i - 1] * ((cols_host[i - 1] + SCAN_TILE - 1) / SCAN_TILE);
+    tot += rows_host[i] * cols_host[i];
+  }
+  c.start[n_chunks] = tot;
+  c.rowstart[n_chunks] = n_chunks ? c.rowstart[n_chunks - 1] + rows_host[n_chunks - 1] * ((cols_host[n_chunks - 1] + SCAN_TILE - 1) / SCAN_TILE) : 0;
+  *total = tot;
+  return 0;
+}
+
 }  // namespace fsg
 
 extern "C" {
@@ -408,6 +563,76 @@ int fsg_count_samples(const float* const* chunks_host, const int64_t* rows_host,
   int64_t blocks = c.rowstart[n_chunks];
   if (blocks > 148 * 16) blocks = 148 * 16;
   count_chunks_kernel<<<(int)blocks, 256, 0, s>>>(c, finite_only, (unsigned long long*)counts_dev);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+/* ---- device-staged selection: same radix select, but the state stays on the device and the host layer only
+ * enqueues kernels and all-reduces of the exchange area (no host round trip between the levels).
+ * workspace: fsg_select_workspace_bytes() bytes, 8-byte aligned; the exchange area is its first
+ * fsg_select_exchange_words() int64 words (see SEL_X_* above). */
+size_t fsg_select_exchange_words(void) { return fsg::SEL_X_WORDS; }
+size_t fsg_select_workspace_bytes(void) { return fsg::SEL_X_WORDS * 8 + sizeof(fsg::SelState) + 64; }
+
+static fsg::SelState* sel_state(void* ws) { return (fsg::SelState*)((unsigned char*)ws + fsg::SEL_X_WORDS * 8); }
+
+int fsg_select_begin(void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace fsg;
+  if (!workspace || workspace_bytes < fsg_select_workspace_bytes() || ((uintptr_t)workspace & 7))
+    return fail(FSG_E_WORKSPACE, "fsg_select_begin: workspace too small or misaligned");
+  sel_begin_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sel_state(workspace), (unsigned long long*)workspace);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_select_hist(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                    const int64_t* ld_host, int n_chunks, int level, int take_abs, int finite_only, void* workspace,
+                    void* stream) {
+  using namespace fsg;
+  if (n_chunks < 0 || n_chunks > MAX_CHUNKS || level < 0 || level > 2 || !workspace)
+    return fail(FSG_E_INVALID, "fsg_select_hist: bad argument");
+  if (n_chunks == 0) return FSG_OK;
+  Chunks c{};
+  int64_t tot = 0;
+  if (fill_chunks(c, chunks_host, rows_host, cols_host, ld_host, n_chunks, &tot)) return fail(FSG_E_INVALID, "fsg_select_hist: bad chunk");
+  if (tot == 0) return FSG_OK;
+  int blocks = (int)((tot + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sel_hist_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(c, level, take_abs, finite_only, sel_state(workspace),
+                                                            (unsigned long long*)workspace);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_select_pick(int level, float q32, void* workspace, void* stream) {
+  using namespace fsg;
+  if (level < 0 || level > 2 || !workspace) return fail(FSG_E_INVALID, "fsg_select_pick: bad argument");
+  sel_pick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(level, q32, sel_state(workspace), (unsigned long long*)workspace);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_select_next(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                    const int64_t* ld_host, int n_chunks, int take_abs, int finite_only, void* workspace, void* stream) {
+  using namespace fsg;
+  if (n_chunks < 0 || n_chunks > MAX_CHUNKS || !workspace) return fail(FSG_E_INVALID, "fsg_select_next: bad argument");
+  if (n_chunks == 0) return FSG_OK;
+  Chunks c{};
+  int64_t tot = 0;
+  if (fill_chunks(c, chunks_host, rows_host, cols_host, ld_host, n_chunks, &tot)) return fail(FSG_E_INVALID, "fsg_select_next: bad chunk");
+  if (tot == 0) return FSG_OK;
+  int blocks = (int)((tot + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sel_next_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(c, take_abs, finite_only, sel_state(workspace),
+                                                            (unsigned long long*)workspace);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_select_finish(void* workspace, int take_abs, double* result_dev, void* stream) {
+  using namespace fsg;
+  if (!workspace || !result_dev) return fail(FSG_E_INVALID, "fsg_select_finish: bad argument");
+  sel_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sel_state(workspace), (const unsigned long long*)workspace, take_abs, result_dev);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }

@@ -323,6 +323,15 @@ def count_samples(chunks: Sequence, *, finite_only: bool = True):
 
 def percentile(chunks: Sequence, q: float, *, take_abs=False, finite_only=False) -> float:
     """np.percentile(sample, q) for an f32 sample (method 'linear'); NaN when the sample is empty.
+    One pass structure: device-staged radix select (4 scans of the sample, one host synchronisation)."""
+    views = _pooled_views(chunks)
+    if not views:
+        return float("nan")
+    return staged_percentile(views, q, take_abs=take_abs, finite_only=finite_only, device=views[0].device)
+
+
+def percentile_two_pass(chunks: Sequence, q: float, *, take_abs=False, finite_only=False) -> float:
+    """Same result through fsg_order_stats (count first, then a[k], a[k+1]): the host derives the rank.
     Index and interpolation arithmetic are NumPy's own f32 scalar ops
     (numpy/lib/_function_base_impl.py: percentile -> _quantile -> _lerp)."""
     views = _pooled_views(chunks)
@@ -485,3 +494,45 @@ def key_rank_info(chunks, key: int, *, take_abs: bool, finite_only: bool, device
 
 def key_to_float(key: int, take_abs: bool) -> float:
     return float(_lib.load().fsg_key_to_float(int(key), 1 if take_abs else 0))
+
+
+def staged_percentile(chunks, q: float, *, take_abs: bool, finite_only: bool, device, all_reduce=None) -> float:
+    """np.percentile(sample, q) (method 'linear', f32 sample) of the union of every rank's chunks with the
+    selection state kept on the device: the host only enqueues the radix-select stages and, between them,
+    `all_reduce(tensor, op)` (op in {"sum", "min"}) of the exchange area -- no host round trip until the
+    4-double result is read.  all_reduce=None: single device.  (reference: _normalization.py:22-32)"""
+    lib = _lib.load()
+    views = _pooled_views(chunks) if chunks else []
+    nx = int(lib.fsg_select_exchange_words())
+    ws = torch.empty((int(lib.fsg_select_workspace_bytes()) + 7) // 8, dtype=torch.int64, device=device)
+    res = torch.empty(4, dtype=torch.float64, device=device)
+    stream = C.c_void_p(int(torch.cuda.current_stream(device).cuda_stream))
+    ptrs, rows, cols, lds = _chunk_args(views)
+    ta, fo = 1 if take_abs else 0, 1 if finite_only else 0
+    q32 = np.true_divide(q, np.float32(100))       # NumPy's own f32 quantile (python float / f32 -> f32)
+    check(lib.fsg_select_begin(_ptr(ws), ws.numel() * 8, stream), "fsg_select_begin")
+    for level in range(3):
+        check(lib.fsg_select_hist(ptrs, rows, cols, lds, len(views), level, ta, fo, _ptr(ws), stream), "fsg_select_hist")
+        if all_reduce is not None:
+            all_reduce(ws[:2049], "sum")
+        check(lib.fsg_select_pick(level, float(q32), _ptr(ws), stream), "fsg_select_pick")
+    check(lib.fsg_select_next(ptrs, rows, cols, lds, len(views), ta, fo, _ptr(ws), stream), "fsg_select_next")
+    if all_reduce is not None:
+        all_reduce(ws[2049:2050], "sum")
+        all_reduce(ws[2050:2051], "min")
+    check(lib.fsg_select_finish(_ptr(ws), ta, _ptr(res), stream), "fsg_select_finish")
+    a_k, a_k1, rank_dev, n = [float(v) for v in res.cpu().tolist()]   # the only host synchronisation
+    n = int(n)
+    if n == 0:
+        return float("nan")
+    vi = (n - 1) * q32
+    prev = min(max(int(np.floor(vi)), 0), n - 1)
+    if prev != int(rank_dev):
+        raise _lib.FsgError(f"staged_percentile: device rank {int(rank_dev)} != NumPy rank {prev} (n={n}, q={q})")
+    gamma = np.asanyarray(vi - np.floor(vi), dtype=np.asanyarray(vi).dtype)[()]
+    a_k, a_k1 = np.float32(a_k), np.float32(a_k1)
+    diff = a_k1 - a_k
+    out = a_k + diff * gamma
+    if gamma >= 0.5:
+        out = a_k1 - diff * (1 - gamma)
+    return float(out)

@@ -235,6 +235,25 @@ int fsg_key_rank_info(const float* const* chunks_host, const int64_t* rows_host,
                       uint64_t* out_dev, void* stream);
 float fsg_key_to_float(uint32_t key, int take_abs);
 
+/* Device-staged variant of the same selection: the state stays on the device; between the stages the host
+ * layer all-reduces the exchange area (the first fsg_select_exchange_words() int64 words of the workspace:
+ * [0..2047] level histogram and [2048] sample count with SUM, [2049] #keys <= key with SUM, [2050] next key
+ * with MIN) in stream order, so a percentile costs no host round trip until the 4-double result is read.
+ * Stages: begin; for level 0..2 { hist; all-reduce x[0..2048]; pick }; next; all-reduce x[2049] (SUM),
+ * x[2050] (MIN); finish.  q32 = f32(q)/f32(100): the rank is derived on the device with NumPy's f32
+ * virtual-index arithmetic (np.percentile, method 'linear'; reference _normalization.py:22-32). */
+size_t fsg_select_exchange_words(void);
+size_t fsg_select_workspace_bytes(void);
+int fsg_select_begin(void* workspace, size_t workspace_bytes, void* stream);
+int fsg_select_hist(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                    const int64_t* ld_host, int n_chunks, int level, int take_abs, int finite_only, void* workspace,
+                    void* stream);
+int fsg_select_pick(int level, float q32, void* workspace, void* stream);
+int fsg_select_next(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                    const int64_t* ld_host, int n_chunks, int take_abs, int finite_only, void* workspace, void* stream);
+int fsg_select_finish(void* workspace, int take_abs, double* result_dev, void* stream);
+
+
 /* synthetic DEM generator used by bench/tests: eight sinusoid octaves +
  * hash noise, optional NoData wedge/ellipses; rows [row0,row0+rows) of an H x W raster. */
 int fsg_synth_dem(float* out, int64_t H, int64_t W, int64_t row0, int64_t rows, int64_t ld,

@@ -323,6 +323,36 @@ def test_stats_percentile_matches_numpy():
     assert topousm_fast_stat_func(_cuda(data))[0] == pytest.approx(0.5, rel=1e-2)
 
 
+def test_staged_percentile_matches_numpy_and_two_pass():
+    """Device-staged radix select (rank derived on the device with NumPy's f32 virtual-index arithmetic) ==
+    np.percentile on the f32 sample == the host-ranked two-pass selection; empty, single, tied and signed samples."""
+    from fujishadergpu_b200 import kernels as k
+    rng = np.random.default_rng(12)
+    cases = []
+    for n in (1, 2, 3, 101, 4097, 250_001):
+        a = (rng.standard_normal(n) * 50).astype(np.float32)
+        cases.append(a)
+    tied = np.repeat(np.float32([0.5, -0.5, 0.25, 7.0]), 1000)
+    cases.append(tied)
+    withnan = (rng.standard_normal(20_000) * 3).astype(np.float32)
+    withnan[rng.random(withnan.shape) < 0.3] = np.nan
+    withnan[5] = np.inf
+    cases.append(withnan)
+    for a in cases:
+        t = _cuda(a.reshape(1, -1))
+        for q in (0.0, 1.0, 50.0, 99.0, 100.0):
+            for take_abs, finite_only in ((True, False), (False, True)):
+                sample = a[np.isfinite(a)] if finite_only else a[~np.isnan(a)]
+                sample = np.abs(sample) if take_abs else sample
+                want = float(np.percentile(sample, q)) if sample.size else float("nan")
+                got = k.percentile([t], q, take_abs=take_abs, finite_only=finite_only)
+                old = k.percentile_two_pass([t], q, take_abs=take_abs, finite_only=finite_only)
+                assert (got == want) or (got != got and want != want), (a.size, q, take_abs, got, want)
+                assert (got == old) or (got != got and old != old), (a.size, q, take_abs, got, old)
+    allnan = _cuda(np.full((4, 9), np.nan, np.float32))
+    assert k.percentile([allnan], 99.0, take_abs=True) != k.percentile([allnan], 99.0, take_abs=True)   # NaN
+
+
 def test_openness_vs_reference_golden(golden, manifest):
     from fujishadergpu_b200.algorithms._impl_openness import compute_openness_vectorized, compute_openness_spatial_block
     from fujishadergpu_b200.algorithms._global_stats import _apply_display_stretch_block

@@ -132,7 +132,7 @@ def _numpy_select_fns(pooled):
     return dict(hist_fn=hist_fn, rank_info_fn=rank_info_fn, key_to_float=key_to_float)
 
 
-def _worker(rank, world, port, dem_path, out_dir, radii, weights, with_stats):
+def _worker(rank, world, port, dem_path, out_dir, radii, weights, with_stats, haloed=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -142,12 +142,19 @@ def _worker(rank, world, port, dem_path, out_dir, radii, weights, with_stats):
     r0, r1 = sh.band_bounds(H, world)[rank]
     band = torch.from_numpy(np.ascontiguousarray(dem[r0:r1]))
     be = NumpyBackend()
+    ext = None
+    if haloed:   # the band lives inside its halo buffer: only the halo rows are exchanged, nothing is copied
+        ext, view = sh.haloed_band(H, dem.shape[1], world, rank, radii, device="cpu", backend=be)
+        ext.fill_(float("nan"))
+        view.copy_(band)
+        band = view
     scale = None
     if with_stats:
         scale = sh.sharded_topousm_scale(band, H, rank, world, radii=radii, weights=weights, dist=dist,
                                          block_fn=lambda a: torch.from_numpy(orc.topousm_fast_block(a.numpy(), radii=radii, weights=weights)),
                                          select_fns=_numpy_select_fns)
-    out = sh.topousm_fast_sharded(band, H, rank, world, radii=radii, weights=weights, norm_scale=scale, dist=dist, backend=be)
+    out = sh.topousm_fast_sharded(band, H, rank, world, radii=radii, weights=weights, norm_scale=scale, dist=dist, backend=be,
+                                  dem_ext=ext)
     np.save(os.path.join(out_dir, f"out_{rank}.npy"), out.numpy())
     if rank == 0 and with_stats:
         np.save(os.path.join(out_dir, "scale.npy"), np.array([scale if scale is not None else np.nan]))
@@ -155,13 +162,13 @@ def _worker(rank, world, port, dem_path, out_dir, radii, weights, with_stats):
     dist.destroy_process_group()
 
 
-def _run(world, dem, radii, weights, with_stats=False):
+def _run(world, dem, radii, weights, with_stats=False, haloed=False):
     import torch.multiprocessing as mp
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "dem.npy")
         np.save(path, dem)
         port = 29500 + (os.getpid() * 7 + world * 13 + dem.shape[0]) % 2000
-        mp.spawn(_worker, args=(world, port, path, td, radii, weights, with_stats), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, path, td, radii, weights, with_stats, haloed), nprocs=world, join=True)
         outs = [np.load(os.path.join(td, f"out_{r}.npy")) for r in range(world)]
         scale = float(np.load(os.path.join(td, "scale.npy"))[0]) if with_stats else None
     return np.concatenate(outs, axis=0), scale
@@ -194,6 +201,9 @@ def test_sharded_topousm_equals_single_block_oracle(world):
     want = orc.topousm_fast_block(dem, radii=radii, weights=w)
     assert got.shape == want.shape
     assert np.array_equal(got, want, equal_nan=True), float(np.nanmax(np.abs(got - want)))
+    if world == 3:
+        got2, _ = _run(world, dem, radii, w, haloed=True)
+        assert np.array_equal(got2, want, equal_nan=True)
 
 
 def test_sharded_topousm_nodata_void_fill_and_stats():
