@@ -55,6 +55,10 @@ _SIGNATURES = {
                                     _D, C.POINTER(Encode), _P]),
     "fsg_topousm_large_part": (_I, [_P, _P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _L, _L, _L, _D, _P]),
     "fsg_openness": (_I, [_P, _P, C.POINTER(Window), _I, _I, _I, _D, _D, _D, _D, _D, C.POINTER(Encode), _P]),
+    "fsg_ambient_occlusion_workspace_bytes": (C.c_size_t, [_L, _L]),
+    "fsg_ambient_occlusion": (_I, [_P, _P, _L, _L, _L, _L, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_float), C.POINTER(C.c_float), _D, _D, _D, C.POINTER(Encode), _P,
+                                   C.c_size_t, _P]),
     "fsg_decimate_workspace_bytes": (C.c_size_t, [_L, _L, _I]),
     "fsg_decimate": (_I, [_P, _P, _L, _L, _L, _I, _P, C.c_size_t, _P]),
     "fsg_upsample": (_I, [_P, _P, _L, _L, _L, _L, _P, C.c_size_t, _P]),

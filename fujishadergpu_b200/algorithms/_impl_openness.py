@@ -5,7 +5,9 @@ from .. import kernels as _k
 from .. import _device as _dev
 from ._base import DaskAlgorithm
 from ._global_stats import apply_display_stretch_dask, robust_unsigned_stretch_stat_func  # noqa: F401 (re-export)
-from ._nan_utils import _downsample_nan_aware, _radius_to_downsample_factor, _upsample_to_shape
+from ._nan_utils import (_combine_multiscale_dask, _downsample_nan_aware, _radius_to_downsample_factor,
+                         _resolve_spatial_radii_weights, _upsample_to_shape, large_radius_threshold,
+                         multiscale_response_fields)
 
 
 def compute_openness_vectorized(block, *, openness_type="positive", num_directions=16, max_distance=50,
@@ -35,8 +37,8 @@ def compute_openness_spatial_block(block, *, openness_type="positive", num_direc
 
 
 class OpennessAlgorithm(DaskAlgorithm):
-    """reference :167-227.  local: the full-resolution block function; spatial: one decimated run per
-    radius (a single radius is supported on the B200 path; the weighted multi-radius mix is 8f-next)."""
+    """reference :167-227.  local: the full-resolution block function; spatial: one (decimated) run per radius,
+    radii above the large-radius threshold on a coarsened DEM, responses mixed by _combine_multiscale_dask."""
 
     def process(self, gpu_arr, **params):
         kw = dict(openness_type=params.get("openness_type", "positive"),
@@ -44,11 +46,19 @@ class OpennessAlgorithm(DaskAlgorithm):
                   pixel_scale_x=params.get("pixel_scale_x"), pixel_scale_y=params.get("pixel_scale_y"))
         mode = str(params.get("mode", "local")).lower()
         if mode == "spatial":
-            radii = params.get("radii") or [params.get("max_distance", 50)]
-            if len(radii) != 1:
-                raise NotImplementedError("openness --mode spatial: exactly one radius is supported on the B200 path")
-            md = float(int(max(2, round(float(radii[0])))))
-            result = compute_openness_spatial_block(gpu_arr, max_distance=md, **kw)
+            if hasattr(gpu_arr, "map_overlap"):
+                raise NotImplementedError("openness: spatial mode takes a device block, not a dask array, on the B200 path")
+            radii, weights = _resolve_spatial_radii_weights(params.get("radii"), params.get("weights", None),
+                                                            kw["pixel_size"])
+            thr = large_radius_threshold(gpu_arr, fallback=max(radii) if radii else 64)
+            responses = multiscale_response_fields(
+                gpu_arr, [float(int(max(2, round(float(r))))) for r in radii],
+                block_fn=compute_openness_spatial_block, radius_kw="max_distance",
+                depth_for_scale=lambda md: int(md) + 1, is_large=lambda md: int(md) > thr,
+                pixel_size=kw["pixel_size"], pixel_scale_x=kw["pixel_scale_x"], pixel_scale_y=kw["pixel_scale_y"],
+                coarse_dem=params.get("_overview_coarse_dem"), coarse_decimation=params.get("_overview_decimation"),
+                openness_type=kw["openness_type"], num_directions=kw["num_directions"])
+            result = _combine_multiscale_dask(responses, weights=weights, agg=params.get("agg", "mean"))
         elif hasattr(gpu_arr, "map_overlap"):
             md = params.get("max_distance", 50)
             result = gpu_arr.map_overlap(compute_openness_vectorized, depth=md + 1, boundary="reflect",

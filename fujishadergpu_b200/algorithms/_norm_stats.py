@@ -16,6 +16,7 @@ logger = logging.getLogger(__name__)
 _NORM_STAT_SPECS = {
     "topousm_fast": ("_impl_topousm_fast", "compute_topousm_fast_efficient_block", "topousm_fast_stat_func"),
     "openness": ("_impl_openness", "compute_openness_vectorized", "robust_unsigned_stretch_stat_func"),
+    "ambient_occlusion": ("_impl_ambient_occlusion", "compute_ambient_occlusion_block", "robust_unsigned_stretch_stat_func"),
 }
 
 

@@ -82,6 +82,14 @@ def _direct_openness(block, p):
         stretch=p.get("global_stats")), block)
 
 
+def _direct_ambient_occlusion(block, p):
+    # reference :190-206; display stretch fused into the kernel epilogue
+    return _dev.like_input(_k.ambient_occlusion(
+        block, num_samples=p.get("num_samples", 16), radius=p.get("radius", 10.0), intensity=p.get("intensity", 1.0),
+        pixel_size=p.get("pixel_size", 1.0), pixel_scale_x=p.get("pixel_scale_x"), pixel_scale_y=p.get("pixel_scale_y"),
+        stretch=p.get("global_stats")), block)
+
+
 def _direct_topousm_fast(block, p, algo):
     """reference :225-271 -- raw + normalisation fused when global_stats is present."""
     stats = p.get("global_stats")
@@ -98,6 +106,7 @@ def _direct_topousm_fast(block, p, algo):
 _DIRECT = {
     "HillshadeAlgorithm": _direct_hillshade, "SlopeAlgorithm": _direct_slope,
     "CurvatureAlgorithm": _direct_curvature, "OpennessAlgorithm": _direct_openness,
+    "AmbientOcclusionAlgorithm": _direct_ambient_occlusion,
 }
 
 

@@ -19,8 +19,9 @@ _TORCH_DT = {"float32": torch.float32, "int16": torch.int16, "uint8": torch.uint
 DEFAULT_ALGORITHMS = {
     "topousm_fast": "TopoUSMFastAlgorithm", "hillshade": "HillshadeAlgorithm", "slope": "SlopeAlgorithm",
     "curvature": "CurvatureAlgorithm", "openness": "OpennessAlgorithm",
+    "ambient_occlusion": "AmbientOcclusionAlgorithm",
 }
-SPATIAL_TILE_ALGORITHMS = {"hillshade", "slope", "curvature", "openness"}
+SPATIAL_TILE_ALGORITHMS = {"hillshade", "slope", "curvature", "openness", "ambient_occlusion"}
 
 
 def _required_padding_for_algorithm(algorithm: str, algo_params: dict, sigma: float, pixel_size: float,
@@ -59,7 +60,7 @@ def _required_padding_for_algorithm(algorithm: str, algo_params: dict, sigma: fl
                 max_radius = max(int(round(r)) for r in radii_f)
         except Exception:
             max_radius = 32
-        if algorithm == "openness":
+        if algorithm in {"ambient_occlusion", "openness"}:
             required = max(required, int(max_radius + 16))
         else:
             required = max(required, int(max_radius * 2 + 2))
@@ -106,9 +107,11 @@ class HostTilePipeline:
                             norm_scale=scale, output_dtype=self.output_dtype, qp=self.qp, workspace=self.workspace,
                             out=self.dev_out)
         else:
-            fn = {"hillshade": _k.hillshade, "slope": _k.slope, "curvature": _k.curvature, "openness": _k.openness}[algo]
+            fn = {"hillshade": _k.hillshade, "slope": _k.slope, "curvature": _k.curvature, "openness": _k.openness,
+                  "ambient_occlusion": _k.ambient_occlusion}[algo]
             keys = {"hillshade": ("azimuth", "altitude", "z_factor"), "slope": ("unit",), "curvature": ("curvature_type",),
-                    "openness": ("openness_type", "num_directions", "max_distance")}[algo]
+                    "openness": ("openness_type", "num_directions", "max_distance"),
+                    "ambient_occlusion": ("num_samples", "radius", "intensity")}[algo]
             kw = {k: p[k] for k in keys + ("pixel_size", "pixel_scale_x", "pixel_scale_y") if k in p}
             self.dev_out = fn(self.dev_in, output_dtype=self.output_dtype, qp=self.qp, **kw)
         for r in range(0, H, self.chunk_rows):

@@ -12,6 +12,7 @@ OUTPUT_VALUE_RANGES: Dict[str, Tuple[float, float]] = {
     "hillshade": (0.0, 1.0),
     "curvature": (0.0, 1.0),
     "openness": (0.0, 1.0),
+    "ambient_occlusion": (0.0, 1.0),
     "slope": (0.0, 90.0),
 }
 SUPPORTED_OUTPUT_DTYPES = ("float32", "int16", "uint8")

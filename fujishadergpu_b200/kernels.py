@@ -190,6 +190,60 @@ def openness(dem, *, openness_type="positive", num_directions=16, max_distance=5
     return out
 
 
+def ao_table(num_samples: int, radius: float, pixel_size=1.0, pixel_scale_x=None, pixel_scale_y=None):
+    """Ring-sample table of compute_ambient_occlusion_block, built with NumPy exactly as
+    algorithms/_impl_ambient_occlusion.py:52-88 does (host integers and Python floats only)."""
+    angles = np.linspace(0, 2 * np.pi, num_samples, endpoint=False)
+    directions = np.stack([np.cos(angles), np.sin(angles)], axis=1)
+    sx = abs(float(pixel_scale_x)) if pixel_scale_x is not None else float(pixel_size)
+    sy = abs(float(pixel_scale_y)) if pixel_scale_y is not None else float(pixel_size)
+    if sx < 1e-9:
+        sx = float(pixel_size) if pixel_size else 1.0
+    if sy < 1e-9:
+        sy = float(pixel_size) if pixel_size else 1.0
+    ox, oy, dist, fac = [], [], [], []
+    for r_factor in (0.25, 0.5, 0.75, 1.0):
+        r = radius * r_factor
+        dx_all = np.round(r * directions[:, 0]).astype(int)
+        dy_all = np.round(r * directions[:, 1]).astype(int)
+        for i in range(num_samples):
+            dx, dy = int(dx_all[i]), int(dy_all[i])
+            if dx == 0 and dy == 0:
+                continue
+            ox.append(dx)
+            oy.append(dy)
+            dist.append(max(float(np.hypot(float(dx) * sx, float(dy) * sy)), 1e-9))
+            fac.append(1.0 - (r_factor * 0.3))
+    return (np.asarray(ox, np.int32), np.asarray(oy, np.int32), np.asarray(dist, np.float32), np.asarray(fac, np.float32))
+
+
+def ambient_occlusion(dem, *, num_samples=16, radius=10.0, intensity=1.0, pixel_size=1.0, pixel_scale_x=None,
+                      pixel_scale_y=None, stretch=None, output_dtype="float32", qp=None) -> torch.Tensor:
+    """compute_ambient_occlusion_block (algorithms/_impl_ambient_occlusion.py:33-118) on one device block."""
+    t = dev.as_f32_2d(dem)
+    if int(num_samples) < 1 or int(num_samples) > 64:
+        raise ValueError("ambient_occlusion: num_samples must be 1..64")
+    ox, oy, dist, fac = ao_table(int(num_samples), float(radius), pixel_size, pixel_scale_x, pixel_scale_y)
+    n = len(ox)
+    if n == 0:  # keep pointers valid
+        ox = np.zeros(1, np.int32); oy = np.zeros(1, np.int32); dist = np.ones(1, np.float32); fac = np.ones(1, np.float32)
+    lib = _lib.load()
+    H, W = int(t.shape[0]), int(t.shape[1])
+    out = dev.empty_out(t, (H, W), output_dtype)
+    wsb = int(lib.fsg_ambient_occlusion_workspace_bytes(H, W))
+    ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=t.device)
+    lo, sc = (float("nan"), float("nan"))
+    if isinstance(stretch, (tuple, list)) and len(stretch) >= 2 and float(stretch[1]) > 1e-12:
+        lo, sc = float(stretch[0]), float(stretch[1])
+    enc = make_encode(output_dtype, qp)
+    i32, f32 = C.POINTER(C.c_int32), C.POINTER(C.c_float)
+    check(lib.fsg_ambient_occlusion(_ptr(t), _ptr(out), H, W, int(t.stride(0)), int(out.stride(0)), n,
+                                    ox.ctypes.data_as(i32), oy.ctypes.data_as(i32), dist.ctypes.data_as(f32),
+                                    fac.ctypes.data_as(f32), float(intensity), lo, sc, C.byref(enc), _ptr(ws),
+                                    ws.numel(), C.c_void_p(dev.stream_ptr(t))), "fsg_ambient_occlusion")
+    return out
+
+
 def decimate(dem, factor: int) -> torch.Tensor:
     t = dev.as_f32_2d(dem)
     f = int(factor)

@@ -181,6 +181,18 @@ int fsg_openness_samples(const float* dem, void* out, const fsg_window* win, int
                          const float* dist_host, double stretch_lo, double stretch_scale,
                          const fsg_encode* enc, void* stream);
 
+/* ---- ambient occlusion (algorithms/_impl_ambient_occlusion.py:33-118) --------------
+ * compute_ambient_occlusion_block on the whole H x W block: 4 rings x num_samples edge-replicated gathers,
+ * clip(1 - mean occlusion * intensity), sigma=1 Gaussian ('nearest'), power 1/2.2, NaN restore; optional
+ * display stretch (tile/dask_bridge.py:173-187) and integer encoding.  The sample table (offsets with the
+ * (0,0) entries dropped, f32 physical distance, f32 ring weight 1 - 0.3 k/4) is built by the host layer with
+ * NumPy exactly as the reference does (:52-88). */
+size_t fsg_ambient_occlusion_workspace_bytes(int64_t H, int64_t W);
+int fsg_ambient_occlusion(const float* dem, void* out, int64_t H, int64_t W, int64_t ld_in, int64_t ld_out,
+                          int n_samples, const int32_t* ox_host, const int32_t* oy_host, const float* dist_host,
+                          const float* factor_host, double intensity, double stretch_lo, double stretch_scale,
+                          const fsg_encode* enc, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- helpers ------------------------------------------------------------------------------
  * fsg_decimate      : _downsample_nan_aware incl. enclosed-void fill (needs workspace)
  * fsg_upsample      : _upsample_to_shape (plain and NaN-aware branch)

@@ -40,14 +40,52 @@ def _ref():
     return tf, hs, sl, cv, op, nu, nm, gs, sm, oe
 
 
-def main(out_dir: str) -> None:
-    tf, hs, sl, cv, op, nu, nm, gs, sm, oe = _ref()
+def ambient_occlusion_section(save) -> None:
+    """compute_ambient_occlusion_block / _spatial_block of the reference, through the shim."""
+    from FujiShaderGPU.algorithms import _impl_ambient_occlusion as ao
+    adense = synth_dem(160, 208, seed=20261031)
+    aholes = synth_dem(160, 208, seed=20261032, nodata=True)
+    aholes[50:54, 80:91] = np.nan
+    aholes[0, 100:103] = np.nan
+    arrays = {"adense": adense, "aholes": aholes}
+    params = {}
+    src = {"adense": adense, "aholes": aholes}
+    for cname, (key, kw) in {
+        "s16_r10": ("adense", dict(num_samples=16, radius=10.0, intensity=1.0)),
+        "s8_r3p5_i2": ("adense", dict(num_samples=8, radius=3.5, intensity=2.0)),
+        "s16_r24_northup": ("adense", dict(num_samples=16, radius=24.0, intensity=1.0, pixel_scale_x=1.0, pixel_scale_y=-1.0)),
+        "s16_r10_holes": ("aholes", dict(num_samples=16, radius=10.0, intensity=1.0)),
+        "s12_r6_holes_geo": ("aholes", dict(num_samples=12, radius=6.0, intensity=0.7, pixel_scale_x=23.7,
+                                            pixel_scale_y=-30.9, pixel_size=30.0)),
+    }.items():
+        arrays[f"local__{cname}"] = ao.compute_ambient_occlusion_block(src[key].copy(), **kw)
+        params[f"local__{cname}"] = dict(input=key, kw=kw)
+    for cname, (key, kw) in {
+        "s16_r64": ("adense", dict(num_samples=16, radius=64.0, intensity=1.0)),
+        "s8_r40_holes": ("aholes", dict(num_samples=8, radius=40.0, intensity=1.0)),
+    }.items():
+        arrays[f"spatial__{cname}"] = ao.compute_ambient_occlusion_spatial_block(src[key].copy(), **kw)
+        params[f"spatial__{cname}"] = dict(input=key, kw=kw)
+    save("ambient_occlusion", params, **arrays)
+
+
+def main(out_dir: str, only: str = "") -> None:
     os.makedirs(out_dir, exist_ok=True)
     manifest = {}
 
     def save(name, params, **arrays):
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **arrays)
         manifest[name] = params
+
+    if only == "ambient_occlusion":   # add one section to the committed fixtures without rewriting the others
+        with open(os.path.join(out_dir, "manifest.json")) as fh:
+            manifest.update(json.load(fh))
+        ambient_occlusion_section(save)
+        with open(os.path.join(out_dir, "manifest.json"), "w") as fh:
+            json.dump(manifest, fh, indent=1, sort_keys=True, default=lambda o: o.tolist() if hasattr(o, "tolist") else str(o))
+        return
+    tf, hs, sl, cv, op, nu, nm, gs, sm, oe = _ref()
+    ambient_occlusion_section(save)
 
     # ---------------- gradient family ----------------
     dense = synth_dem(128, 176, seed=20261017)
@@ -251,4 +289,4 @@ def main(out_dir: str) -> None:
 
 
 if __name__ == "__main__":
-    main(os.path.join(ROOT, "tests", "golden"))
+    main(os.path.join(ROOT, "tests", "golden"), only=(sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else ""))

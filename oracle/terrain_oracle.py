@@ -731,6 +731,78 @@ def openness_spatial_block(dem, *, openness_type="positive", num_directions=16, 
     return upsample_align_corners(rs, dem.shape)
 
 
+def ambient_occlusion_table(num_samples: int, radius: float):
+    """Ring sample offsets ``[(ring factor, dx, dy), ...]`` in the reference's loop order and the pad depth D
+    (algorithms/_impl_ambient_occlusion.py:52-80): np.round offsets, the (0, 0) ones skipped."""
+    angles = np.linspace(0, 2 * np.pi, num_samples, endpoint=False)
+    directions = np.stack([np.cos(angles), np.sin(angles)], axis=1)
+    D = max(1, int(round(float(radius))))
+    offs = []
+    for r_factor in (0.25, 0.5, 0.75, 1.0):
+        r = radius * r_factor
+        dx_all = np.round(r * directions[:, 0]).astype(int)
+        dy_all = np.round(r * directions[:, 1]).astype(int)
+        for i in range(num_samples):
+            dx, dy = int(dx_all[i]), int(dy_all[i])
+            if dx == 0 and dy == 0:
+                continue
+            offs.append((r_factor, dx, dy))
+    return offs, D
+
+
+def ambient_occlusion_block(dem, *, num_samples=16, radius=10.0, intensity=1.0, pixel_size=1.0,
+                            pixel_scale_x=None, pixel_scale_y=None) -> np.ndarray:
+    """algorithms/_impl_ambient_occlusion.py:33-118."""
+    dem = np.asarray(dem, dtype=F32)
+    h, w = dem.shape
+    hole = np.isnan(dem)
+    sx = abs(float(pixel_scale_x)) if pixel_scale_x is not None else float(pixel_size)
+    sy = abs(float(pixel_scale_y)) if pixel_scale_y is not None else float(pixel_size)
+    if sx < 1e-9:
+        sx = float(pixel_size) if pixel_size else 1.0
+    if sy < 1e-9:
+        sy = float(pixel_size) if pixel_size else 1.0
+    offs, D = ambient_occlusion_table(num_samples, radius)
+    padded = np.pad(dem, D, mode="edge")
+    total = np.zeros((h, w), dtype=F32)
+    count = np.zeros((h, w), dtype=F32)
+    with np.errstate(invalid="ignore"):
+        for (r_factor, dx, dy) in offs:
+            sh = padded[D + dy:D + dy + h, D + dx:D + dx + w]
+            dist = max(float(np.hypot(float(dx) * sx, float(dy) * sy)), 1e-9)
+            ang = np.arctan((sh - dem) / dist)
+            occ = np.maximum(0, ang) / (np.pi / 4)
+            occ = np.minimum(occ, 1.0)
+            ok = ~(np.isnan(sh) | hole)
+            total += np.where(ok, occ * (1.0 - (r_factor * 0.3)), 0)
+            count += np.where(ok, 1.0, 0)
+    count = np.maximum(count, 1.0)
+    ao = np.clip(1.0 - (total / count) * intensity, 0, 1)
+    if hole.any():
+        ao = np.where(hole, 1.0, ao)
+    ao = _ndi.gaussian_filter(ao, sigma=1.0, mode="nearest")
+    out = np.power(ao, GAMMA)
+    if hole.any():
+        out[hole] = np.nan
+    return out.astype(F32)
+
+
+def ambient_occlusion_spatial_block(dem, *, num_samples=16, radius=10.0, intensity=1.0, pixel_size=1.0,
+                                    pixel_scale_x=None, pixel_scale_y=None) -> np.ndarray:
+    """algorithms/_impl_ambient_occlusion.py:121-158."""
+    ds = decimation_factor(float(radius), pixel_size=pixel_size, algorithm="ambient_occlusion")
+    if ds <= 1:
+        return ambient_occlusion_block(dem, num_samples=num_samples, radius=radius, intensity=intensity,
+                                       pixel_size=pixel_size, pixel_scale_x=pixel_scale_x, pixel_scale_y=pixel_scale_y)
+    small = decimate_valid_mean(np.asarray(dem, dtype=F32), ds)
+    psx = float(abs(float(pixel_scale_x)) * ds) if pixel_scale_x is not None else None
+    psy = float(abs(float(pixel_scale_y)) * ds) if pixel_scale_y is not None else None
+    rs = ambient_occlusion_block(small, num_samples=num_samples, radius=max(1.0, float(radius) / float(ds)),
+                                 intensity=intensity, pixel_size=float(pixel_size) * float(ds),
+                                 pixel_scale_x=psx, pixel_scale_y=psy)
+    return upsample_align_corners(rs, dem.shape)
+
+
 def display_stretch(block, stats) -> np.ndarray:
     """algorithms/tile/dask_bridge.py:173-187 / _global_stats.py:156-178."""
     if not (isinstance(stats, (tuple, list)) and len(stats) >= 2):

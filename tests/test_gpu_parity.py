@@ -368,6 +368,57 @@ def test_openness_vs_reference_golden(golden, manifest):
     assert_close_f32(got, g["stretch__pos8_r64"], what="stretch")
 
 
+def test_ambient_occlusion_vs_reference_golden(golden, manifest):
+    """compute_ambient_occlusion_block / _spatial_block against reference outputs."""
+    from fujishadergpu_b200.algorithms._impl_ambient_occlusion import (compute_ambient_occlusion_block,
+                                                                       compute_ambient_occlusion_spatial_block)
+    g = golden("ambient_occlusion")
+    for name, meta in manifest["ambient_occlusion"].items():
+        fn = compute_ambient_occlusion_block if name.startswith("local__") else compute_ambient_occlusion_spatial_block
+        got = _np(fn(_cuda(g[meta["input"]]), **meta["kw"]))
+        assert_close_f32(got, g[name], what=name)
+
+
+def test_ambient_occlusion_classes_stretch_and_encoding():
+    """Registry / tile adapter / fused stretch + uint8 encoding against the oracle composition."""
+    from fujishadergpu_b200 import kernels as k
+    from fujishadergpu_b200.algorithms.dask_registry import ALGORITHMS
+    from fujishadergpu_b200.algorithms.tile.ambient_occlusion import AmbientOcclusionAlgorithm as TileAO
+    from fujishadergpu_b200.io.output_encoding import quantize_params, resolve_output_range
+    dem = orc.synth_dem(300, 420, seed=41, nodata=True)
+    d = _cuda(dem)
+    kw = dict(num_samples=16, radius=12.0, intensity=1.0, pixel_size=1.0, pixel_scale_x=1.0, pixel_scale_y=-1.0)
+    want = orc.ambient_occlusion_block(dem, **kw)
+    assert_close_f32(_np(ALGORITHMS["ambient_occlusion"].process(d, **kw)), want, what="ao local")
+    stats = orc.p1_p99_stretch_stats(want)
+    want_st = orc.display_stretch(want, stats)
+    assert_close_f32(_np(TileAO().process(d, global_stats=stats, **kw)), want_st, rtol=2e-5, atol=2e-6, what="ao tile stretch")
+    assert_close_f32(_np(ALGORITHMS["ambient_occlusion"].process(d, global_stats=stats, **kw)), want_st, rtol=2e-5,
+                     atol=2e-6, what="ao dask-class stretch")
+    qp = quantize_params(*resolve_output_range("ambient_occlusion"), "uint8")
+    got8 = _np(k.ambient_occlusion(d, output_dtype="uint8", qp=qp, **kw)).astype(np.int32)
+    want8 = orc.encode_array(want, qp, "uint8").astype(np.int32)
+    assert np.array_equal(got8 == 0, want8 == 0)
+    assert np.abs(got8 - want8).max() <= 1
+    # spatial mode: two radii mixed with the automatic 2^n weights
+    radii = [6, 40]
+    resp = [orc.ambient_occlusion_spatial_block(dem, **{**kw, "radius": float(r)}) for r in radii]
+    want_sp = orc.combine_responses(resp, weights=orc.pow2_weights(2), agg="mean")
+    got_sp = _np(ALGORITHMS["ambient_occlusion"].process(d, mode="spatial", radii=radii, weights=None, **kw))
+    assert_close_f32(got_sp, want_sp, what="ao spatial")
+
+
+def test_openness_spatial_multi_radius_vs_oracle():
+    from fujishadergpu_b200.algorithms.dask_registry import ALGORITHMS
+    dem = orc.synth_dem(300, 420, seed=43, nodata=True)
+    kw = dict(openness_type="positive", num_directions=8, pixel_size=1.0)
+    radii, w = [8, 40, 120], [0.5, 0.3, 0.2]
+    resp = [orc.openness_spatial_block(dem, max_distance=float(int(max(2, round(float(r))))), **kw) for r in radii]
+    want = orc.combine_responses(resp, weights=w, agg="mean")
+    got = _np(ALGORITHMS["openness"].process(_cuda(dem), mode="spatial", radii=radii, weights=w, **kw))
+    assert_close_f32(got, want, what="openness spatial 3 radii")
+
+
 def test_openness_known_answers():
     """tests/test_openness_yokoyama.py:21-47 of the reference, on the CUDA path."""
     from fujishadergpu_b200.algorithms._impl_openness import compute_openness_vectorized as op

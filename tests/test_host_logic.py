@@ -103,8 +103,8 @@ def test_radii_weight_resolution():
 
 def test_registry_names_and_unaccelerated_error():
     from fujishadergpu_b200.algorithms.dask_registry import ALGORITHMS, UNACCELERATED, get_algorithm
-    assert set(ALGORITHMS) == {"topousm_fast", "hillshade", "slope", "curvature", "openness"}
-    assert len(UNACCELERATED) == 16
+    assert set(ALGORITHMS) == {"topousm_fast", "hillshade", "slope", "curvature", "openness", "ambient_occlusion"}
+    assert len(UNACCELERATED) == 15
     with pytest.raises(NotImplementedError):
         get_algorithm("frangi")
     with pytest.raises(KeyError):
@@ -144,7 +144,7 @@ def test_percentile_host_arithmetic_equals_numpy():
 def test_tile_padding_rules():
     """reference core/tile_processor.py:207-383 (hot-path algorithms), values worked from the reference's rules."""
     from fujishadergpu_b200.core.tile_processor import DEFAULT_ALGORITHMS, _required_padding_for_algorithm as pad
-    assert set(DEFAULT_ALGORITHMS) == {"topousm_fast", "hillshade", "slope", "curvature", "openness"}
+    assert set(DEFAULT_ALGORITHMS) == {"topousm_fast", "hillshade", "slope", "curvature", "openness", "ambient_occlusion"}
     ladder = [2, 8, 32, 128, 512, 2048]
     assert pad("topousm_fast", {"radii": ladder, "mode": "spatial"}, 1.0, 1.0) == 2080          # 2048 + 16 -> 32-aligned
     assert pad("topousm_fast", {"radii": [1], "mode": "local"}, 1.0, 1.0) == 32
@@ -154,4 +154,5 @@ def test_tile_padding_rules():
     assert pad("slope", {"mode": "spatial", "radii": ladder}, 1.0, 1.0, tile_size=16384) == 1056     # thr 1024, R = 512
     assert pad("curvature", {"mode": "spatial", "radii": None}, 1.0, 1.0) == 4128                    # auto ladder, no overview
     assert pad("openness", {"mode": "spatial", "radii": [256]}, 1.0, 1.0) == 288                     # R + 16
+    assert pad("ambient_occlusion", {"mode": "spatial", "radii": [100]}, 1.0, 1.0) == 128            # R + 16
     assert pad("hillshade", {"mode": "local"}, 20.0, 1.0) == 128                                     # 5 sigma

@@ -136,6 +136,15 @@ def test_openness_matches_reference(golden, manifest):
     assert np.array_equal(orc.display_stretch(loc, tuple(st["stats"])), g["stretch__pos8_r64"], equal_nan=True)
 
 
+# ---- ambient occlusion -----------------------------------
+def test_ambient_occlusion_matches_reference(golden, manifest):
+    g = golden("ambient_occlusion")
+    for name, meta in manifest["ambient_occlusion"].items():
+        dem = g[meta["input"]]
+        fn = orc.ambient_occlusion_block if name.startswith("local__") else orc.ambient_occlusion_spatial_block
+        assert np.array_equal(fn(dem, **_kw(meta["kw"])), g[name], equal_nan=True), name
+
+
 def _radial(n=101):
     yy, xx = np.mgrid[0:n, 0:n]
     return np.sqrt((xx - n // 2) ** 2 + (yy - n // 2) ** 2)
