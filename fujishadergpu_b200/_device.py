@@ -54,3 +54,32 @@ _TORCH_DTYPE = {"float32": torch.float32, "int16": torch.int16, "uint8": torch.u
 
 def empty_out(t: torch.Tensor, shape, output_dtype: str = "float32") -> torch.Tensor:
     return torch.empty(tuple(int(s) for s in shape), dtype=_TORCH_DTYPE[str(output_dtype)], device=t.device)
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def run_concurrently(fns, device, n_streams: int = 3) -> list:
+    """Enqueue independent jobs (callables returning device tensors) round-robin on a few side streams that
+    fork from and join the current stream: small launches of different jobs overlap on the device.  The jobs'
+    results may be used on the current stream afterwards; on a CPU device (tests) the jobs run in order."""
+    dev = torch.device(device)
+    if dev.type != "cuda" or len(fns) <= 1:
+        return [fn() for fn in fns]
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), n_streams)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    streams = _SIDE_STREAMS[key]
+    main = torch.cuda.current_stream(dev)
+    for s in streams:
+        s.wait_stream(main)
+    outs = []
+    for i, fn in enumerate(fns):
+        with torch.cuda.stream(streams[i % len(streams)]):
+            outs.append(fn())
+    for s in streams:
+        main.wait_stream(s)
+    for o in outs:          # the caching allocator must not hand these blocks out again before the main stream is done
+        if isinstance(o, torch.Tensor) and o.is_cuda:
+            o.record_stream(main)
+    return outs

@@ -113,27 +113,30 @@ def compute_norm_stats_device(dem, algorithm: str, params: dict, *, grid: int = 
         by0, by1 = int(rows.min()) * cov, min(H, (int(rows.max()) + 1) * cov)
         bx0, bx1 = int(cols.min()) * cov, min(W, (int(cols.max()) + 1) * cov)
 
-    pooled = []
     wins = [t[wy0:wy0 + th, wx0:wx0 + tw]
             for wy0, wx0, tw, th in stratified_windows(W, H, by0, by1, bx0, bx1, grid=grid, tile=min(tile, max(W, H)))]
     # valid fraction of every window in one counting launch (one host sync instead of one per window)
     n_valid = _k.count_samples(wins, finite_only=True) if wins else []
+    jobs = []
     for win, nv in zip(wins, n_valid):
         if nv < min_valid_frac * float(win.numel()):
             continue
         m = int(min(margin, win.shape[0] // 3, win.shape[1] // 3))
-        if algorithm == "topousm_fast" and m > 0:
-            # same block function, same values: the kernel is only asked for the region the trim keeps
-            # (reference :275-277 computes the whole window and throws the margin away)
-            raw = _k.topousm_fast(win, radii=kw.get("radii") or [4, 16, 64], weights=kw.get("weights"),
-                                  pixel_size=kw.get("pixel_size", 1.0), norm_scale=None,
-                                  roi=(m, int(win.shape[0]) - 2 * m, m, int(win.shape[1]) - 2 * m))
-        else:
-            raw = _dev.as_tensor(block_func(win, **kw))
-        if m > 0:
-            raw = raw[m:-m, m:-m]
-        if raw.numel():
-            pooled.append(raw)
+
+        def job(win=win, m=m):
+            if algorithm == "topousm_fast" and m > 0:
+                # same block function, same values: the kernel is only asked for the region the trim keeps
+                # (reference :275-277 computes the whole window and throws the margin away)
+                raw = _k.topousm_fast(win, radii=kw.get("radii") or [4, 16, 64], weights=kw.get("weights"),
+                                      pixel_size=kw.get("pixel_size", 1.0), norm_scale=None,
+                                      roi=(m, int(win.shape[0]) - 2 * m, m, int(win.shape[1]) - 2 * m))
+            else:
+                raw = _dev.as_tensor(block_func(win, **kw))
+            return raw[m:-m, m:-m] if m > 0 else raw
+
+        jobs.append(job)
+    # the windows are independent: their (small) launches overlap on a few side streams
+    pooled = [r for r in _dev.run_concurrently(jobs, t.device) if r.numel()]
     if not pooled:
         return None
     stats = stat_func(pooled)

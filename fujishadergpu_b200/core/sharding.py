@@ -320,10 +320,32 @@ def distributed_percentile(chunks, q: float, *, take_abs: bool, finite_only: boo
 # ------------------------------------------------------------------------------------------------
 # sharded statistics pre-pass (reference: algorithms/_norm_stats.py:176-298)
 # ------------------------------------------------------------------------------------------------
+def assign_window_owners(wins, own) -> List[int]:
+    """Owner rank of every statistics window: the rank that already holds most of the window's rows among
+    the ranks with the fewest windows so far (no rank gets more than ceil(n / world) windows), so that most
+    of a window does not travel at all.  Deterministic, identical on every rank."""
+    world = len(own)
+    cap = (len(wins) + world - 1) // world
+    load = [0] * world
+    owners = []
+    for (wy0, _wx0, _tw, th) in wins:
+        best, best_key = 0, None
+        for q in range(world):
+            if load[q] >= cap:
+                continue
+            ov = _overlap(own[q], (wy0, wy0 + th))
+            key = (-(ov[1] - ov[0]) if ov else 0, load[q], q)
+            if best_key is None or key < best_key:
+                best, best_key = q, key
+        owners.append(best)
+        load[best] += 1
+    return owners
+
+
 def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, radii, weights, pixel_size=1.0,
                           dist=None, grid: int = 3, block_fn=None, select_fns=None) -> Optional[float]:
     """p99(|raw topousm_fast|) over the reference's stratified full-resolution windows.  Each window is
-    evaluated whole by ONE rank (round-robin) after gathering its rows from the owning bands; the
+    evaluated whole by ONE rank (assign_window_owners) after gathering its rows from the owning bands; the
     percentile over all windows is an exact distributed selection."""
     from ..algorithms._norm_stats import _norm_stat_window_geometry, stratified_windows
     W = int(band.shape[1])
@@ -362,10 +384,11 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
             raw = k.topousm_fast(a, radii=radii, weights=weights, pixel_size=pixel_size,
                                  roi=(m, int(a.shape[0]) - 2 * m, m, int(a.shape[1]) - 2 * m) if m > 0 else None)
             return raw[m:-m, m:-m] if m > 0 else raw
-    # 1. move every window's rows to its owner (round-robin) ...
+    # 1. move every window's rows to its owner ...
+    owners = assign_window_owners(wins, own)
     mine = []
     for wi, (wy0, wx0, tw, th) in enumerate(wins):
-        owner = wi % world
+        owner = owners[wi]
         need = [(0, 0)] * world
         need[owner] = (wy0, wy0 + th)
         cols = band[:, wx0:wx0 + tw]
@@ -373,17 +396,17 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
         if rank == owner:
             mine.append(win)
     # 2. ... then every rank evaluates its own windows, all ranks at the same time
-    pooled = []
-    for win in mine:
-        m = int(min(margin, win.shape[0] // 3, win.shape[1] // 3))
-        if trimmed_fn is not None:
-            raw = trimmed_fn(win, m)
-        else:
+    def job_for(win):
+        def job():
+            m = int(min(margin, win.shape[0] // 3, win.shape[1] // 3))
+            if trimmed_fn is not None:
+                return trimmed_fn(win, m)
             raw = block_fn(win)
-            if m > 0:
-                raw = raw[m:-m, m:-m]
-        if raw.numel():
-            pooled.append(raw)
+            return raw[m:-m, m:-m] if m > 0 else raw
+        return job
+
+    from .. import _device as _dev
+    pooled = [r for r in _dev.run_concurrently([job_for(w) for w in mine], band.device) if r.numel()]
     kw = select_fns(pooled) if select_fns is not None else {}   # tests inject stand-ins for the kernels
     s = distributed_percentile(pooled, 99.0, take_abs=True, finite_only=False, device=band.device, dist=dist, **kw)
     if not (s == s) or s <= 1e-9:
