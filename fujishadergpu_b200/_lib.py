@@ -59,6 +59,7 @@ _SIGNATURES = {
     "fsg_ambient_occlusion": (_I, [_P, _P, _L, _L, _L, _L, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                    C.POINTER(C.c_float), C.POINTER(C.c_float), _D, _D, _D, C.POINTER(Encode), _P,
                                    C.c_size_t, _P]),
+    "fsg_overview_average": (_I, [_P, _P, _L, _L, _L, _L, _I, _D, _I, _P]),
     "fsg_decimate_workspace_bytes": (C.c_size_t, [_L, _L, _I]),
     "fsg_decimate": (_I, [_P, _P, _L, _L, _L, _I, _P, C.c_size_t, _P]),
     "fsg_upsample": (_I, [_P, _P, _L, _L, _L, _L, _P, C.c_size_t, _P]),

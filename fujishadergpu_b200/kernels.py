@@ -244,6 +244,24 @@ def ambient_occlusion(dem, *, num_samples=16, radius=10.0, intensity=1.0, pixel_
     return out
 
 
+def overview_average(arr: torch.Tensor, nodata=None) -> torch.Tensor:
+    """One 2 x 2 AVERAGE overview level (ceil(H/2) x ceil(W/2)) of a float32 / int16 / uint8 device raster;
+    members equal to `nodata` (NaN for float32) are skipped (core/dask_processor.py:201-228: OVERVIEW_RESAMPLING=AVERAGE)."""
+    t = dev.as_tensor(arr)
+    kinds = {torch.float32: _lib.FSG_OUT_F32, torch.int16: _lib.FSG_OUT_I16, torch.uint8: _lib.FSG_OUT_U8}
+    if t.ndim != 2 or t.dtype not in kinds:
+        raise ValueError("overview_average: 2-D float32 / int16 / uint8 raster expected")
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    H, W = int(t.shape[0]), int(t.shape[1])
+    out = torch.empty(((H + 1) // 2, (W + 1) // 2), dtype=t.dtype, device=t.device)
+    has = nodata is not None and not (isinstance(nodata, float) and nodata != nodata)
+    check(_lib.load().fsg_overview_average(_ptr(t), _ptr(out), H, W, int(t.stride(0)), int(out.stride(0)), kinds[t.dtype],
+                                           float(nodata) if has else 0.0, 1 if has else 0,
+                                           C.c_void_p(dev.stream_ptr(t))), "fsg_overview_average")
+    return out
+
+
 def decimate(dem, factor: int) -> torch.Tensor:
     t = dev.as_f32_2d(dem)
     f = int(factor)

@@ -193,6 +193,13 @@ int fsg_ambient_occlusion(const float* dem, void* out, int64_t H, int64_t W, int
                           const float* factor_host, double intensity, double stretch_lo, double stretch_scale,
                           const fsg_encode* enc, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- output pyramid (core/dask_processor.py:201-228, io/cog_builder.py:295-310) ---
+ * One 2 x 2 AVERAGE overview level of an encoded raster (element kind FSG_OUT_*): NoData members (DN == nodata
+ * when has_nodata, NaN for f32) are skipped, an empty cell is NoData, integers round half up.  out is
+ * ceil(H/2) x ceil(W/2).  The host layer (io/cog_writer.py) cascades it for the COG's overview levels. */
+int fsg_overview_average(const void* in, void* out, int64_t H, int64_t W, int64_t ld_in, int64_t ld_out, int kind,
+                         double nodata, int has_nodata, void* stream);
+
 /* ---- helpers ------------------------------------------------------------------------------
  * fsg_decimate      : _downsample_nan_aware incl. enclosed-void fill (needs workspace)
  * fsg_upsample      : _upsample_to_shape (plain and NaN-aware branch)

@@ -803,6 +803,33 @@ def ambient_occlusion_spatial_block(dem, *, num_samples=16, radius=10.0, intensi
     return upsample_align_corners(rs, dem.shape)
 
 
+def overview_average_2x(a: np.ndarray, nodata=None) -> np.ndarray:
+    """One 2 x 2 AVERAGE overview level as the COG writer's GPU kernel defines it (GDAL OVERVIEW_RESAMPLING=AVERAGE,
+    core/dask_processor.py:201-228): members equal to `nodata` (NaN for floats) are skipped, an empty cell is NoData,
+    integers round half up, a mean that collides with the NoData value moves to the nearest valid DN."""
+    h, w = a.shape
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    is_f = a.dtype.kind == "f"
+    pad = np.zeros((oh * 2, ow * 2), dtype=np.float64)
+    ok = np.zeros((oh * 2, ow * 2), dtype=bool)
+    pad[:h, :w] = np.where(np.isnan(a), 0.0, a) if is_f else a
+    ok[:h, :w] = ~np.isnan(a) if is_f else (np.ones_like(a, bool) if nodata is None else a != nodata)
+    v = np.where(ok, pad, 0.0)
+    s = v[0::2, 0::2] + v[0::2, 1::2]
+    s = s + v[1::2, 0::2]
+    s = s + v[1::2, 1::2]
+    n = ok[0::2, 0::2].astype(np.int64) + ok[0::2, 1::2] + ok[1::2, 0::2] + ok[1::2, 1::2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mean = s / n
+    if is_f:
+        return np.where(n > 0, mean, np.nan).astype(a.dtype)
+    m = np.floor(mean + 0.5)
+    if nodata is not None:
+        m = np.where((n > 0) & (m == nodata), np.where(mean >= nodata, nodata + 1.0, nodata - 1.0), m)
+        m = np.where(n > 0, m, float(nodata))
+    return m.astype(a.dtype)
+
+
 def display_stretch(block, stats) -> np.ndarray:
     """algorithms/tile/dask_bridge.py:173-187 / _global_stats.py:156-178."""
     if not (isinstance(stats, (tuple, list)) and len(stats) >= 2):
