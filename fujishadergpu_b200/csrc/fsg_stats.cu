@@ -241,16 +241,28 @@ __global__ void __launch_bounds__(256) rank_info_kernel(Chunks c, int take_abs, 
 // per-chunk sample counts (the statistics pre-pass checks the valid fraction of every window, _norm_stats.py:268-270)
 __global__ void __launch_bounds__(256) count_chunks_kernel(Chunks c, int finite_only, unsigned long long* counts) {
   const int64_t ntiles = c.rowstart[c.n];
+  // per-thread running count of the current chunk; flushed (one atomic per warp) only when the CTA moves on to
+  // another chunk -- one atomic per warp and tile made 2.4 M atomics on nine addresses the whole cost of the scan
+  unsigned int local = 0;
+  int cur = -1;
+  auto flush = [&]() {
+    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counts[cur], (unsigned long long)local);
+    local = 0;
+  };
   for (int64_t T = blockIdx.x; T < ntiles; T += gridDim.x) {
     int k = 0;
     while (k + 1 < c.n && T >= c.rowstart[k + 1]) ++k;
+    if (k != cur) {          // (CTA-uniform)
+      if (cur >= 0) flush();
+      cur = k;
+    }
     const int64_t cols = c.cols[k];
     const int64_t tpr = (cols + SCAN_TILE - 1) / SCAN_TILE;
     const int64_t t = T - c.rowstart[k];
     const int64_t r = t / tpr, cb = (t - r * tpr) * SCAN_TILE;
     const float* row = c.ptr[k] + r * c.ld[k];
     const int64_t cend = cb + SCAN_TILE < cols ? cb + SCAN_TILE : cols;
-    unsigned int local = 0;
     constexpr int NL = SCAN_TILE / 256;
     float v[NL];
 #pragma unroll
@@ -260,9 +272,8 @@ __global__ void __launch_bounds__(256) count_chunks_kernel(Chunks c, int finite_
     }
 #pragma unroll
     for (int q = 0; q < NL; ++q) local += finite_only ? (isfinite(v[q]) ? 1u : 0u) : (v[q] == v[q] ? 1u : 0u);
-    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counts[k], (unsigned long long)local);
   }
+  if (cur >= 0) flush();
 }
 
 // ---- device-staged selection (multi-GPU): the selection state never leaves the device ----------------

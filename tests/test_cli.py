@@ -1,0 +1,92 @@
+"""The command line over the B200 path (fujishadergpu_b200/cli.py): GeoTIFF in -> algorithm -> COG out, held to the
+oracle's composition of the same steps (reference flow: core/dask_processor.py:1146-1490)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import terrain_oracle as orc  # noqa: E402
+
+
+def test_parser_matches_reference_flags():
+    from fujishadergpu_b200.cli import build_parser, resolve_params
+    p = build_parser()
+    a = p.parse_args(["in.tif", "out.tif", "--algorithm", "topousm_fast", "--mode", "spatial", "--radii", "2,8,32",
+                      "--weights", "0.5,0.3,0.2", "--output-dtype", "uint8"])
+    prm = resolve_params(a, (4000, 3000), 1.0, 1.0, -1.0)
+    assert prm["radii"] == [2, 8, 32] and prm["weights"] == [0.5, 0.3, 0.2] and prm["mode"] == "radius"
+    a = p.parse_args(["in.tif", "out.tif", "--algo", "topousm_fast", "--mode", "local", "--radii", "4,16"])
+    prm = resolve_params(a, (4000, 3000), 1.0, 1.0, -1.0)
+    assert prm["radii"] == [1] and prm["weights"] == [1.0]          # --mode local ignores explicit radii
+    a = p.parse_args(["in.tif", "out.tif", "--algorithm", "topousm_fast"])
+    prm = resolve_params(a, (30000, 40000), 1.0, 1.0, -1.0)
+    assert prm["radii"] == orc.ladder_radii(30000) and prm["weights"] == orc.pow2_weights(len(prm["radii"]))
+    a = p.parse_args(["in.tif", "out.tif", "--algorithm", "hillshade", "--mode", "local", "--azimuth", "300"])
+    prm = resolve_params(a, (500, 500), 2.0, 2.0, -2.0)
+    assert prm["radii"] == [1] and prm["azimuth"] == 300.0 and prm["pixel_scale_y"] == -2.0
+    a = p.parse_args(["in.tif", "out.tif", "--algorithm", "openness", "--max-distance", "64", "--num-directions", "8"])
+    prm = resolve_params(a, (5000, 5000), 1.0, 1.0, -1.0)
+    assert prm["max_distance"] == 64 and prm["radii"] == orc.ladder_radii(5000)
+
+
+def _write_input(path, dem, nodata=-9999.0, px=2.0):
+    from fujishadergpu_b200.io.cog_writer import write_tiff_pyramid
+    a = np.where(np.isnan(dem), np.float32(nodata), dem).astype(np.float32)
+    write_tiff_pyramid(path, [a], nodata=nodata, transform=(500000.0, px, 0.0, 4100000.0, 0.0, -px), epsg=6677,
+                       compress="deflate", bigtiff=False)
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end_against_oracle(tmp_path):
+    pytest.importorskip("torch")
+    from fujishadergpu_b200.cli import main
+    from fujishadergpu_b200.io.geotiff_reader import read_geotiff
+    dem = orc.synth_dem(900, 700, seed=61, nodata=True)
+    src = str(tmp_path / "dem.tif")
+    _write_input(src, dem)
+    # hillshade, local, uint8
+    out = str(tmp_path / "hs.tif")
+    assert main([src, out, "--algorithm", "hillshade", "--mode", "local", "--output-dtype", "uint8"]) == 0
+    got, meta = read_geotiff(out)
+    want = orc.encode_array(orc.hillshade_block(dem, pixel_size=2.0, pixel_scale_x=2.0, pixel_scale_y=-2.0),
+                            orc.encode_params(0.0, 1.0, "uint8"), "uint8")
+    assert np.array_equal(got == 0, want == 0) and np.abs(got.astype(int) - want.astype(int)).max() <= 1
+    assert meta["epsg"] == 6677 and meta["transform"] == (500000.0, 2.0, 0.0, 4100000.0, 0.0, -2.0) and meta["nodata"] == 0.0
+    # topousm_fast, explicit radii, float32: raw block / p99 of the stratified windows (here: the whole raster, trimmed)
+    out = str(tmp_path / "topo.tif")
+    radii, w = [2, 8, 32], [0.5, 0.3, 0.2]
+    assert main([src, out, "--algorithm", "topousm_fast", "--radii", "2,8,32", "--weights", "0.5,0.3,0.2"]) == 0
+    got, meta = read_geotiff(out)
+    raw = orc.topousm_fast_block(dem, radii=radii, weights=w, pixel_size=2.0)
+    margin, tile = orc.stats_window_geometry("topousm_fast", {"radii": radii})
+    ok = np.isfinite(dem)
+    cov = max(1, max(dem.shape) // 512)
+    ov = ok[::cov, ::cov][: max(1, dem.shape[0] // cov), : max(1, dem.shape[1] // cov)]
+    rows, cols = np.nonzero(ov.any(axis=1))[0], np.nonzero(ov.any(axis=0))[0]
+    by0, by1 = int(rows.min()) * cov, min(dem.shape[0], (int(rows.max()) + 1) * cov)
+    bx0, bx1 = int(cols.min()) * cov, min(dem.shape[1], (int(cols.max()) + 1) * cov)
+    pooled = []
+    for (wy0, wx0, tw, th) in orc.stats_windows(dem.shape[1], dem.shape[0], by0, by1, bx0, bx1, grid=3,
+                                                tile=min(tile, max(dem.shape))):
+        win = dem[wy0:wy0 + th, wx0:wx0 + tw]
+        if np.isfinite(win).sum() < 0.02 * win.size:
+            continue
+        r = orc.topousm_fast_block(win, radii=radii, weights=w, pixel_size=2.0)
+        m = int(min(margin, r.shape[0] // 3, r.shape[1] // 3))
+        if m > 0:
+            r = r[m:-m, m:-m]
+        pooled.append(r[~np.isnan(r)])
+    scale = orc.abs_p99_scale(np.concatenate(pooled))[0]
+    want = orc.normalise_by_scale(raw.copy(), (scale,))
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.allclose(got[~np.isnan(want)], want[~np.isnan(want)], rtol=1e-5, atol=1e-6)
+    assert meta["nodata"] != meta["nodata"] and meta["predictor"] == 3
+    # ambient occlusion, local, int16
+    out = str(tmp_path / "ao.tif")
+    assert main([src, out, "--algorithm", "ambient_occlusion", "--mode", "local", "--radius", "8", "--output-dtype", "int16"]) == 0
+    got, meta = read_geotiff(out)
+    assert got.dtype == np.int16 and meta["predictor"] == 2 and np.array_equal(got == 0, np.isnan(dem))
