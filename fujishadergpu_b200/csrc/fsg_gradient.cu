@@ -104,6 +104,33 @@ __device__ __forceinline__ float deriv(const float* f, int s, int64_t g, int64_t
   return c.inv_two_h != 0.f ? d * c.inv_two_h : d / c.two_h;   // exact reciprocal when 2h is a power of two
 }
 
+// curvature from first / second derivatives + display mapping (_impl_curvature.py:34-55), op for op
+__device__ __forceinline__ float curv_result(const GradParams& p, float dy, float dx, float dyy, float dyx, float dxy,
+                                             float dxx) {
+  float k;
+  if (p.sub == FSG_CURV_MEAN) {
+    float pp = dx, q = dy, r = dxx, t = dyy;
+    float s = (dxy + dyx) / 2.f;
+    float den = pow15((1.f + pp * pp) + q * q);
+    float num = ((1.f + q * q) * r - ((2.f * pp) * q) * s) + (1.f + pp * pp) * t;
+    k = (-num) / (2.f * den + 1e-10f);
+  } else if (p.sub == FSG_CURV_GAUSSIAN) {
+    float b = (1.f + dx * dx) + dy * dy;
+    k = (dxx * dyy - dxy * dxy) / (b * b);
+  } else if (p.sub == FSG_CURV_PLANFORM) {
+    float num = ((dy * dy) * dxx - ((2.f * dx) * dy) * dxy) + (dx * dx) * dyy;
+    k = (-num) / (pow15(dx * dx + dy * dy) + 1e-10f);
+  } else {
+    float num = ((dx * dx) * dxx + ((2.f * dx) * dy) * dxy) + (dy * dy) * dyy;
+    float g2 = dx * dx + dy * dy;
+    k = (-num) / (g2 * pow15((1.f + dx * dx) + dy * dy) + 1e-10f);
+  }
+  float t = tanhf(k * 100.f);
+  // x^(1/2.2) for x in [0, 1] as exp2f(c * log2f(x)) (log2f <= 1 ulp, exp2f <= 2 ulp: <= 4e-7 relative for
+  // x >= 1e-3, the range the 1e-5 bar applies to; 0 -> 0, NaN -> NaN) instead of the ~100-instruction powf
+  return exp2f((float)(1 / 2.2) * log2f((t + 1.f) / 2.f));
+}
+
 template <int CLASS>
 struct TileGeom {
   static constexpr int HALO = (CLASS == 2) ? 3 : 2;
@@ -190,26 +217,7 @@ __device__ __forceinline__ void grad_tile(const GradParams& p, int64_t ty0, int6
       float dyx = deriv(gyp, 1, gx, p.W, p.x2);
       float dxy = deriv(gxp, DW, gy, p.H, p.y2);
       float dxx = deriv(gxp, 1, gx, p.W, p.x2);
-      float k;
-      if (p.sub == FSG_CURV_MEAN) {
-        float pp = dx, q = dy, r = dxx, t = dyy;
-        float s = (dxy + dyx) / 2.f;
-        float den = pow15((1.f + pp * pp) + q * q);
-        float num = ((1.f + q * q) * r - ((2.f * pp) * q) * s) + (1.f + pp * pp) * t;
-        k = (-num) / (2.f * den + 1e-10f);
-      } else if (p.sub == FSG_CURV_GAUSSIAN) {
-        float b = (1.f + dx * dx) + dy * dy;
-        k = (dxx * dyy - dxy * dxy) / (b * b);
-      } else if (p.sub == FSG_CURV_PLANFORM) {
-        float num = ((dy * dy) * dxx - ((2.f * dx) * dy) * dxy) + (dx * dx) * dyy;
-        k = (-num) / (pow15(dx * dx + dy * dy) + 1e-10f);
-      } else {
-        float num = ((dx * dx) * dxx + ((2.f * dx) * dy) * dxy) + (dy * dy) * dyy;
-        float g2 = dx * dx + dy * dy;
-        k = (-num) / (g2 * pow15((1.f + dx * dx) + dy * dy) + 1e-10f);
-      }
-      float t = tanhf(k * 100.f);
-      res = powf((t + 1.f) / 2.f, (float)(1 / 2.2));
+      res = curv_result(p, dy, dx, dyy, dyx, dxy, dxx);
     }
     store_out(p.out, (gy - p.out_row0) * p.ld_out + gx, res, p.enc);
   }
@@ -392,6 +400,139 @@ __global__ void __launch_bounds__(GS_THREADS, 4) grad_stream_kernel(const __grid
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Streaming curvature (16-byte aligned rows): same scheme with a 5 x 5 footprint.  A thread owns four adjacent
+// columns and keeps rows y-2 .. y+2 of columns c-2 .. c+5 in registers (three more rows of loads in flight);
+// first derivatives are formed where they are needed and the second derivatives from them -- the op sequence of
+// np.gradient applied twice (_impl_curvature.py:23-33: |step| for the first, signed step for the second pass).
+// The hot loop uses the central forms everywhere and clamped loads; the two-pixel frame of the raster (where
+// np.gradient's one-sided forms enter a first or a second derivative) is redone afterwards tile by tile with
+// grad_tile<2>, and so is the whole block when a NaN / Inf was loaded (gap fill).
+// ------------------------------------------------------------------------------------------
+struct CsRow {
+  float v[GS_VEC + 4];   // columns c-2 .. c+5
+};
+
+__device__ __forceinline__ void cs_issue(const GradParams& p, int64_t gy, int64_t c, CsRow& r) {
+  gy = gy < 0 ? 0 : (gy > p.H - 1 ? p.H - 1 : gy);           // clamped: only frame pixels see the difference
+  int64_t by = gy - p.buf_row0;                               // (row bands: the look-ahead rows may lie outside the buffer)
+  by = by < 0 ? 0 : (by > p.buf_rows - 1 ? p.buf_rows - 1 : by);
+  const float* row = p.dem + by * p.ld_in;
+  if (c + GS_VEC <= p.W) {
+    float4 q = __ldg(reinterpret_cast<const float4*>(row + c));
+    r.v[2] = q.x; r.v[3] = q.y; r.v[4] = q.z; r.v[5] = q.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < GS_VEC; ++k) r.v[2 + k] = (c + k < p.W) ? __ldg(row + c + k) : 0.f;
+  }
+  if (c >= 2) {
+    float2 l = __ldg(reinterpret_cast<const float2*>(row + c - 2));
+    r.v[0] = l.x; r.v[1] = l.y;
+  } else {
+    r.v[0] = r.v[1] = 0.f;
+  }
+  if (c + GS_VEC + 2 <= p.W) {
+    float2 h = __ldg(reinterpret_cast<const float2*>(row + c + GS_VEC));
+    r.v[6] = h.x; r.v[7] = h.y;
+  } else {
+    r.v[6] = c + GS_VEC < p.W ? __ldg(row + c + GS_VEC) : 0.f;
+    r.v[7] = 0.f;
+  }
+}
+
+// POW2: every 2h is a power of two (the usual case: 1 m, 0.5 m, 2 m ... pixels), so each central difference is one
+// subtraction and one exact multiplication -- no per-call test for the division form
+template <bool POW2>
+__device__ __forceinline__ float central_t(float hi, float lo, const AxisCoef& c) {
+  if (POW2) return (hi - lo) * c.inv_two_h;
+  return central(hi, lo, c);
+}
+
+template <bool POW2>
+__global__ void __launch_bounds__(GS_THREADS, 2) curv_stream_kernel(const __grid_constant__ GradParams p) {
+  __shared__ float F[TileGeom<2>::FH * TileGeom<2>::FW];
+  __shared__ unsigned char M[GT_H * GT_W];
+  __shared__ float DY[TileGeom<2>::DH * TileGeom<2>::DW];
+  __shared__ float DX[TileGeom<2>::DH * TileGeom<2>::DW];
+  const int64_t cx0 = (int64_t)blockIdx.x * GS_COLS;
+  const int64_t c = cx0 + (int64_t)threadIdx.x * GS_VEC;
+  const int64_t y0 = p.out_row0 + (int64_t)blockIdx.y * GS_BAND;
+  const int64_t yend = p.out_row0 + p.out_rows;
+  const int64_t y1 = y0 + GS_BAND < yend ? y0 + GS_BAND : yend;
+  const bool live = c < p.W;
+  float nanprobe = 0.f;
+  if (live) {
+    CsRow r0, r1, r2, r3, r4, q1, q2, q3;   // rows y-2 .. y+2, then rows whose loads are in flight
+    cs_issue(p, y0 - 2, c, r0);
+    cs_issue(p, y0 - 1, c, r1);
+    cs_issue(p, y0, c, r2);
+    cs_issue(p, y0 + 1, c, r3);
+    cs_issue(p, y0 + 2, c, r4);
+    cs_issue(p, y0 + 3, c, q1);
+    cs_issue(p, y0 + 4, c, q2);
+    const bool vec_out = (p.ld_out % 4 == 0) && (c + GS_VEC <= p.W);
+#pragma unroll
+    for (int i = 0; i < GS_VEC + 4; ++i) nanprobe += (r0.v[i] + r1.v[i]) + (r2.v[i] + r3.v[i]);
+    nanprobe *= 0.f;
+#pragma unroll 1
+    for (int64_t y = y0; y < y1; ++y) {
+      cs_issue(p, y + 5, c, q3);
+      float res[GS_VEC];
+#pragma unroll
+      for (int k = 0; k < GS_VEC; ++k) {
+        const int i = k + 2;
+        // first derivatives (|step|): dy at (y-1, y, y+1; x) and (y; x-1, x+1); dx at (y; x-1, x, x+1) and (y-1, y+1; x)
+        const float dy_m = central_t<POW2>(r2.v[i], r0.v[i], p.y1);
+        const float dy_0 = central_t<POW2>(r3.v[i], r1.v[i], p.y1);
+        const float dy_p = central_t<POW2>(r4.v[i], r2.v[i], p.y1);
+        const float dy_l = central_t<POW2>(r3.v[i - 1], r1.v[i - 1], p.y1);
+        const float dy_r = central_t<POW2>(r3.v[i + 1], r1.v[i + 1], p.y1);
+        const float dx_l = central_t<POW2>(r2.v[i], r2.v[i - 2], p.x1);
+        const float dx_0 = central_t<POW2>(r2.v[i + 1], r2.v[i - 1], p.x1);
+        const float dx_r = central_t<POW2>(r2.v[i + 2], r2.v[i], p.x1);
+        const float dx_m = central_t<POW2>(r1.v[i + 1], r1.v[i - 1], p.x1);
+        const float dx_p = central_t<POW2>(r3.v[i + 1], r3.v[i - 1], p.x1);
+        // second derivatives (signed step)
+        const float dyy = central_t<POW2>(dy_p, dy_m, p.y2);
+        const float dyx = central_t<POW2>(dy_r, dy_l, p.x2);
+        const float dxy = central_t<POW2>(dx_p, dx_m, p.y2);
+        const float dxx = central_t<POW2>(dx_r, dx_l, p.x2);
+        res[k] = curv_result(p, dy_0, dx_0, dyy, dyx, dxy, dxx);
+      }
+#pragma unroll
+      for (int i = 0; i < GS_VEC + 4; ++i) nanprobe += r4.v[i];
+      nanprobe *= 0.f;
+      const int64_t o = (y - p.out_row0) * p.ld_out + c;
+      if (vec_out && p.enc.kind == FSG_OUT_F32) {
+        *reinterpret_cast<float4*>((float*)p.out + o) = make_float4(res[0], res[1], res[2], res[3]);
+      } else if (vec_out && p.enc.kind == FSG_OUT_U8) {
+        uchar4 q = make_uchar4((unsigned char)(int)encode_dn(res[0], p.enc), (unsigned char)(int)encode_dn(res[1], p.enc),
+                               (unsigned char)(int)encode_dn(res[2], p.enc), (unsigned char)(int)encode_dn(res[3], p.enc));
+        *reinterpret_cast<uchar4*>((uint8_t*)p.out + o) = q;
+      } else {
+#pragma unroll
+        for (int k = 0; k < GS_VEC; ++k)
+          if (c + k < p.W) store_out(p.out, o + k, res[k], p.enc);
+      }
+      r0 = r1; r1 = r2; r2 = r3; r3 = r4; r4 = q1; q1 = q2; q2 = q3;
+    }
+#pragma unroll
+    for (int i = 0; i < GS_VEC + 4; ++i) nanprobe += r3.v[i] + r4.v[i];   // rows y1, y1+1 (read by the last rows)
+    nanprobe *= 0.f;
+  }
+  // ---- cold paths: NaN in the block -> everything again with gap fill; otherwise only the raster frame ----
+  const bool redo_all = __syncthreads_or((int)(nanprobe != nanprobe)) != 0;
+  for (int64_t ty = y0; ty < y1; ty += GT_H) {
+    for (int64_t tx = cx0; tx < cx0 + GS_COLS && tx < p.W; tx += GT_W) {
+      const bool frame = ty < 2 || ty + GT_H > p.H - 2 || tx < 2 || tx + GT_W > p.W - 2;
+      if (!redo_all && !frame) continue;
+      __syncthreads();
+      grad_tile<2>(p, ty, tx, F, M, DY, DX);
+    }
+  }
+}
+
 static int check_window(const fsg_window* w, int need_halo, const char* who) {
   if (!w) return fail(FSG_E_INVALID, "%s: window is NULL", who);
   if (w->H_global < 3 || w->W < 3)
@@ -429,7 +570,18 @@ static int run_grad(int cls, const float* dem, void* out, const fsg_window* win,
                          (((uintptr_t)p.out & 15) == 0) && p.buf_row0 <= (p.out_row0 > 0 ? p.out_row0 - 1 : 0) &&
                          p.buf_row0 + p.buf_rows >= (p.out_row0 + p.out_rows < p.H ? p.out_row0 + p.out_rows + 1 : p.H) &&
                          !getenv("FSG_GRAD_TILED");
-  if (stream_ok) {
+  // curvature: the buffer must hold the two rows above / below the output rows (clamped at the raster edge)
+  const bool cstream_ok = cls == 2 && (((uintptr_t)p.dem & 15) == 0) && (p.ld_in % 4 == 0) &&
+                          (((uintptr_t)p.out & 15) == 0) && p.H >= 8 && p.W >= 8 &&
+                          p.buf_row0 <= (p.out_row0 > 2 ? p.out_row0 - 2 : 0) &&
+                          p.buf_row0 + p.buf_rows >= (p.out_row0 + p.out_rows + 2 < p.H ? p.out_row0 + p.out_rows + 2 : p.H) &&
+                          !getenv("FSG_GRAD_TILED");
+  if (cstream_ok) {
+    dim3 sgrid((unsigned)((p.W + GS_COLS - 1) / GS_COLS), (unsigned)((p.out_rows + GS_BAND - 1) / GS_BAND));
+    const bool pow2 = p.y1.inv_two_h != 0.f && p.x1.inv_two_h != 0.f && p.y2.inv_two_h != 0.f && p.x2.inv_two_h != 0.f;
+    if (pow2) curv_stream_kernel<true><<<sgrid, GS_THREADS, 0, s>>>(p);
+    else curv_stream_kernel<false><<<sgrid, GS_THREADS, 0, s>>>(p);
+  } else if (stream_ok) {
     dim3 sgrid((unsigned)((p.W + GS_COLS - 1) / GS_COLS), (unsigned)((p.out_rows + GS_BAND - 1) / GS_BAND));
     if (cls == 0) grad_stream_kernel<0><<<sgrid, GS_THREADS, 0, s>>>(p);
     else grad_stream_kernel<1><<<sgrid, GS_THREADS, 0, s>>>(p);

@@ -368,6 +368,33 @@ def test_openness_vs_reference_golden(golden, manifest):
     assert_close_f32(got, g["stretch__pos8_r64"], what="stretch")
 
 
+def test_curvature_streaming_kernel_equals_tile_kernel_bitwise(monkeypatch):
+    """curv_stream_kernel (registers, central forms, frame redone) against the tile kernel it replaces for aligned
+    rasters: every curvature type, dense / NoData, f32 and uint8, an odd-sized and a band-limited call."""
+    from fujishadergpu_b200 import kernels as k
+    for shape, nod in (((1500, 2900), False), ((777, 1164), True), ((64, 2048), False), ((9, 12), False)):
+        dem = orc.synth_dem(shape[0], shape[1], seed=70 + shape[0], nodata=nod)
+        d = _cuda(dem)
+        for ct in ("mean", "gaussian", "planform", "profile"):
+            kw = dict(curvature_type=ct, pixel_size=1.0, pixel_scale_x=2.0, pixel_scale_y=-2.0)
+            monkeypatch.setenv("FSG_GRAD_TILED", "1")
+            want = k.curvature(d, **kw)
+            want8 = k.curvature(d, output_dtype="uint8", qp={"a_coef": 254.0, "b_coef": 1.0, "dn_min": 1, "dn_max": 255}, **kw)
+            monkeypatch.delenv("FSG_GRAD_TILED")
+            got = k.curvature(d, **kw)
+            got8 = k.curvature(d, output_dtype="uint8", qp={"a_coef": 254.0, "b_coef": 1.0, "dn_min": 1, "dn_max": 255}, **kw)
+            assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0)), (shape, ct)
+            assert torch.equal(got8, want8), (shape, ct)
+        if shape[0] >= 777:   # rows [200, 500) of the raster from a buffer holding rows [190, 520)
+            monkeypatch.setenv("FSG_GRAD_TILED", "1")
+            wb = k.curvature(d[190:520], curvature_type="mean", band=dict(h_global=shape[0], buf_row0=190, out_row0=200, out_rows=300))
+            monkeypatch.delenv("FSG_GRAD_TILED")
+            gb = k.curvature(d[190:520], curvature_type="mean", band=dict(h_global=shape[0], buf_row0=190, out_row0=200, out_rows=300))
+            whole = k.curvature(d, curvature_type="mean")[200:500]
+            assert torch.equal(torch.nan_to_num(gb, nan=-7.0), torch.nan_to_num(wb, nan=-7.0))
+            assert torch.equal(torch.nan_to_num(gb, nan=-7.0), torch.nan_to_num(whole, nan=-7.0))
+
+
 def test_ambient_occlusion_vs_reference_golden(golden, manifest):
     """compute_ambient_occlusion_block / _spatial_block against reference outputs."""
     from fujishadergpu_b200.algorithms._impl_ambient_occlusion import (compute_ambient_occlusion_block,

@@ -185,6 +185,40 @@ def test_band_bounds_are_aligned_and_cover():
                 assert r0 % 16 == 0 and (r1 % 16 == 0 or r1 == H)
 
 
+def test_window_owner_assignment_is_balanced_and_local():
+    """Statistics windows go to the rank that already holds most of their rows; no rank gets more than
+    ceil(n / world) windows (the critical path of the pre-pass), every rank computes the same assignment."""
+    from fujishadergpu_b200.algorithms._norm_stats import stratified_windows
+    H = W = 65536
+    wins = stratified_windows(W, H, 0, H, 0, W, grid=3, tile=8256)
+    for world in (1, 2, 3, 4, 8, 16):
+        own = sh.band_bounds(H, world)
+        owners = sh.assign_window_owners(wins, own)
+        assert len(owners) == len(wins) and all(0 <= o < world for o in owners)
+        cap = (len(wins) + world - 1) // world
+        assert max(owners.count(q) for q in range(world)) <= cap
+        local = sum((sh._overlap(own[o], (w[0], w[0] + w[3])) or (0, 0))[1] - (sh._overlap(own[o], (w[0], w[0] + w[3])) or (0, 0))[0]
+                    for o, w in zip(owners, wins))
+        rr = sum((sh._overlap(own[i % world], (w[0], w[0] + w[3])) or (0, 0))[1] - (sh._overlap(own[i % world], (w[0], w[0] + w[3])) or (0, 0))[0]
+                 for i, w in enumerate(wins))
+        assert local >= rr          # never more traffic than round-robin
+    assert sh.assign_window_owners(wins, sh.band_bounds(H, 8)) == sh.assign_window_owners(list(wins), sh.band_bounds(H, 8))
+
+
+def test_haloed_band_layout():
+    be = NumpyBackend()
+    H, W, radii = 400, 64, [2, 8, 32, 128]
+    for world in (2, 3):
+        own = sh.band_bounds(H, world)
+        for rank in range(world):
+            lo, hi = sh.dem_halo_rows(H, world, rank, radii, backend=be)
+            a, b = own[rank]
+            assert lo == max(0, a - 32) and hi == min(H, b + 32)
+            ext, band = sh.haloed_band(H, W, world, rank, radii, device="cpu", backend=be)
+            assert tuple(ext.shape) == (hi - lo, W) and tuple(band.shape) == (b - a, W)
+            assert band.data_ptr() == ext[a - lo:].data_ptr()
+
+
 def test_mirror_need():
     assert sh.mirror_need(-3, 5, 100, True) == (0, 6)
     assert sh.mirror_need(95, 104, 100, True) == (95, 100)
