@@ -261,6 +261,14 @@ __device__ __forceinline__ float central(float hi, float lo, const AxisCoef& c) 
   return c.inv_two_h != 0.f ? d * c.inv_two_h : d / c.two_h;
 }
 
+// POW2: every 2h is a power of two (the usual case: 1 m, 0.5 m, 2 m ... pixels), so each central difference is one
+// subtraction and one exact multiplication -- no per-call test for the division form
+template <bool POW2>
+__device__ __forceinline__ float central_t(float hi, float lo, const AxisCoef& c) {
+  if (POW2) return (hi - lo) * c.inv_two_h;
+  return central(hi, lo, c);
+}
+
 template <int CLASS>
 __device__ __forceinline__ float grad_result(const GradParams& p, float dy, float dx) {
   if (CLASS == 0) {
@@ -315,7 +323,7 @@ __device__ __forceinline__ void gs_issue(const GradParams& p, int64_t gy, int64_
   r.v[5] = c + GS_VEC < p.W ? __ldg(row + c + GS_VEC) : 0.f;
 }
 
-template <int CLASS>
+template <int CLASS, bool POW2>
 __global__ void __launch_bounds__(GS_THREADS, 4) grad_stream_kernel(const __grid_constant__ GradParams p) {
   __shared__ float F[TileGeom<CLASS>::FH * TileGeom<CLASS>::FW];
   __shared__ unsigned char M[GT_H * GT_W];
@@ -350,8 +358,8 @@ __global__ void __launch_bounds__(GS_THREADS, 4) grad_stream_kernel(const __grid
       for (int k = 0; k < GS_VEC; ++k) {
         float up = prev.v[k + 1], dn = next.v[k + 1], lf = cur.v[k], rt = cur.v[k + 2];
         if (scale) { up = up * p.zscale; dn = dn * p.zscale; lf = lf * p.zscale; rt = rt * p.zscale; }
-        float dy = central(dn, up, p.y1);
-        float dx = central(rt, lf, p.x1);
+        float dy = central_t<POW2>(dn, up, p.y1);
+        float dx = central_t<POW2>(rt, lf, p.x1);
         res[k] = grad_result<CLASS>(p, dy, dx);
       }
       nanprobe += ((cur.v[0] + cur.v[1]) + (cur.v[2] + cur.v[3])) + (cur.v[4] + cur.v[5]);
@@ -439,14 +447,6 @@ __device__ __forceinline__ void cs_issue(const GradParams& p, int64_t gy, int64_
     r.v[6] = c + GS_VEC < p.W ? __ldg(row + c + GS_VEC) : 0.f;
     r.v[7] = 0.f;
   }
-}
-
-// POW2: every 2h is a power of two (the usual case: 1 m, 0.5 m, 2 m ... pixels), so each central difference is one
-// subtraction and one exact multiplication -- no per-call test for the division form
-template <bool POW2>
-__device__ __forceinline__ float central_t(float hi, float lo, const AxisCoef& c) {
-  if (POW2) return (hi - lo) * c.inv_two_h;
-  return central(hi, lo, c);
 }
 
 template <bool POW2>
@@ -583,8 +583,11 @@ static int run_grad(int cls, const float* dem, void* out, const fsg_window* win,
     else curv_stream_kernel<false><<<sgrid, GS_THREADS, 0, s>>>(p);
   } else if (stream_ok) {
     dim3 sgrid((unsigned)((p.W + GS_COLS - 1) / GS_COLS), (unsigned)((p.out_rows + GS_BAND - 1) / GS_BAND));
-    if (cls == 0) grad_stream_kernel<0><<<sgrid, GS_THREADS, 0, s>>>(p);
-    else grad_stream_kernel<1><<<sgrid, GS_THREADS, 0, s>>>(p);
+    const bool pow2 = p.y1.inv_two_h != 0.f && p.x1.inv_two_h != 0.f;
+    if (cls == 0 && pow2) grad_stream_kernel<0, true><<<sgrid, GS_THREADS, 0, s>>>(p);
+    else if (cls == 0) grad_stream_kernel<0, false><<<sgrid, GS_THREADS, 0, s>>>(p);
+    else if (pow2) grad_stream_kernel<1, true><<<sgrid, GS_THREADS, 0, s>>>(p);
+    else grad_stream_kernel<1, false><<<sgrid, GS_THREADS, 0, s>>>(p);
   } else if (cls == 0) grad_kernel<0><<<grid, G_THREADS, 0, s>>>(p);
   else if (cls == 1) grad_kernel<1><<<grid, G_THREADS, 0, s>>>(p);
   else grad_kernel<2><<<grid, G_THREADS, 0, s>>>(p);
