@@ -181,6 +181,8 @@ def run_gpu_arm(a) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL writes its version banner / warnings to stdout by default: keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if world > 1:
         from fujishadergpu_b200.core import sharding

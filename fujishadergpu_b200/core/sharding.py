@@ -69,12 +69,11 @@ def _overlap(a, b):
     return (lo, hi) if hi > lo else None
 
 
-def exchange_rows(local: torch.Tensor, own: Sequence[Tuple[int, int]], need: Sequence[Tuple[int, int]], rank: int,
-                  dist=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Every rank holds rows own[rank] of a global 2-D array and wants rows need[rank]; returns the
-    tensor covering need[rank].  Point-to-point only (NCCL send/recv over NVLink, or gloo on CPU).
-    `out`: caller's buffer for need[rank]; when `local` already is the matching slice of `out` (a band kept
-    inside its halo buffer, see haloed_band) the own rows are not copied, only the halo rows arrive."""
+def plan_exchange(local: torch.Tensor, own: Sequence[Tuple[int, int]], need: Sequence[Tuple[int, int]], rank: int,
+                  dist=None, out: Optional[torch.Tensor] = None):
+    """First half of exchange_rows: allocates / fills the own part of the result and returns
+    (out, p2p ops, buffers to keep alive).  Several plans can be sent as ONE batch (run_exchanges): a group
+    launch costs ~0.1 ms, which dominated the nine window gathers of the statistics pre-pass."""
     lo, hi = need[rank]
     if out is None:
         out = torch.empty((max(0, hi - lo),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
@@ -100,11 +99,29 @@ def exchange_rows(local: torch.Tensor, own: Sequence[Tuple[int, int]], need: Seq
             rcv = _overlap(own[q], need[rank])
             if rcv:
                 view = out[rcv[0] - lo:rcv[1] - lo]
+                if not view.is_contiguous():
+                    raise ValueError("exchange_rows: the receive view must be contiguous")
                 ops.append(dist.P2POp(dist.irecv, view, q))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-    return out
+    return out, ops, keep
+
+
+def run_exchanges(plans, dist=None) -> list:
+    """Issue the point-to-point operations of several plan_exchange() results as one batch; returns the outs.
+    Every rank must pass the plans in the same order (sends and receives between a pair match in issue order)."""
+    ops = [op for (_out, o, _keep) in plans for op in o]
+    if ops and dist is not None:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return [out for (out, _o, _keep) in plans]
+
+
+def exchange_rows(local: torch.Tensor, own: Sequence[Tuple[int, int]], need: Sequence[Tuple[int, int]], rank: int,
+                  dist=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Every rank holds rows own[rank] of a global 2-D array and wants rows need[rank]; returns the
+    tensor covering need[rank].  Point-to-point only (NCCL send/recv over NVLink, or gloo on CPU).
+    `out`: caller's buffer for need[rank]; when `local` already is the matching slice of `out` (a band kept
+    inside its halo buffer, see haloed_band) the own rows are not copied, only the halo rows arrive."""
+    return run_exchanges([plan_exchange(local, own, need, rank, dist, out)], dist)[0]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -185,13 +202,16 @@ def topousm_fast_sharded(band: torch.Tensor, H: int, rank: int, world: int, *, r
             dem_need.append((lo, hi))
         else:
             dem_need.append((0, 0))
-    dem_ext = exchange_rows(band, own, dem_need, rank, dist, out=dem_ext)
+    dem_plan = plan_exchange(band, own, dem_need, rank, dist, out=dem_ext)
     dem_row0 = dem_need[rank][0]
 
-    # ---- 2. pyramid levels of the own rows, halo rows of each level, coarse means
+    # ---- 2. pyramid levels of the own rows, halo rows of each level, coarse means.  The DEM halo and the halo
+    # rows of every level travel in ONE point-to-point batch (a group launch costs ~0.1 ms).
     levels = sorted({factors[i] for i in range(n) if kinds[i] == 1})
     term_grids: List[Optional[torch.Tensor]] = [None] * n
     term_grow0: List[int] = [0] * n
+    plans = [dem_plan]
+    per_level = []
     if levels:
         if r1 > r0:
             grids, flags = backend.pyramid(band, levels)
@@ -218,24 +238,22 @@ def topousm_fast_sharded(band: torch.Tensor, H: int, rank: int, world: int, *, r
             if void[li]:
                 # a coarse cell is entirely NoData: the enclosed-void fill is a Gaussian over ~1/16 of the
                 # raster side, so gather the (small) level once and fill it whole on every rank
-                full = exchange_rows(grids[li], g_own, [(0, gh)] * world, rank, dist)
-                full = backend.void_fill(full)
-                for i in terms:
-                    lo, hi = mean_rows[rank]
-                    if hi > lo:
-                        term_grids[i] = backend.grid_mean(full, 0, gh, sizes[i], lo, hi - lo)
-                        term_grow0[i] = lo
-                continue
-            reach = max((4 if sizes[i] == 0 else sizes[i] // 2) for i in terms)
-            g_need = []
-            for (lo, hi) in mean_rows:
-                g_need.append(mirror_need(lo - reach, hi - 1 + reach, gh, reflect=True) if hi > lo else (0, 0))
-            g_ext = exchange_rows(grids[li], g_own, g_need, rank, dist)
-            for i in terms:
-                lo, hi = mean_rows[rank]
-                if hi > lo:
-                    term_grids[i] = backend.grid_mean(g_ext, g_need[rank][0], gh, sizes[i], lo, hi - lo)
-                    term_grow0[i] = lo
+                g_need = [(0, gh)] * world
+            else:
+                reach = max((4 if sizes[i] == 0 else sizes[i] // 2) for i in terms)
+                g_need = [mirror_need(lo - reach, hi - 1 + reach, gh, reflect=True) if hi > lo else (0, 0)
+                          for (lo, hi) in mean_rows]
+            plans.append(plan_exchange(grids[li], g_own, g_need, rank, dist))
+            per_level.append((gh, terms, mean_rows[rank], g_need[rank][0], bool(void[li])))
+    outs = run_exchanges(plans, dist)
+    dem_ext = outs[0]
+    for (gh, terms, (lo, hi), g_row0, is_void), g_ext in zip(per_level, outs[1:]):
+        if is_void:
+            g_ext = backend.void_fill(g_ext)
+        for i in terms:
+            if hi > lo:
+                term_grids[i] = backend.grid_mean(g_ext, g_row0, gh, sizes[i], lo, hi - lo)
+                term_grow0[i] = lo
     # full-resolution planes (radius <= 1 -> sigma-1 Gaussian; general fallback boxes)
     for i in range(n):
         if kinds[i] == 2 and r1 > r0:
@@ -386,15 +404,17 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
             return raw[m:-m, m:-m] if m > 0 else raw
     # 1. move every window's rows to its owner ...
     owners = assign_window_owners(wins, own)
-    mine = []
+    plans, mine_idx = [], []
     for wi, (wy0, wx0, tw, th) in enumerate(wins):
         owner = owners[wi]
         need = [(0, 0)] * world
         need[owner] = (wy0, wy0 + th)
         cols = band[:, wx0:wx0 + tw]
-        win = exchange_rows(cols, own, need, rank, dist)
+        plans.append(plan_exchange(cols, own, need, rank, dist))
         if rank == owner:
-            mine.append(win)
+            mine_idx.append(wi)
+    outs = run_exchanges(plans, dist)          # all nine gathers in one point-to-point batch
+    mine = [outs[wi] for wi in mine_idx]
     # 2. ... then every rank evaluates its own windows, all ranks at the same time
     def job_for(win):
         def job():
