@@ -181,6 +181,15 @@ def topousm_fast_sharded(band: torch.Tensor, H: int, rank: int, world: int, *, r
     """`band` = this rank's rows band_bounds(H, world)[rank] of the H x W raster (f32, NaN = NoData).
     Returns the same rows of the topousm_fast result (normalised by norm_scale when given).
     dem_ext: optional halo buffer from haloed_band() that already contains `band` (no copy of the own rows)."""
+    prep = topousm_sharded_prepare(band, H, rank, world, radii=radii, pixel_size=pixel_size, dist=dist, backend=backend,
+                                   dem_ext=dem_ext)
+    return topousm_sharded_finish(prep, weights=weights, norm_scale=norm_scale, output_dtype=output_dtype, qp=qp, out=out)
+
+
+def topousm_sharded_prepare(band: torch.Tensor, H: int, rank: int, world: int, *, radii, pixel_size=1.0, dist=None,
+                            backend=None, dem_ext: Optional[torch.Tensor] = None) -> dict:
+    """Everything of the sharded main pass that does not depend on the normalisation scale: DEM halo rows,
+    pyramid levels, their halo rows, the coarse means.  topousm_sharded_finish() runs the fused pass."""
     backend = backend or CudaBackend()
     W = int(band.shape[1])
     own = band_bounds(H, world)
@@ -260,13 +269,54 @@ def topousm_fast_sharded(band: torch.Tensor, H: int, rank: int, world: int, *, r
             term_grids[i] = backend.grid_mean(dem_ext, dem_row0, H, sizes[i], r0, r1 - r0)
             term_grow0[i] = r0
 
-    # ---- 3. fused pass over the own rows
+    return dict(backend=backend, band=band, dem_ext=dem_ext, dem_row0=dem_row0, H=H, W=W, r0=r0, r1=r1, radii=radii,
+                pixel_size=pixel_size, term_grids=term_grids, term_grow0=term_grow0)
+
+
+def topousm_sharded_finish(prep: dict, *, weights=None, norm_scale=None, output_dtype="float32", qp=None,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """---- 3. fused pass over the own rows (the only part that needs the scale)."""
+    r0, r1, W, band = prep["r0"], prep["r1"], prep["W"], prep["band"]
     if r1 <= r0:
         return torch.empty((0, W), dtype=band.dtype if output_dtype == "float32" else getattr(torch, output_dtype),
                            device=band.device)
-    return backend.fused(dem_ext, dem_row0, H, r0, r1 - r0, radii=radii, weights=weights, pixel_size=pixel_size,
-                         term_grids=term_grids, term_grow0=term_grow0, norm_scale=norm_scale,
-                         output_dtype=output_dtype, qp=qp, out=out)
+    return prep["backend"].fused(prep["dem_ext"], prep["dem_row0"], prep["H"], r0, r1 - r0, radii=prep["radii"],
+                                 weights=weights, pixel_size=prep["pixel_size"], term_grids=prep["term_grids"],
+                                 term_grow0=prep["term_grow0"], norm_scale=norm_scale, output_dtype=output_dtype,
+                                 qp=qp, out=out)
+
+
+def topousm_fast_sharded_with_stats(band: torch.Tensor, H: int, rank: int, world: int, *, radii, weights=None,
+                                    pixel_size=1.0, output_dtype="float32", qp=None, dist=None,
+                                    out: Optional[torch.Tensor] = None, dem_ext: Optional[torch.Tensor] = None):
+    """Statistics pre-pass + main pass of one step.  The scale-independent part of the main pass (halo exchange,
+    pyramid, coarse means) is enqueued on a side stream FIRST, so it fills the device while the pre-pass sits in
+    its latency-bound stages (bounding box, window gather, the selection's collectives); the fused pass starts
+    when both are done.  Every rank issues its NCCL calls in the same program order.  -> (out, scale)"""
+    dev = band.device
+    if dev.type != "cuda":
+        scale = sharded_topousm_scale(band, H, rank, world, radii=radii, weights=weights, pixel_size=pixel_size, dist=dist)
+        return topousm_fast_sharded(band, H, rank, world, radii=radii, weights=weights, pixel_size=pixel_size,
+                                    norm_scale=scale, output_dtype=output_dtype, qp=qp, dist=dist, out=out,
+                                    dem_ext=dem_ext), scale
+    cur = torch.cuda.current_stream(dev)
+    key = (dev.index, "prep")
+    if key not in _PREP_STREAMS:
+        _PREP_STREAMS[key] = torch.cuda.Stream(device=dev)
+    side = _PREP_STREAMS[key]
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        prep = topousm_sharded_prepare(band, H, rank, world, radii=radii, pixel_size=pixel_size, dist=dist, dem_ext=dem_ext)
+    scale = sharded_topousm_scale(band, H, rank, world, radii=radii, weights=weights, pixel_size=pixel_size, dist=dist)
+    cur.wait_stream(side)
+    for t in [prep["dem_ext"]] + [g for g in prep["term_grids"] if g is not None]:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            t.record_stream(cur)
+    res = topousm_sharded_finish(prep, weights=weights, norm_scale=scale, output_dtype=output_dtype, qp=qp, out=out)
+    return res, scale
+
+
+_PREP_STREAMS: dict = {}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -452,9 +502,8 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
     torch.cuda.synchronize()
 
     def step():
-        scale = sharded_topousm_scale(band, H, rank, world, radii=radii, weights=weights, dist=dist)
-        topousm_fast_sharded(band, H, rank, world, radii=radii, weights=weights, norm_scale=scale, dist=dist, out=out,
-                             dem_ext=ext)
+        _res, scale = topousm_fast_sharded_with_stats(band, H, rank, world, radii=radii, weights=weights, dist=dist,
+                                                      out=out, dem_ext=ext)
         return scale
 
     for _ in range(a.warmup):
@@ -505,9 +554,8 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
 
     def e2e_step():
         dband.copy_(hin, non_blocking=True)
-        sc = sharded_topousm_scale(dband, H, rank, world, radii=radii, weights=weights, dist=dist)
-        topousm_fast_sharded(dband, H, rank, world, radii=radii, weights=weights, norm_scale=sc, dist=dist,
-                             output_dtype="uint8", qp=qp, out=out8, dem_ext=dext)
+        topousm_fast_sharded_with_stats(dband, H, rank, world, radii=radii, weights=weights, dist=dist,
+                                        output_dtype="uint8", qp=qp, out=out8, dem_ext=dext)
         hout.copy_(out8, non_blocking=True)
         torch.cuda.synchronize()
 

@@ -95,6 +95,10 @@ def _nccl_worker(rank, world, port, path, out_dir):
     view.copy_(band)
     out2 = sh.topousm_fast_sharded(view, H, rank, world, radii=radii, weights=w, norm_scale=scale, dist=dist, dem_ext=ext)
     assert torch.equal(torch.nan_to_num(out, nan=-7777.0), torch.nan_to_num(out2, nan=-7777.0))
+    # one-call form: the scale-independent part of the main pass overlaps the statistics pre-pass on a side stream
+    out3, scale3 = sh.topousm_fast_sharded_with_stats(view, H, rank, world, radii=radii, weights=w, dist=dist, dem_ext=ext)
+    assert scale3 == scale
+    assert torch.equal(torch.nan_to_num(out, nan=-7777.0), torch.nan_to_num(out3, nan=-7777.0))
     np.save(os.path.join(out_dir, f"out_{rank}.npy"), out.cpu().numpy())
     if rank == 0:
         np.save(os.path.join(out_dir, "scale.npy"), np.array([scale]))
