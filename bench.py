@@ -198,11 +198,18 @@ def run_gpu_arm(a) -> None:
     ws = torch.empty(max(256, k.topousm_fast_workspace_bytes((H, W), RADII, 1.0)), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
+    from fujishadergpu_b200.core import sharding as sh
+
     def step():
-        st = compute_norm_stats_device(dem, "topousm_fast", params)
-        k.topousm_fast(dem, radii=RADII, weights=weights, pixel_size=1.0, norm_scale=float(st[0]),
-                       workspace=ws, out=out)
-        return st
+        # one rank of the sharded orchestration (the same code as N > 1): the scale-independent part of the main
+        # pass (pyramid, coarse means) runs on a side stream underneath the statistics pre-pass
+        _res, scale = sh.topousm_fast_sharded_with_stats(dem, H, 0, 1, radii=RADII, weights=weights, pixel_size=1.0,
+                                                         out=out, dem_ext=dem)
+        if scale is None:   # no valid statistics window: un-normalised fallback of the sequential path
+            st = compute_norm_stats_device(dem, "topousm_fast", params)
+            k.topousm_fast(dem, radii=RADII, weights=weights, pixel_size=1.0, norm_scale=float(st[0]), workspace=ws, out=out)
+            return st
+        return (scale,)
 
     for _ in range(a.warmup):
         step()

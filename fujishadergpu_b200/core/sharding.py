@@ -75,6 +75,11 @@ def plan_exchange(local: torch.Tensor, own: Sequence[Tuple[int, int]], need: Seq
     (out, p2p ops, buffers to keep alive).  Several plans can be sent as ONE batch (run_exchanges): a group
     launch costs ~0.1 ms, which dominated the nine window gathers of the statistics pre-pass."""
     lo, hi = need[rank]
+    world = len(own)
+    if out is None and hi > lo and own[rank][0] <= lo and hi <= own[rank][1] and not any(
+            _overlap(own[rank], need[q]) for q in range(world) if q != rank):
+        # everything this rank wants is already here and nobody else wants its rows: a view, no copy, no traffic
+        return local[lo - own[rank][0]:hi - own[rank][0]], [], []
     if out is None:
         out = torch.empty((max(0, hi - lo),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     else:
@@ -86,7 +91,6 @@ def plan_exchange(local: torch.Tensor, own: Sequence[Tuple[int, int]], need: Seq
         if not (dst.data_ptr() == src.data_ptr() and dst.stride() == src.stride()):
             dst.copy_(src)
     ops, keep = [], []
-    world = len(own)
     if dist is not None and world > 1:
         for q in range(world):
             if q == rank:
@@ -140,9 +144,9 @@ class CudaBackend:
         from .. import kernels as k
         return k.grid_mean_band(src, src_row0, gh, size, out_row0, out_rows)
 
-    def void_fill(self, grid):
+    def void_fill(self, grid, inplace=False):
         from .. import kernels as k
-        return k.grid_void_fill(grid)
+        return k.grid_void_fill(grid, inplace=inplace)
 
     def fused(self, dem_ext, dem_row0, H, out_row0, out_rows, **kw):
         from .. import kernels as k
@@ -227,10 +231,14 @@ def topousm_sharded_prepare(band: torch.Tensor, H: int, rank: int, world: int, *
         else:
             grids = [torch.empty((0, (W + f - 1) // f), dtype=torch.float32, device=band.device) for f in levels]
             flags = torch.zeros(len(levels), dtype=torch.int32, device=band.device)
-        void = flags.clone().to(torch.int32)
-        if dist is not None and world > 1:
+        single = not (dist is not None and world > 1)
+        if single:
+            # one rank holds the whole level: the void fill is gated by a device-side flag, no host round trip
+            void = [1] * len(levels)
+        else:
+            void = flags.clone().to(torch.int32)
             dist.all_reduce(void, op=dist.ReduceOp.MAX)
-        void = void.cpu().tolist()
+            void = void.cpu().tolist()
         for li, f in enumerate(levels):
             gh, gw = (H + f - 1) // f, (W + f - 1) // f
             g_own = [((a + f - 1) // f if b > a else 0, (b + f - 1) // f if b > a else 0) for (a, b) in own]
@@ -258,7 +266,7 @@ def topousm_sharded_prepare(band: torch.Tensor, H: int, rank: int, world: int, *
     dem_ext = outs[0]
     for (gh, terms, (lo, hi), g_row0, is_void), g_ext in zip(per_level, outs[1:]):
         if is_void:
-            g_ext = backend.void_fill(g_ext)
+            g_ext = backend.void_fill(g_ext, True) if isinstance(backend, CudaBackend) and world == 1 else backend.void_fill(g_ext)
         for i in terms:
             if hi > lo:
                 term_grids[i] = backend.grid_mean(g_ext, g_row0, gh, sizes[i], lo, hi - lo)

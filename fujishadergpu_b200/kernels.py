@@ -496,9 +496,11 @@ def grid_mean_band(src, src_row0: int, gh: int, size: int, out_row0: int, out_ro
     return out
 
 
-def grid_void_fill(grid) -> torch.Tensor:
-    """Enclosed-void fill of a whole decimated grid (returns a filled copy)."""
-    t = dev.as_f32_2d(grid).contiguous().clone()
+def grid_void_fill(grid, inplace: bool = False) -> torch.Tensor:
+    """Enclosed-void fill of a whole decimated grid (returns a filled copy, or fills `grid` itself).  The kernels
+    are gated by a device-side "grid has NaN" flag, so the call is cheap on a grid without voids."""
+    t = dev.as_f32_2d(grid)
+    t = t if (inplace and t.is_contiguous()) else t.contiguous().clone()
     gh, gw = int(t.shape[0]), int(t.shape[1])
     sigma = max(1.0, min(gh, gw) / 64.0)
     need = 2 * ((gh * gw * 4 + 255) // 256 * 256) + (int(4 * sigma + 0.5) + 1) * 8 + 2048

@@ -76,6 +76,27 @@ def test_band_stages_equal_whole_raster_bitwise(world):
         assert torch.equal(torch.nan_to_num(whole, nan=-7777.0), torch.nan_to_num(bands, nan=-7777.0)), (world, radii)
 
 
+def test_single_rank_orchestration_equals_whole_raster():
+    """world = 1 through the sharded orchestration (what bench.py times at N = 1: main-pass preparation on a side
+    stream underneath the statistics pre-pass, device-gated void fill) == the sequential whole-raster calls,
+    bit for bit, dense and with all-NaN coarse cells."""
+    from fujishadergpu_b200 import kernels as k
+    from fujishadergpu_b200.core import sharding as sh
+    from fujishadergpu_b200.algorithms._norm_stats import compute_norm_stats_device
+    radii, w = [2, 8, 32, 128, 512, 2048], orc.pow2_weights(6)
+    for nodata in (False, True):
+        dem = orc.synth_dem(2100, 1900, seed=33, nodata=nodata)
+        if nodata:
+            dem[640:800, 512:700] = np.nan        # whole 16 x 16 and 4 x 4 cells without data -> enclosed-void fill
+        d = torch.from_numpy(dem).cuda()
+        st = compute_norm_stats_device(d, "topousm_fast", {"radii": radii, "weights": w, "pixel_size": 1.0})
+        want = k.topousm_fast(d, radii=radii, weights=w, norm_scale=st[0])
+        for _ in range(2):   # second call: warm side stream, same result
+            got, scale = sh.topousm_fast_sharded_with_stats(d, 2100, 0, 1, radii=radii, weights=w, dem_ext=d)
+            assert scale == st[0]
+            assert torch.equal(torch.nan_to_num(got, nan=-7777.0), torch.nan_to_num(want, nan=-7777.0)), nodata
+
+
 def _nccl_worker(rank, world, port, path, out_dir):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
