@@ -46,10 +46,10 @@ struct OpenTable {
 };
 
 __global__ void __launch_bounds__(256) openness_kernel(OpenParams p, const __grid_constant__ OpenTable tab, int fast_halo) {
-  if (fast_halo >= 0) {   // interior 128 x 4 tiles are done by openness_interior_kernel
-    const int64_t tx0 = (int64_t)(blockIdx.x / 2) * 128, ty0 = p.out_row0 + (int64_t)blockIdx.y * 4;
-    if (tx0 >= fast_halo && tx0 + 128 + fast_halo <= p.W && ty0 >= fast_halo && ty0 + 4 + fast_halo <= p.H &&
-        ty0 + 4 <= p.out_row0 + p.out_rows)
+  if (fast_halo >= 0) {   // interior 128 x 8 tiles are done by openness_interior_kernel
+    const int64_t tx0 = (int64_t)(blockIdx.x / 2) * 128, ty0 = p.out_row0 + (int64_t)(blockIdx.y / 2) * 8;
+    if (tx0 >= fast_halo && tx0 + 128 + fast_halo <= p.W && ty0 >= fast_halo && ty0 + 8 + fast_halo <= p.H &&
+        ty0 + 8 <= p.out_row0 + p.out_rows)
       return;
   }
   const int64_t x = (int64_t)blockIdx.x * 64 + (threadIdx.x & 63);
@@ -99,71 +99,71 @@ __global__ void __launch_bounds__(256) openness_kernel(OpenParams p, const __gri
 // Interior tiles (every sample of every pixel lies inside the raster): no bounds checks, linear sample
 // offsets, and (v - c) / dist evaluated as q = d*rinv corrected by one FMA residual step, which returns
 // the correctly rounded quotient (Markstein) -- the same f32 value as the IEEE division of the generic
-// kernel, at a third of the instructions.  Two pixels per thread for more loads in flight.
+// kernel, at a third of the instructions.  Four pixels per thread (2 x 2 at strides 64 / 4): more loads in flight,
+// and the per-sample constant loads, address arithmetic and loop bookkeeping are shared by four pixels.
 template <bool NEG>
 __global__ void __launch_bounds__(256) openness_interior_kernel(const __grid_constant__ OpenParams p,
                                                                 const __grid_constant__ OpenTable tab, int halo) {
-  const int64_t x0 = (int64_t)blockIdx.x * 128, y0 = p.out_row0 + (int64_t)blockIdx.y * 4;
-  // tiles that touch the border band are left to openness_kernel (launched over the same grid)
-  const bool interior = x0 >= halo && x0 + 128 + halo <= p.W && y0 >= halo && y0 + 4 + halo <= p.H &&
-                        y0 + 4 <= p.out_row0 + p.out_rows;
+  const int64_t x0 = (int64_t)blockIdx.x * 128, y0 = p.out_row0 + (int64_t)blockIdx.y * 8;
+  // tiles that touch the border band are left to openness_kernel (launched over the same area)
+  const bool interior = x0 >= halo && x0 + 128 + halo <= p.W && y0 >= halo && y0 + 8 + halo <= p.H &&
+                        y0 + 8 <= p.out_row0 + p.out_rows;
   if (!interior) return;
-  const int64_t x = x0 + (threadIdx.x & 63);     // this thread's pixels: x and x + 64 (coalesced warp loads)
+  // this thread's four pixels: columns x and x + 64 (coalesced warp loads) of rows y and y + 4; the sample
+  // table entry (three constant-bank loads) and the loop bookkeeping are shared by the four
+  const int64_t x = x0 + (threadIdx.x & 63);
   const int64_t y = y0 + (threadIdx.x >> 6);
   const float* pc = p.dem + (y - p.buf_row0) * p.ld_in + x;
-  const float c0 = __ldg(pc), c1 = __ldg(pc + 64);
+  const int64_t down = 4 * p.ld_in;
+  constexpr int NP = 4;
+  float c[NP], asum[NP], acnt[NP];
+  c[0] = __ldg(pc); c[1] = __ldg(pc + 64); c[2] = __ldg(pc + down); c[3] = __ldg(pc + down + 64);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) { asum[j] = 0.f; acnt[j] = 0.f; }
   const float half_pi = (float)(3.14159265358979323846 / 2);
   const float start = NEG ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
-  float asum0 = 0.f, acnt0 = 0.f, asum1 = 0.f, acnt1 = 0.f;
   for (int d = 0; d < p.n_dirs; ++d) {
-    float e0 = start, e1 = start;
+    float e[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) e[j] = start;
     const int k1 = tab.dir_start[d + 1];
 #pragma unroll 5
     for (int k = tab.dir_start[d]; k < k1; ++k) {
       const OpenSample sm = tab.s[k];
-      const float v0 = __ldg(pc + sm.off), v1 = __ldg(pc + sm.off + 64);
-      const float d0 = v0 - c0, d1 = v1 - c1;
-      float q0 = d0 * sm.rinv, q1 = d1 * sm.rinv;
-      const float r0 = fmaf(-q0, sm.dist, d0), r1 = fmaf(-q1, sm.dist, d1);
-      q0 = (r0 == r0) ? fmaf(r0, sm.rinv, q0) : q0;   // residual is NaN only for infinite / NaN quotients
-      q1 = (r1 == r1) ? fmaf(r1, sm.rinv, q1) : q1;
-      // a NaN sample gives a NaN quotient, which fminf / fmaxf ignore: invalid samples drop out by themselves
-      e0 = NEG ? fminf(e0, q0) : fmaxf(e0, q0);
-      e1 = NEG ? fminf(e1, q1) : fmaxf(e1, q1);
+      const float* ps = pc + sm.off;
+      float v[NP];
+      v[0] = __ldg(ps); v[1] = __ldg(ps + 64); v[2] = __ldg(ps + down); v[3] = __ldg(ps + down + 64);
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const float dd = v[j] - c[j];
+        float q = dd * sm.rinv;
+        const float r = fmaf(-q, sm.dist, dd);
+        q = (r == r) ? fmaf(r, sm.rinv, q) : q;   // residual is NaN only for infinite / NaN quotients
+        // a NaN sample gives a NaN quotient, which fminf / fmaxf ignore: invalid samples drop out by themselves
+        e[j] = NEG ? fminf(e[j], q) : fmaxf(e[j], q);
+      }
     }
-    if (e0 != start) {   // at least one valid sample in this direction
-      float a = atanf(e0);
-      a = NEG ? fminf(half_pi, a) : fmaxf(-half_pi, a);
-      asum0 = asum0 + (NEG ? half_pi + a : half_pi - a);
-      acnt0 = acnt0 + 1.f;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      if (e[j] != start) {   // at least one valid sample in this direction
+        float a = atanf(e[j]);
+        a = NEG ? fminf(half_pi, a) : fmaxf(-half_pi, a);
+        asum[j] = asum[j] + (NEG ? half_pi + a : half_pi - a);
+        acnt[j] = acnt[j] + 1.f;
+      }
     }
-    if (e1 != start) {
-      float a = atanf(e1);
-      a = NEG ? fminf(half_pi, a) : fmaxf(-half_pi, a);
-      asum1 = asum1 + (NEG ? half_pi + a : half_pi - a);
-      acnt1 = acnt1 + 1.f;
-    }
-  }
-  float res0, res1;
-  {
-    float o = asum0 / fmaxf(acnt0, 1.f);
-    o = o / half_pi;
-    o = fminf(fmaxf(o, 0.f), 1.f);
-    res0 = powf(o, (float)(1 / 2.2));
-    if (p.stretch) res0 = fmaxf((res0 - p.stretch_lo) / p.stretch_scale, 0.f);
-    if (c0 != c0) res0 = nanf("");
-  }
-  {
-    float o = asum1 / fmaxf(acnt1, 1.f);
-    o = o / half_pi;
-    o = fminf(fmaxf(o, 0.f), 1.f);
-    res1 = powf(o, (float)(1 / 2.2));
-    if (p.stretch) res1 = fmaxf((res1 - p.stretch_lo) / p.stretch_scale, 0.f);
-    if (c1 != c1) res1 = nanf("");
   }
   const int64_t o = (y - p.out_row0) * p.ld_out + x;
-  store_out(p.out, o, res0, p.enc);
-  store_out(p.out, o + 64, res1, p.enc);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    float oo = asum[j] / fmaxf(acnt[j], 1.f);
+    oo = oo / half_pi;
+    oo = fminf(fmaxf(oo, 0.f), 1.f);
+    float res = powf(oo, (float)(1 / 2.2));
+    if (p.stretch) res = fmaxf((res - p.stretch_lo) / p.stretch_scale, 0.f);
+    if (c[j] != c[j]) res = nanf("");
+    store_out(p.out, o + (j & 1) * 64 + (int64_t)(j >> 1) * 4 * p.ld_out, res, p.enc);
+  }
 }
 
 static double py_round(double v) { return nearbyint(v); }  // half-to-even, like Python's round()
@@ -201,7 +201,7 @@ static int run_openness(const float* dem, void* out, const fsg_window* win, int 
       t2.s[k].off = (int)((int64_t)t2.s[k].oy * p.ld_in + t2.s[k].ox);
       t2.s[k].rinv = 1.0f / t2.s[k].dist;
     }
-    dim3 g2((unsigned)((p.W + 127) / 128), grid.y);
+    dim3 g2((unsigned)((p.W + 127) / 128), (unsigned)((p.out_rows + 7) / 8));
     if (p.negative) openness_interior_kernel<true><<<g2, 256, 0, (cudaStream_t)stream>>>(p, t2, D);
     else openness_interior_kernel<false><<<g2, 256, 0, (cudaStream_t)stream>>>(p, t2, D);
     FSG_LAUNCH_OK();
