@@ -1,10 +1,4 @@
-"""Tile-backend class for ambient_occlusion (reference: algorithms/tile/ambient_occlusion.py)."""
-from .._impl_ambient_occlusion import AmbientOcclusionAlgorithm as _DaskAmbientOcclusionAlgorithm
-from .dask_bridge import DaskSharedTileAdapter
+"""AmbientOcclusionAlgorithm of the tile backend, looked up by name in this module (core/tile_processor.py:807-820 of the reference)."""
+from .dask_bridge import tile_adapter_for
 
-
-class AmbientOcclusionAlgorithm(DaskSharedTileAdapter):
-    dask_algorithm_cls = _DaskAmbientOcclusionAlgorithm
-
-
-__all__ = ["AmbientOcclusionAlgorithm"]
+AmbientOcclusionAlgorithm = tile_adapter_for("ambient_occlusion", __name__)

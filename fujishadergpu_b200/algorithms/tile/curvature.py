@@ -1,7 +1,4 @@
-"""Tile-backend class for curvature (reference: algorithms/tile/curvature.py)."""
-from .._impl_curvature import CurvatureAlgorithm as _DaskCurvatureAlgorithm
-from .dask_bridge import DaskSharedTileAdapter
+"""CurvatureAlgorithm of the tile backend, looked up by name in this module (core/tile_processor.py:807-820 of the reference)."""
+from .dask_bridge import tile_adapter_for
 
-
-class CurvatureAlgorithm(DaskSharedTileAdapter):
-    dask_algorithm_cls = _DaskCurvatureAlgorithm
+CurvatureAlgorithm = tile_adapter_for("curvature", __name__)

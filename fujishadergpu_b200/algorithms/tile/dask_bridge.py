@@ -136,3 +136,14 @@ class DaskSharedTileAdapter:
 
     def process(self, dem_gpu, **params):
         return _process_direct(self._algo, self.dask_algorithm_cls.__name__, dem_gpu, params)
+
+
+def tile_adapter_for(name: str, module: str):
+    """The tile-backend class of registry algorithm `name` (core/tile_processor.py finds it by class name in
+    algorithms/tile/<name>.py): a DaskSharedTileAdapter bound to the class registered in dask_registry.ALGORITHMS."""
+    from ..dask_registry import ALGORITHMS
+    algo_cls = type(ALGORITHMS[name])
+    return type(algo_cls.__name__, (DaskSharedTileAdapter,),
+                {"dask_algorithm_cls": algo_cls, "__module__": module,
+                 "__doc__": f"Tile adapter of {name} (direct CUDA block function; reference: algorithms/tile/{name}.py)."})
+

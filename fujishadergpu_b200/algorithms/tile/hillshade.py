@@ -1,7 +1,4 @@
-"""Tile-backend class for hillshade (reference: algorithms/tile/hillshade.py)."""
-from .._impl_hillshade import HillshadeAlgorithm as _DaskHillshadeAlgorithm
-from .dask_bridge import DaskSharedTileAdapter
+"""HillshadeAlgorithm of the tile backend, looked up by name in this module (core/tile_processor.py:807-820 of the reference)."""
+from .dask_bridge import tile_adapter_for
 
-
-class HillshadeAlgorithm(DaskSharedTileAdapter):
-    dask_algorithm_cls = _DaskHillshadeAlgorithm
+HillshadeAlgorithm = tile_adapter_for("hillshade", __name__)

@@ -1,7 +1,4 @@
-"""Tile-backend class for openness (reference: algorithms/tile/openness.py)."""
-from .._impl_openness import OpennessAlgorithm as _DaskOpennessAlgorithm
-from .dask_bridge import DaskSharedTileAdapter
+"""OpennessAlgorithm of the tile backend, looked up by name in this module (core/tile_processor.py:807-820 of the reference)."""
+from .dask_bridge import tile_adapter_for
 
-
-class OpennessAlgorithm(DaskSharedTileAdapter):
-    dask_algorithm_cls = _DaskOpennessAlgorithm
+OpennessAlgorithm = tile_adapter_for("openness", __name__)

@@ -1,7 +1,4 @@
-"""Tile-backend class for slope (reference: algorithms/tile/slope.py)."""
-from .._impl_slope import SlopeAlgorithm as _DaskSlopeAlgorithm
-from .dask_bridge import DaskSharedTileAdapter
+"""SlopeAlgorithm of the tile backend, looked up by name in this module (core/tile_processor.py:807-820 of the reference)."""
+from .dask_bridge import tile_adapter_for
 
-
-class SlopeAlgorithm(DaskSharedTileAdapter):
-    dask_algorithm_cls = _DaskSlopeAlgorithm
+SlopeAlgorithm = tile_adapter_for("slope", __name__)

@@ -1,7 +1,4 @@
-"""Tile-backend class for topousm_fast (reference: algorithms/tile/topousm_fast.py)."""
-from .._impl_topousm_fast import TopoUSMFastAlgorithm as _DaskTopoUSMFastAlgorithm
-from .dask_bridge import DaskSharedTileAdapter
+"""TopoUSMFastAlgorithm of the tile backend, looked up by name in this module (core/tile_processor.py:807-820 of the reference)."""
+from .dask_bridge import tile_adapter_for
 
-
-class TopoUSMFastAlgorithm(DaskSharedTileAdapter):
-    dask_algorithm_cls = _DaskTopoUSMFastAlgorithm
+TopoUSMFastAlgorithm = tile_adapter_for("topousm_fast", __name__)
