@@ -169,6 +169,22 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class stdout_to_stderr:
+    """Context manager: C-level and Python-level writes to stdout go to stderr inside the block."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def run_gpu_arm(a) -> None:
     import torch
     import torch.distributed as dist
@@ -181,9 +197,11 @@ def run_gpu_arm(a) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its version banner / warnings to stdout by default: keep stdout to the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout while the communicator comes up: send file descriptor 1 to
+        # stderr for that moment so that stdout carries the one JSON line only
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
     if world > 1:
         from fujishadergpu_b200.core import sharding
         return sharding.bench_sharded(a, dist, dev, METRIC, UNIT, RADII, _weights(), clock_sampler=ClockSampler,
