@@ -107,6 +107,30 @@ def test_reader_handles_strips_deflate_and_nodata_mask(tmp_path):
     assert np.array_equal(got, want, equal_nan=True)
 
 
+def test_small_and_ragged_rasters_round_trip(tmp_path):
+    for shape in ((1, 1), (3, 700), (513, 5), (512, 512)):
+        a = _sample("int16", shape, seed=shape[0])
+        a[0, 0] = 7
+        n = cw.overview_levels(shape)
+        lv = _levels(a, 0, n)
+        p = str(tmp_path / f"s_{shape[0]}_{shape[1]}.tif")
+        cw.write_tiff_pyramid(p, lv, nodata=0)
+        for li, want in enumerate(lv):
+            got, meta = read_geotiff(p, li)
+            assert got.shape == want.shape and np.array_equal(got, want), (shape, li)
+        assert meta["levels"] == n + 1
+
+
+def test_overview_oracle_nodata_rules():
+    a = np.array([[1, -1, 5, 0], [1, -1, 0, 0], [-1, -1, 0, 0], [1, 0, 0, 0]], np.int16)
+    o = orc.overview_average_2x(a, 0)
+    assert o.tolist() == [[1, 5], [-1, 0]]       # mean 0 collides with NoData -> +1; (-1,-1,1)/3 rounds to 0 -> -1; empty -> 0
+    f = np.array([[1.0, np.nan], [np.nan, np.nan], [2.0, 4.0]], np.float32)
+    assert np.array_equal(orc.overview_average_2x(f), np.array([[1.0], [3.0]], np.float32))
+    u = np.array([[1, 2, 255]], np.uint8)
+    assert orc.overview_average_2x(u, 0).tolist() == [[2, 255]]       # (1 + 2) / 2 = 1.5 -> 2 (half up)
+
+
 def test_overview_level_count():
     assert cw.overview_levels((65536, 65536)) == 8
     assert cw.overview_levels((100, 3)) == 7
@@ -128,6 +152,20 @@ def test_write_cog_from_device_matches_oracle_pyramid(tmp_path, dt):
         got, meta = read_geotiff(p, li)
         assert got.shape == want.shape and np.array_equal(got, want, equal_nan=True), (dt, li)
     assert meta["compression"] == 50000 and meta["bigtiff"]
+
+
+@pytest.mark.gpu
+def test_overview_kernel_nodata_collisions():
+    torch = pytest.importorskip("torch")
+    from fujishadergpu_b200 import kernels as k
+    rng = np.random.default_rng(2)
+    a = rng.integers(-2, 3, size=(301, 257)).astype(np.int16)       # many zeros (NoData) and means that round to 0
+    got = k.overview_average(torch.from_numpy(a).cuda(), 0).cpu().numpy()
+    assert np.array_equal(got, orc.overview_average_2x(a, 0))
+    f = rng.standard_normal((301, 257)).astype(np.float32)
+    f[rng.random(f.shape) < 0.4] = np.nan
+    gotf = k.overview_average(torch.from_numpy(f).cuda()).cpu().numpy()
+    assert np.array_equal(gotf, orc.overview_average_2x(f), equal_nan=True)
 
 
 @pytest.mark.gpu
