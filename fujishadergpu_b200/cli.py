@@ -106,6 +106,19 @@ def resolve_params(args, shape, pixel_size: float, psx: float, psy: float) -> di
     return params
 
 
+def resolve_pixel_scales(pixel_size_arg, meta: dict, shape):
+    """(pixel_size, pixel_scale_x, pixel_scale_y, is_geographic) as run_pipeline injects them
+    (core/dask_processor.py:1188-1221): signed metres per pixel from the raster's metadata (degrees converted at the
+    centre latitude for a geographic CRS); an explicit --pixel-size makes the pixels isotropic, keeps the axis signs
+    and drops the geographic approximation."""
+    from .io.raster_info import metric_pixel_scales
+    sx, sy, mean_m, is_geo, _lat = metric_pixel_scales(meta.get("transform"), meta.get("epsg"), shape)
+    if pixel_size_arg is not None:
+        p = float(pixel_size_arg)
+        return p, (p if sx >= 0 else -p), (p if sy >= 0 else -p), False
+    return float(mean_m), float(sx), float(sy), bool(is_geo)
+
+
 def run(args) -> dict:
     import torch
     from . import kernels as _k
@@ -122,13 +135,9 @@ def run(args) -> dict:
     dem = dem.astype(np.float32, copy=False)
     if nod is not None and nod == nod:
         dem = np.where(np.isclose(dem, np.float32(nod), rtol=0.0, atol=1e-6), np.float32(np.nan), dem)
-    sx = sy = 1.0
-    if meta.get("pixel_scale"):
-        sx, sy = float(meta["pixel_scale"][0]), float(meta["pixel_scale"][1])
-    if args.pixel_size is not None:
-        sx = sy = float(args.pixel_size)
-    pixel_size = float(args.pixel_size) if args.pixel_size is not None else float((abs(sx) + abs(sy)) / 2.0)
-    params = resolve_params(args, dem.shape, pixel_size, +abs(sx), -abs(sy))     # north-up raster: +dx, -dy
+    pixel_size, psx, psy, is_geo = resolve_pixel_scales(args.pixel_size, meta, dem.shape)
+    params = resolve_params(args, dem.shape, pixel_size, psx, psy)
+    params["is_geographic_dem"] = bool(is_geo)
     dev = torch.device(args.device)
     d = torch.from_numpy(np.ascontiguousarray(dem)).pin_memory().to(dev, non_blocking=True)
     t_read = time.perf_counter() - t0

@@ -33,6 +33,27 @@ def test_parser_matches_reference_flags():
     assert prm["max_distance"] == 64 and prm["radii"] == orc.ladder_radii(5000)
 
 
+def test_pixel_scales_from_metadata_match_reference_known_answers():
+    """io/raster_info.py of the reference (values produced by its meters_per_degree /
+    metric_pixel_scales_from_metadata in the build container) and the --pixel-size override rule."""
+    from fujishadergpu_b200.cli import resolve_pixel_scales
+    from fujishadergpu_b200.io.raster_info import meters_per_degree, metric_pixel_scales
+    known = {0.0: (111319.458, 110574.2727), 35.0: (91288.13767578507, 110940.55217300118),
+             60.0: (55799.979000000014, 111412.24020000001), -45.5: (78158.03450200213, 111141.51580157726),
+             89.9: (194.94258232671098, 111693.91386062495)}
+    for lat, want in known.items():
+        assert meters_per_degree(lat) == want
+    geo = (138.0, 1 / 3600, 0.0, 36.0, 0.0, -1 / 3600)
+    assert metric_pixel_scales(geo, 4326, (3600, 3600)) == (25.202599870885926, -30.8193712366885, 28.010985553787215, True, 35.5)
+    assert metric_pixel_scales((0.0, 2.0, 0.0, 10.0, 0.0, -2.0), 6677, (5, 5)) == (2.0, -2.0, 2.0, False, None)
+    with pytest.raises(ValueError):
+        metric_pixel_scales(geo, None, (3600, 3600))          # degree-sized pixels without a CRS
+    assert resolve_pixel_scales(None, {"transform": geo, "epsg": 4326}, (3600, 3600)) == (
+        28.010985553787215, 25.202599870885926, -30.8193712366885, True)
+    assert resolve_pixel_scales(10.0, {"transform": geo, "epsg": 4326}, (3600, 3600)) == (10.0, 10.0, -10.0, False)
+    assert resolve_pixel_scales(None, {}, (10, 10)) == (1.0, 1.0, -1.0, False)
+
+
 def _write_input(path, dem, nodata=-9999.0, px=2.0):
     from fujishadergpu_b200.io.cog_writer import write_tiff_pyramid
     a = np.where(np.isnan(dem), np.float32(nodata), dem).astype(np.float32)
