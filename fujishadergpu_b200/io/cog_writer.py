@@ -7,9 +7,10 @@ OVERVIEW_COUNT=8, NoData 0 (integers) or NaN.  GDAL is not in this image, so thi
 itself: the overview levels come from the GPU (kernels.overview_average, a 2 x 2 valid-mean cascade), the tiles
 are predicted with NumPy and compressed with libzstd (ctypes, one thread per tile row) and the container is
 laid out the way a COG reader expects -- header, every IFD with its tile index first, then the tile data from
-the smallest overview to the full-resolution level.  GDAL's ghost-area hints and tile leaders are not written.
-Parity with GDAL's own AVERAGE kernel is unpinned (no GDAL here); the container is checked by reading it back
-with this module's reader and with Pillow's libtiff (tests/test_cog_io.py).
+the smallest overview to the full-resolution level, with GDAL's structural-metadata "ghost area" after the header
+and its block leaders / trailers, so that GDAL reports LAYOUT=COG.  Parity with GDAL's own AVERAGE kernel and its
+reading of the ghost area are unpinned (no GDAL here); the container is checked by reading it back with this module's
+reader, with io/cog_validator.py and with Pillow's libtiff (tests/test_cog_io.py).
 """
 from __future__ import annotations
 
@@ -30,6 +31,13 @@ COMPRESSION_NONE, COMPRESSION_DEFLATE, COMPRESSION_ZSTD = 1, 8, 50000
 T_BYTE, T_ASCII, T_SHORT, T_LONG, T_DOUBLE, T_LONG8 = 1, 2, 3, 4, 12, 16
 _TYPE_FMT = {T_BYTE: "B", T_ASCII: "s", T_SHORT: "H", T_LONG: "I", T_DOUBLE: "d", T_LONG8: "Q"}
 _TYPE_SIZE = {T_BYTE: 1, T_ASCII: 1, T_SHORT: 2, T_LONG: 4, T_DOUBLE: 8, T_LONG8: 8}
+
+# GDAL's "ghost area" right after the TIFF header: how its COG driver declares the layout (IFDs before the tile
+# data, row-major blocks, every block preceded by its size as uint32 and followed by a repeat of its last 4 bytes).
+# A reader that finds it reports LAYOUT=COG (what the reference's io/cog_validator.py:75-82 checks).
+GDAL_GHOST_BODY = (b"LAYOUT=IFDS_BEFORE_DATA\nBLOCK_ORDER=ROW_MAJOR\nBLOCK_LEADER=SIZE_AS_UINT4\n"
+                   b"BLOCK_TRAILER=LAST_4_BYTES_REPEATED\nKNOWN_INCOMPATIBLE_EDITION=NO\n ")
+GDAL_GHOST = b"GDAL_STRUCTURAL_METADATA_SIZE=%06d bytes\n" % len(GDAL_GHOST_BODY) + GDAL_GHOST_BODY
 
 _zstd = None
 
@@ -200,7 +208,7 @@ def _sample_format(dt: np.dtype) -> int:
 
 def write_tiff_pyramid(path: str, levels: Sequence, *, nodata=None, transform=None, epsg=None, blocksize: int = 512,
                        compress: str = "zstd", level: int = 1, bigtiff: bool = True, num_threads: Optional[int] = None,
-                       row_reader=None) -> dict:
+                       row_reader=None, gdal_ghost: bool = True) -> dict:
     """Write levels[0] (full resolution) and levels[1:] (overviews, each a NumPy array or any object with .shape /
     .dtype whose rows `row_reader(level_obj, r0, r1)` returns as a NumPy array) as one tiled (Big)TIFF."""
     comp = {"zstd": COMPRESSION_ZSTD, "deflate": COMPRESSION_DEFLATE, "none": COMPRESSION_NONE}[compress]
@@ -241,7 +249,8 @@ def write_tiff_pyramid(path: str, levels: Sequence, *, nodata=None, transform=No
         if nodata is not None:
             ifd.add(TAG_GDAL_NODATA, T_ASCII, _nodata_text(nodata))
         ifds.append(ifd)
-    header = 16 if bigtiff else 8
+    header = (16 if bigtiff else 8) + (len(GDAL_GHOST) if gdal_ghost else 0)
+    header = (header + 7) // 8 * 8
     ifd_off = []
     pos = header
     for ifd in ifds:
@@ -281,10 +290,16 @@ def write_tiff_pyramid(path: str, levels: Sequence, *, nodata=None, transform=No
                         t = full
                     tiles.append(np.ascontiguousarray(t))
                 for blob in pool.map(encode_tile, tiles):
+                    if gdal_ghost:       # leader: size as uint32; trailer: the last 4 bytes once more
+                        fh.write(struct.pack("<I", len(blob)))
+                        cur += 4
                     fh.write(blob)
                     offs.append(cur)
                     cnts.append(len(blob))
                     cur += len(blob)
+                    if gdal_ghost:
+                        fh.write(blob[-4:])
+                        cur += len(blob[-4:])
             off_t = T_LONG8 if bigtiff else T_LONG
             ifds[li].set_payload(TAG_TILEOFFS, off_t, offs)
             ifds[li].set_payload(TAG_TILECOUNTS, off_t, cnts)
@@ -293,6 +308,8 @@ def write_tiff_pyramid(path: str, levels: Sequence, *, nodata=None, transform=No
             raise ValueError("file exceeds 4 GiB: use bigtiff=True")
         fh.seek(0)
         fh.write(struct.pack("<2sHHHQ", b"II", 43, 8, 0, ifd_off[0]) if bigtiff else struct.pack("<2sHI", b"II", 42, ifd_off[0]))
+        if gdal_ghost:
+            fh.write(GDAL_GHOST)
         for i, ifd in enumerate(ifds):
             fh.seek(ifd_off[i])
             fh.write(ifd.serialise(ifd_off[i], ifd_off[i + 1] if i + 1 < len(ifds) else 0))

@@ -66,8 +66,20 @@ def test_pyramid_round_trip_and_layout(tmp_path, dt):
     first_data = min(min(i[324]) for i in ifds)
     with open(p, "rb") as fh:
         head = fh.read(16)
-    assert struct.unpack("<Q", head[8:16])[0] == 16 and first_data > 16
+    ifd0 = struct.unpack("<Q", head[8:16])[0]
+    assert ifd0 == (16 + len(cw.GDAL_GHOST) + 7) // 8 * 8 and first_data > ifd0
     assert max(ifds[3][324]) < min(ifds[2][324]) and max(ifds[1][324]) < min(ifds[0][324])
+    # GDAL's structural metadata right after the header, block leaders / trailers, and the validator's verdict
+    from fujishadergpu_b200.io.cog_validator import inspect_cog, validate_cog
+    with open(p, "rb") as fh:
+        fh.seek(16)
+        assert fh.read(43) == b"GDAL_STRUCTURAL_METADATA_SIZE=000140 bytes\n"
+    info = inspect_cog(p)
+    assert info["tiled"] and info["ghost"] and info["leaders_ok"] and info["ifds_before_data"] and info["overview_data_first"]
+    assert info["overviews"] == 3 and info["block"] == (512, 512) and info["score"] == 90 and validate_cog(p)
+    plain = str(tmp_path / f"{dt}_plain.tif")
+    cw.write_tiff_pyramid(plain, lv[:1], nodata=nod, gdal_ghost=False)
+    assert not validate_cog(plain) and inspect_cog(plain)["score"] == 40
 
 
 def test_pillow_decodes_the_same_pixels(tmp_path):
