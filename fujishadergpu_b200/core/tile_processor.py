@@ -67,6 +67,18 @@ def _required_padding_for_algorithm(algorithm: str, algo_params: dict, sigma: fl
     return max(32, ((required + 31) // 32) * 32)
 
 
+def _format_algorithm_output(result_core: np.ndarray, algorithm: str):
+    """reference core/tile_processor.py:606-624 -- host-side format of a finished tile: float32, NaN as the NoData
+    of every float output, hillshade clipped to [0, 1] (NaN survives the clip) with an RGB(A)-last result reduced to
+    its first band.  -> (array, nodata)"""
+    out = np.asarray(result_core).astype(np.float32, copy=False)
+    if algorithm == "hillshade":
+        if out.ndim == 3 and out.shape[-1] in (3, 4) and out.shape[-2:] != out.shape[:2]:
+            out = out[:, :, 0]
+        out = np.clip(out, 0.0, 1.0)
+    return out, float("nan")
+
+
 class HostTilePipeline:
     """Re-usable device/host staging for repeated tiles of one shape (no allocation per call)."""
 

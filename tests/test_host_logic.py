@@ -156,3 +156,30 @@ def test_tile_padding_rules():
     assert pad("openness", {"mode": "spatial", "radii": [256]}, 1.0, 1.0) == 288                     # R + 16
     assert pad("ambient_occlusion", {"mode": "spatial", "radii": [100]}, 1.0, 1.0) == 128            # R + 16
     assert pad("hillshade", {"mode": "local"}, 20.0, 1.0) == 128                                     # 5 sigma
+
+
+def test_format_algorithm_output_nodata_policy():
+    """tests/test_output_nodata_policy.py of the reference: NaN is the NoData of float tiles and survives hillshade's clip."""
+    from fujishadergpu_b200.core.tile_processor import _format_algorithm_output
+    arr = np.array([[0.0, -0.5], [0.2, 1.0]], dtype=np.float32)
+    out, nod = _format_algorithm_output(arr, "topousm_fast")
+    assert out.dtype == np.float32 and np.isnan(nod) and out[0, 0] == 0.0 and out[0, 1] == -0.5
+    arr = np.array([[np.nan, 0.5], [1.2, -0.1]], dtype=np.float32)
+    out, nod = _format_algorithm_output(arr, "hillshade")
+    assert np.isnan(nod) and np.isnan(out[0, 0]) and out[1, 0] == 1.0 and out[1, 1] == 0.0
+    rgb = np.zeros((4, 5, 3), np.float32)
+    rgb[..., 0] = 2.0
+    out, _ = _format_algorithm_output(rgb, "hillshade")
+    assert out.shape == (4, 5) and (out == 1.0).all()
+
+
+def test_ambient_occlusion_sample_table_matches_oracle():
+    from fujishadergpu_b200.kernels import ao_table
+    for ns, radius in ((16, 10.0), (8, 3.5), (12, 6.0), (16, 1.0), (5, 24.0)):
+        ox, oy, dist, fac = ao_table(ns, radius, 30.0, 23.7, -30.9)
+        offs, D = orc.ambient_occlusion_table(ns, radius)
+        assert [(dx, dy) for (_f, dx, dy) in offs] == list(zip(ox.tolist(), oy.tolist()))
+        assert np.array_equal(fac, np.asarray([1.0 - (f * 0.3) for (f, _x, _y) in offs], np.float32))
+        want = [max(float(np.hypot(float(dx) * 23.7, float(dy) * 30.9)), 1e-9) for (_f, dx, dy) in offs]
+        assert np.array_equal(dist, np.asarray(want, np.float32))
+        assert max([max(abs(dx), abs(dy)) for (_f, dx, dy) in offs] + [0]) <= D
