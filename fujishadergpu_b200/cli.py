@@ -61,9 +61,29 @@ def _parse_list(text: Optional[str], typ) -> Optional[List]:
 
 
 def _parse_nodata(text: Optional[str]) -> Optional[float]:
+    """cli/args.py parse_nodata_override: a float, or nan / +nan / -nan."""
     if text is None:
         return None
-    return float("nan") if str(text).strip().lower() == "nan" else float(text)
+    if str(text).strip().lower() in {"nan", "+nan", "-nan"}:
+        return float("nan")
+    try:
+        return float(text)
+    except ValueError as exc:
+        raise ValueError(f"Invalid --nodata value: {text}") from exc
+
+
+def _parse_output_range(text: Optional[str]):
+    """cli/args.py parse_output_range: 'lo,hi' with hi > lo."""
+    if text is None:
+        return None
+    try:
+        lo_s, hi_s = str(text).split(",")
+        lo, hi = float(lo_s), float(hi_s)
+    except (ValueError, TypeError) as exc:
+        raise ValueError(f"Invalid --output-range {text!r}; expected 'lo,hi' (e.g. 0,90).") from exc
+    if not (hi > lo):
+        raise ValueError(f"--output-range requires hi > lo, got {text!r}.")
+    return (lo, hi)
 
 
 def resolve_params(args, shape, pixel_size: float, psx: float, psy: float) -> dict:
@@ -73,14 +93,15 @@ def resolve_params(args, shape, pixel_size: float, psx: float, psy: float) -> di
     weights = _parse_list(args.weights, float)
     algo = args.algorithm
     short = min(int(shape[0]), int(shape[1]))
-    params = {"mode": args.mode, "agg": args.agg, "pixel_size": float(pixel_size), "pixel_scale_x": float(psx),
-              "pixel_scale_y": float(psy), "is_geographic_dem": False}
+    params = {"mode": args.mode, "agg": args.agg, "intensity": args.intensity, "pixel_size": float(pixel_size),
+              "pixel_scale_x": float(psx), "pixel_scale_y": float(psy), "is_geographic_dem": False}
     per_algo = {
         "hillshade": dict(azimuth=args.azimuth, altitude=args.altitude, z_factor=args.z_factor, multiscale=args.multiscale),
         "slope": dict(unit=args.unit),
         "curvature": dict(curvature_type=args.curvature_type),
-        "openness": dict(openness_type=args.openness_type, num_directions=args.num_directions, max_distance=args.max_distance),
-        "ambient_occlusion": dict(num_samples=args.num_samples, radius=float(args.radius), intensity=args.intensity),
+        "openness": dict(radius=args.radius, openness_type=args.openness_type, num_directions=args.num_directions,
+                         max_distance=args.max_distance),
+        "ambient_occlusion": dict(num_samples=args.num_samples, radius=args.radius),
         "topousm_fast": {},
     }
     params.update(per_algo[algo])
@@ -150,10 +171,7 @@ def run(args) -> dict:
     if hasattr(result, "ndim") and result.ndim == 3:
         raise NotImplementedError("--agg stack produces a multi-band raster; the COG writer is single-band")
     if args.output_dtype != "float32":
-        override = None
-        if args.output_range:
-            lo, hi = [float(v) for v in args.output_range.split(",")]
-            override = (lo, hi)
+        override = _parse_output_range(args.output_range)
         rng = resolve_output_range(args.algorithm, params=params, override=override)
         if rng is None:
             raise ValueError(f"{args.algorithm}: --output-dtype {args.output_dtype} needs --output-range lo,hi")

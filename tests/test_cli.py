@@ -31,6 +31,23 @@ def test_parser_matches_reference_flags():
     a = p.parse_args(["in.tif", "out.tif", "--algorithm", "openness", "--max-distance", "64", "--num-directions", "8"])
     prm = resolve_params(a, (5000, 5000), 1.0, 1.0, -1.0)
     assert prm["max_distance"] == 64 and prm["radii"] == orc.ladder_radii(5000)
+    # cli/args.py build_algo_params: universal controls and the per-algorithm knobs
+    a = p.parse_args(["in.tif", "out.tif", "--algorithm", "ambient_occlusion", "--radius", "12", "--num-samples", "8",
+                      "--intensity", "1.5", "--mode", "local"])
+    prm = resolve_params(a, (500, 500), 1.0, 1.0, -1.0)
+    assert (prm["radius"], prm["num_samples"], prm["intensity"], prm["mode"], prm["agg"]) == (12, 8, 1.5, "local", "mean")
+    from fujishadergpu_b200.cli import _parse_nodata, _parse_output_range
+    assert _parse_nodata(None) is None and _parse_nodata("-9999") == -9999.0 and _parse_nodata("+NaN") != _parse_nodata("+NaN")
+    assert _parse_output_range("0,90") == (0.0, 90.0) and _parse_output_range(None) is None
+    for bad in ("90,0", "1", "a,b"):
+        with pytest.raises(ValueError):
+            _parse_output_range(bad)
+    with pytest.raises(ValueError):
+        _parse_nodata("none")
+    from fujishadergpu_b200.algorithms.dask_registry import ALGORITHMS
+    from fujishadergpu_b200.core.tile_processor import DEFAULT_ALGORITHMS
+    choices = next(act.choices for act in p._actions if "--algorithm" in act.option_strings)
+    assert sorted(choices) == sorted(ALGORITHMS) == sorted(DEFAULT_ALGORITHMS)      # tests/test_registry_cli_sync.py
 
 
 def test_pixel_scales_from_metadata_match_reference_known_answers():
