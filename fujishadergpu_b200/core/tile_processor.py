@@ -67,6 +67,48 @@ def _required_padding_for_algorithm(algorithm: str, algo_params: dict, sigma: fl
     return max(32, ((required + 31) // 32) * 32)
 
 
+def _sanitize_spatial_radii_weights_for_tile(algorithm: str, radii, weights, tile_size: int):
+    """reference core/tile_processor.py:102-172 -- integer radii for a tile run of a spatial-mode algorithm, duplicates
+    merged (weights of duplicates summed).  Gaussian-smoothing algorithms: round, at least 1, non-positive entries
+    dropped; ambient_occlusion / openness: at least 2, weights follow their radius, a warning text when the list
+    changed.  -> (radii | None, weights | None, warning | None)"""
+    from .tile_compute import deduplicate_radii_weights
+    if not isinstance(radii, (list, tuple)) or len(radii) == 0:
+        return None, weights, None
+
+    def as_float(v):
+        try:
+            return float(v)
+        except (TypeError, ValueError):
+            return None
+
+    if algorithm not in {"ambient_occlusion", "openness"}:
+        kept = [max(1, int(round(f))) for f in (as_float(v) for v in radii) if f is not None and f > 0]
+        if not kept:
+            return None, weights, None
+        rr, ww = deduplicate_radii_weights(kept, weights)
+        return rr, ww, None
+    kept_r, kept_w = [], []
+    for i, v in enumerate(radii):
+        f = as_float(v)
+        if f is None or int(round(f)) <= 0:
+            continue
+        kept_r.append(max(2, int(round(f))))
+        if isinstance(weights, (list, tuple)) and i < len(weights):
+            w = as_float(weights[i])
+            kept_w.append(0.0 if w is None else w)
+    if not kept_r:
+        return None, None, None
+    rr, ww = deduplicate_radii_weights(kept_r, kept_w if len(kept_w) == len(kept_r) else None)
+    warn = None
+    try:
+        if [int(round(float(v))) for v in radii] != rr:
+            warn = f"Spatial radii de-duplicated for {algorithm}: {list(radii)} -> {rr}"
+    except Exception:
+        pass
+    return rr, ww, warn
+
+
 def _format_algorithm_output(result_core: np.ndarray, algorithm: str):
     """reference core/tile_processor.py:606-624 -- host-side format of a finished tile: float32, NaN as the NoData
     of every float output, hillshade clipped to [0, 1] (NaN survives the clip) with an RGB(A)-last result reduced to

@@ -183,3 +183,23 @@ def test_ambient_occlusion_sample_table_matches_oracle():
         want = [max(float(np.hypot(float(dx) * 23.7, float(dy) * 30.9)), 1e-9) for (_f, dx, dy) in offs]
         assert np.array_equal(dist, np.asarray(want, np.float32))
         assert max([max(abs(dx), abs(dy)) for (_f, dx, dy) in offs] + [0]) <= D
+
+
+def test_sanitize_spatial_radii_weights_for_tile_known_answers():
+    """Outputs of the reference's _sanitize_spatial_radii_weights_for_tile (core/tile_processor.py:102-172), produced
+    in the build container from its source."""
+    from fujishadergpu_b200.core.tile_processor import _sanitize_spatial_radii_weights_for_tile as f
+    known = [
+        (("hillshade", [2, 8.4, 8, 0.2, 32, -1], [1, 2, 3, 4, 5, 6], 1024), ([2, 8, 1, 32], None, None)),
+        (("slope", None, None, 1024), (None, None, None)),
+        (("curvature", [0, -3], None, 512), (None, None, None)),
+        (("openness", [1, 1.4, 8, 8, 300], [0.1, 0.2, 0.3, 0.1, 0.3], 1024),
+         ([2, 8, 300], [0.30000000000000004, 0.4, 0.3],
+          "Spatial radii de-duplicated for openness: [1, 1.4, 8, 8, 300] -> [2, 8, 300]")),
+        (("ambient_occlusion", [4, 16, 64], None, 2048), ([4, 16, 64], None, None)),
+        (("openness", ["x", 5], [1.0, 2.0], 1024), ([5], [1.0], None)),
+        (("openness", [0.2], [1.0], 1024), (None, None, None)),
+        (("hillshade", [4, 16, 64], [0.5, 0.3, 0.2], 1024), ([4, 16, 64], [0.5, 0.3, 0.2], None)),
+    ]
+    for args, want in known:
+        assert f(*args) == want, args
