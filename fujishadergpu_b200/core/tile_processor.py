@@ -109,6 +109,29 @@ def _sanitize_spatial_radii_weights_for_tile(algorithm: str, radii, weights, til
     return rr, ww, warn
 
 
+def _load_algorithm(name: str):
+    """reference core/tile_processor.py:807-820 -- the tile backend's plug-in lookup: the class DEFAULT_ALGORITHMS
+    names, found in algorithms/tile/<name>.py, instantiated."""
+    from importlib import import_module
+    cls_name = DEFAULT_ALGORITHMS.get(name)
+    if cls_name is not None:
+        try:
+            cls = getattr(import_module(f"..algorithms.tile.{name}", package=__package__), cls_name, None)
+            if cls is not None:
+                return cls()
+        except ImportError as exc:
+            import logging
+            logging.getLogger(__name__).warning("Failed to load algorithm %s: %s", name, exc)
+    raise ValueError(f"Algorithm {name} not found or not available on this platform")
+
+
+def _replace_nodata_with_nan(data: np.ndarray, nodata):
+    """reference :199-204 -- NoData cells (numeric match within 1e-6, or NaN) become NaN; no NoData value: unchanged."""
+    from .tile_compute import build_nodata_mask
+    mask = build_nodata_mask(data, nodata)
+    return data if mask is None else np.where(mask, np.nan, data)
+
+
 def _format_algorithm_output(result_core: np.ndarray, algorithm: str):
     """reference core/tile_processor.py:606-624 -- host-side format of a finished tile: float32, NaN as the NoData
     of every float output, hillshade clipped to [0, 1] (NaN survives the clip) with an RGB(A)-last result reduced to

@@ -203,3 +203,19 @@ def test_sanitize_spatial_radii_weights_for_tile_known_answers():
     ]
     for args, want in known:
         assert f(*args) == want, args
+
+
+def test_tile_backend_plugin_lookup_and_nodata_replacement():
+    from fujishadergpu_b200.core.tile_processor import DEFAULT_ALGORITHMS, _load_algorithm, _replace_nodata_with_nan
+    from fujishadergpu_b200.algorithms.tile.dask_bridge import DaskSharedTileAdapter
+    for name, cls_name in DEFAULT_ALGORITHMS.items():
+        algo = _load_algorithm(name)
+        assert type(algo).__name__ == cls_name and isinstance(algo, DaskSharedTileAdapter)
+        assert isinstance(algo.get_default_params(), dict)
+    with pytest.raises(ValueError):
+        _load_algorithm("frangi")
+    a = np.array([[1.0, -9999.0], [np.nan, -9999.0000001]], np.float32)
+    out = _replace_nodata_with_nan(a, -9999.0)
+    assert np.array_equal(np.isnan(out), [[False, True], [True, True]]) and out[0, 0] == 1.0
+    assert _replace_nodata_with_nan(a, None) is a
+    assert np.array_equal(np.isnan(_replace_nodata_with_nan(a, float("nan"))), np.isnan(a))
