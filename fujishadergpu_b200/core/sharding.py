@@ -296,17 +296,19 @@ def topousm_sharded_finish(prep: dict, *, weights=None, norm_scale=None, output_
 
 def topousm_fast_sharded_with_stats(band: torch.Tensor, H: int, rank: int, world: int, *, radii, weights=None,
                                     pixel_size=1.0, output_dtype="float32", qp=None, dist=None,
-                                    out: Optional[torch.Tensor] = None, dem_ext: Optional[torch.Tensor] = None):
+                                    out: Optional[torch.Tensor] = None, dem_ext: Optional[torch.Tensor] = None,
+                                    backend=None, block_fn=None, select_fns=None):
     """Statistics pre-pass + main pass of one step.  The scale-independent part of the main pass (halo exchange,
     pyramid, coarse means) is enqueued on a side stream FIRST, so it fills the device while the pre-pass sits in
     its latency-bound stages (bounding box, window gather, the selection's collectives); the fused pass starts
     when both are done.  Every rank issues its NCCL calls in the same program order.  -> (out, scale)"""
     dev = band.device
-    if dev.type != "cuda":
-        scale = sharded_topousm_scale(band, H, rank, world, radii=radii, weights=weights, pixel_size=pixel_size, dist=dist)
+    if dev.type != "cuda":   # host-logic tests (gloo, stand-in compute stages): same stages, one after the other
+        scale = sharded_topousm_scale(band, H, rank, world, radii=radii, weights=weights, pixel_size=pixel_size, dist=dist,
+                                      block_fn=block_fn, select_fns=select_fns)
         return topousm_fast_sharded(band, H, rank, world, radii=radii, weights=weights, pixel_size=pixel_size,
                                     norm_scale=scale, output_dtype=output_dtype, qp=qp, dist=dist, out=out,
-                                    dem_ext=dem_ext), scale
+                                    dem_ext=dem_ext, backend=backend), scale
     cur = torch.cuda.current_stream(dev)
     key = (dev.index, "prep")
     if key not in _PREP_STREAMS:

@@ -155,6 +155,12 @@ def _worker(rank, world, port, dem_path, out_dir, radii, weights, with_stats, ha
                                          select_fns=_numpy_select_fns)
     out = sh.topousm_fast_sharded(band, H, rank, world, radii=radii, weights=weights, norm_scale=scale, dist=dist, backend=be,
                                   dem_ext=ext)
+    if with_stats:   # the one-call form bench.py times must give the same scale and rows
+        out1, scale1 = sh.topousm_fast_sharded_with_stats(
+            band, H, rank, world, radii=radii, weights=weights, dist=dist, dem_ext=ext, backend=be,
+            block_fn=lambda a: torch.from_numpy(orc.topousm_fast_block(a.numpy(), radii=radii, weights=weights)),
+            select_fns=_numpy_select_fns)
+        assert scale1 == scale and torch.equal(torch.nan_to_num(out1, nan=-7.0), torch.nan_to_num(out, nan=-7.0))
     np.save(os.path.join(out_dir, f"out_{rank}.npy"), out.numpy())
     if rank == 0 and with_stats:
         np.save(os.path.join(out_dir, "scale.npy"), np.array([scale if scale is not None else np.nan]))
