@@ -53,6 +53,11 @@ _SIGNATURES = {
     "fsg_topousm_fused_band": (_I, [_P, _L, _L, _L, _L, _L, _P, _L, _L, _L, C.POINTER(C.c_int32),
                                     C.POINTER(C.c_float), _I, _D, C.POINTER(_P), C.POINTER(_L), C.POINTER(_L),
                                     _D, C.POINTER(Encode), _P]),
+    "fsg_topousm_fused_band_workspace_bytes": (C.c_size_t, [_L, _L]),
+    "fsg_topousm_fused_band_ws": (_I, [_P, _L, _L, _L, _L, _L, _P, _L, _L, _L, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_float), _I, _D, C.POINTER(_P), C.POINTER(_L), C.POINTER(_L),
+                                       _D, _P, C.POINTER(Encode), _P, C.c_size_t, _P]),
+    "fsg_debug_reload_switches": (None, []),
     "fsg_topousm_large_part": (_I, [_P, _P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _L, _L, _L, _D, _P]),
     "fsg_openness": (_I, [_P, _P, C.POINTER(Window), _I, _I, _I, _D, _D, _D, _D, _D, C.POINTER(Encode), _P]),
     "fsg_ambient_occlusion_workspace_bytes": (C.c_size_t, [_L, _L]),

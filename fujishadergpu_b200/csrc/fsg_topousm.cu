@@ -56,6 +56,7 @@ struct HostPlan {
   size_t off_tv, off_tw;   // scratch planes (max over users)
   size_t off_taps;         // f64 taps scratch
   size_t off_flags;        // ints: [0..3] level has void cell, [4..7] level still has NaN after fill
+  size_t off_v8flags, v8flag_bytes;   // NaN-block flags of the interior fast path (fused_kernel_v8)
   size_t total;
   int taps_cap;
   int fused_R;             // max fused radius
@@ -146,6 +147,8 @@ static int make_plan(int64_t H, int64_t W, const int32_t* radii, int n, double p
   p->off_tw = off; off = align_up(off + scratch * 4, 256);
   p->off_taps = off; off = align_up(off + (size_t)taps_cap * 8, 256);
   p->off_flags = off; off = align_up(off + 64, 256);
+  p->v8flag_bytes = (size_t)((H + 255) / 256 + 1) * (size_t)(W / 192 + 2) * sizeof(int);
+  p->off_v8flags = off; off = align_up(off + p->v8flag_bytes, 256);
   p->taps_cap = taps_cap;
   p->total = off;
   return FSG_OK;
@@ -463,17 +466,46 @@ struct FusedParams {
   double lvl_cscale[MAX_LEVELS];
   int lvl_gw[MAX_LEVELS];
   float norm_rinv; // f32(1/norm_scale)
-  int norm_mode;   // 0 none, 1 divide by norm_scale, 2 zeros
+  int norm_mode;   // 0 none, 1 divide by norm_scale, 2 zeros, 3 scale read from norm_scale_dev (NaN: none, <= 0: zeros)
   float norm_scale;
+  const float* norm_scale_dev;
   EncodeDev enc;
   int bulk_ok;     // v6: DEM rows are 16-byte aligned (base pointer and row stride) -> bulk async copies
   int out_vec_ok;  // v7: output rows allow 16-byte (f32) / 4-byte (u8) vector stores
   int strip0;      // first column strip to compute (region of interest; 0 for the whole width)
   int64_t roi_col0, roi_cols;   // host side: requested output columns (0, W for the whole width)
+  // v6 rectangle launches (raster borders and NaN blocks next to a v8 launch): strips start at col0, output
+  // columns stop at col_end (0: W); with tile_flags, CTA (bx, by) owns the tile_w x tile_rows tile (bx, by) of the
+  // grid anchored at (col0, tile_row0) and runs only if its flag is set
+  int col0, col_end;
+  const int* tile_flags;
+  int tile_w, tile_rows;
+  int64_t tile_row0, tile_row1;
+  // v8 (interior fast path): strips of V8_TW columns from v8_col0, rows [v8_row0, v8_row1), NaN block flags
+  int v8_col0;
+  int64_t v8_row0, v8_row1;
+  int* v8_flags;
 };
+
+// normalisation resolved on the device: the p99 scale may still be on its way when the launch is enqueued
+struct NormDev {
+  int mode;
+  float sc, rinv;
+};
+__device__ __forceinline__ NormDev resolve_norm(const FusedParams& p) {
+  NormDev n{p.norm_mode, p.norm_scale, p.norm_rinv};
+  if (p.norm_mode == 3) {
+    const float s = *p.norm_scale_dev;
+    if (s != s) n.mode = 0;
+    else if (s > 0.f) { n.mode = 1; n.sc = s; n.rinv = (float)(1.0 / (double)s); }
+    else n.mode = 2;
+  }
+  return n;
+}
 
 __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
   extern __shared__ __align__(16) unsigned char smraw[];
+  const NormDev nd = resolve_norm(p);
   const int R = p.R;
   const int SW = FK_TW + 2 * R;          // strip width incl. halo
   const int SWp = SW | 1;                // odd row stride (bank-conflict-free row-parallel access)
@@ -701,8 +733,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel(FusedParams p) {
       for (int jj = 0; jj < FK_SEG; ++jj) {
         if (jj < hjn) {
           float v = acc[jj];
-          if (p.norm_mode == 1) v = v / p.norm_scale;
-          else if (p.norm_mode == 2) v = (v != v) ? v : 0.f;
+          if (nd.mode == 1) v = v / nd.sc;
+          else if (nd.mode == 2) v = (v != v) ? v : 0.f;
           stage[hi * (FK_TW + 1) + hj0 + jj] = v;
         }
       }
@@ -829,6 +861,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
   constexpr int SEG = FK_TW / NSEG;
   static_assert(SEG * NSEG == FK_TW, "segments must tile the strip");
   extern __shared__ __align__(16) unsigned char smraw[];
+  const NormDev nd = resolve_norm(p);
   const int R = p.R;
   const int SW = FK_TW + 2 * R;
   const int SWp = SW | 1;
@@ -1149,9 +1182,9 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
     float* stage = plane32;   // NB x (FK_TW + 1) floats, inside the plane region
     if (hrow_ok && hjn > 0) {
       float* sp = stage + hi * (FK_TW + 1) + hj0;
-      if (p.norm_mode == 1) {
+      if (nd.mode == 1) {
         // v / s, correctly rounded: q = v*rinv, one FMA residual correction (Markstein); NaN stays NaN
-        const float sc = p.norm_scale, rinv = p.norm_rinv;
+        const float sc = nd.sc, rinv = nd.rinv;
 #pragma unroll
         for (int jj = 0; jj < SEG; ++jj) {
           if (jj < hjn) {
@@ -1160,7 +1193,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) fused_kernel_fast(FusedParams p
             sp[jj] = fmaf(rem, rinv, q);
           }
         }
-      } else if (p.norm_mode == 2) {
+      } else if (nd.mode == 2) {
 #pragma unroll
         for (int jj = 0; jj < SEG; ++jj) if (jj < hjn) sp[jj] = (acc[jj] != acc[jj]) ? acc[jj] : 0.f;
       } else {
@@ -1215,7 +1248,7 @@ static size_t fused_smem_bytes(int R) {
 
 }  // namespace fsg
 #include "fsg_topousm_v6.cuh"
-#include "fsg_topousm_v7.cuh"
+#include "fsg_topousm_v8.cuh"
 namespace fsg {
 
 // ------------------------------------------------------------------------------------------
@@ -1251,49 +1284,24 @@ static int launch_pyramid(const float* dem, int64_t rows, int64_t W, int64_t ld,
   return FSG_OK;
 }
 
-// Fills the per-launch fields of `fp` (kernel variant, grid, shared memory) and launches the fused pass
-// over global output rows [fp.out_row0, +fp.out_rows).
-static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t s) {
-  const int64_t H = fp.H, W = fp.W;
-  fp.R = fused_R;
-  fp.n_lvls = n_levels;
-  if (fp.out_rows <= 0) return FSG_OK;
-  const bool fast_ok = H >= fused_R + 2 && W >= fused_R + 2 && W < (1 << 30) && !getenv("FSG_FORCE_GENERIC");
-  const size_t smem_cap = 227 * 1024;
-  int nb = 0;   // rows per batch of the fast kernel (0: general kernel)
-  int n_fused = 0;
-  for (int i = 0; i < fp.n_terms; ++i) n_fused += fp.terms[i].kind == TERM_BOX_FUSED;
-  const bool v6_ok = fast_ok && fused_R <= 32 && n_levels <= V6_MAXLV && n_fused <= V6_MAXF && !getenv("FSG_FUSED_V5");
-  fp.bulk_ok = (((uintptr_t)fp.dem & 15) == 0 && fp.ld_in % 4 == 0 && !getenv("FSG_NO_BULK")) ? 1 : 0;
-  // v7 (role-split pipeline) is bit-identical but measured 1.6x slower than v6 on B200 (10 warps per SM do not
-  // hide the latencies of either role, see profiles/): opt-in only
-  bool v7_ok = v6_ok && n_fused >= 1 && n_levels <= V7_MAXLV && getenv("FSG_FUSED_V7") != nullptr;
-  for (int l = 0; l < n_levels; ++l) v7_ok = v7_ok && fp.lvl_cscale[l] <= 0.25;   // decimation >= 4 (V7_KMAX cells)
-  {
-    const size_t esz = out_elem_size(fp.enc.kind);
-    const uintptr_t need = fp.enc.kind == FSG_OUT_F32 ? 15 : 3;
-    fp.out_vec_ok = (((uintptr_t)fp.out & need) == 0 && fp.ld_out % 4 == 0 && esz != 2) ? 1 : 0;
-  }
-  // v6 geometry B (640 threads, 12-pixel segments) needs decimation >= 4 for its coarse cell slots
-  bool v6b_ok = v6_ok && getenv("FSG_V6_CFGB") != nullptr;
-  for (int l = 0; l < n_levels; ++l) v6b_ok = v6b_ok && fp.lvl_cscale[l] <= 0.25;
-  if (v7_ok) nb = 7;
-  else if (v6b_ok) nb = 62;
-  else if (v6_ok) nb = 6;
-  else if (fast_ok && fused_fast_smem_bytes<32>(fused_R, n_levels) <= smem_cap) nb = 32;
-  else if (fast_ok && fused_fast_smem_bytes<16>(fused_R, n_levels) <= smem_cap) nb = 16;
-  // bands: few enough that the (2R+1)-row warm-up per band stays small, enough CTAs (>= 6 per SM when the
-  // raster allows) that the slower edge strips and the SM-to-SM spread average out.  (A "fewest waves"
-  // model was tried and lost 25 %: one or two waves leave the chip waiting for the edge-strip CTAs.)
-  const int64_t rows = fp.out_rows;
-  const int tw = nb == 7 ? V7_TW : (nb == 62 ? V6CfgB::TW : FK_TW);
-  int64_t strips = (W + tw - 1) / tw;
-  fp.strip0 = 0;
-  if (fp.roi_cols > 0 && fp.roi_cols < W) {   // only the strips that overlap the requested columns
-    const int64_t s_lo = fp.roi_col0 / tw, s_hi = (fp.roi_col0 + fp.roi_cols + tw - 1) / tw;
-    fp.strip0 = (int)s_lo;
-    strips = s_hi - s_lo;
-  }
+// Debug switches, read once per process (FSG_FORCE_GENERIC, FSG_FUSED_V5, FSG_NO_BULK, FSG_V6_CFGB, FSG_NO_V8).
+struct FusedSwitches {
+  bool force_generic, v5, no_bulk, cfgb, no_v8;
+  FusedSwitches()
+      : force_generic(getenv("FSG_FORCE_GENERIC") != nullptr), v5(getenv("FSG_FUSED_V5") != nullptr),
+        no_bulk(getenv("FSG_NO_BULK") != nullptr), cfgb(getenv("FSG_V6_CFGB") != nullptr),
+        no_v8(getenv("FSG_NO_V8") != nullptr) {}
+};
+static const FusedSwitches& fused_switches() {
+  static const FusedSwitches sw;
+  return sw;
+}
+extern "C" void fsg_debug_reload_switches(void) { const_cast<FusedSwitches&>(fused_switches()) = FusedSwitches(); }
+
+// Rows per CTA band: few enough that the (2R+1)-row warm-up per band stays small, enough CTAs (>= 6 per SM when
+// the raster allows) that the slower edge strips and the SM-to-SM spread average out.  (A "fewest waves" model
+// was tried and lost 25 %: one or two waves leave the chip waiting for the edge-strip CTAs.)
+static int64_t fused_band_rows(int64_t rows, int64_t strips, int fused_R, int64_t multiple) {
   int64_t want_bands = (rows + 1023) / 2048;
   if (want_bands < 1) want_bands = 1;
   const int64_t min_rows = 8 * (int64_t)(2 * fused_R + 1);
@@ -1302,8 +1310,155 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
   while (strips * want_bands < 148 && (rows + 2 * want_bands - 1) / (2 * want_bands) >= 3 * (int64_t)(2 * fused_R + 1))
     want_bands *= 2;
   int64_t band_rows = (rows + want_bands - 1) / want_bands;
-  band_rows = (band_rows + FK_NB - 1) / FK_NB * FK_NB;
+  band_rows = (band_rows + multiple - 1) / multiple * multiple;
   if (band_rows > (1 << 30)) band_rows = 1 << 30;
+  return band_rows;
+}
+
+// One fused_kernel_v6 launch over output rows [r0, r1) x columns [c0, c1) of the raster (`base` describes the
+// whole call; its out pointer belongs to row base.out_row0).
+static int launch_v6_rect(const FusedParams& base, int64_t r0, int64_t r1, int64_t c0, int64_t c1, cudaStream_t s) {
+  if (r1 <= r0 || c1 <= c0) return FSG_OK;
+  FusedParams fp = base;
+  fp.out = (unsigned char*)base.out + (size_t)(r0 - base.out_row0) * (size_t)base.ld_out * out_elem_size(base.enc.kind);
+  fp.out_row0 = r0;
+  fp.out_rows = r1 - r0;
+  fp.strip0 = 0;
+  fp.col0 = (int)c0;
+  fp.col_end = (int)c1;
+  fp.tile_flags = nullptr;
+  if (c0 % 4 != 0) fp.bulk_ok = 0;
+  const int64_t strips = (c1 - c0 + FK_TW - 1) / FK_TW;
+  const int64_t band_rows = fused_band_rows(fp.out_rows, strips, fp.R, FK_NB);
+  fp.band_rows = (int)band_rows;
+  const int64_t bands = (fp.out_rows + band_rows - 1) / band_rows;
+  if (bands > 65535) return fail(FSG_E_UNSUPPORTED, "fsg_topousm_fast: raster too tall");
+  const size_t smem = V6Geom<32, V6CfgA>::BYTES;
+  FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v6<32, V6CfgA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fused_kernel_v6<32, V6CfgA><<<dim3((unsigned)strips, (unsigned)bands), V6Geom<32, V6CfgA>::THREADS, smem, s>>>(fp);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+// bytes of the v8 NaN-block flags for a raster (or band) of H x W
+static size_t v8_flag_bytes(int64_t rows, int64_t W) {
+  return (size_t)((rows + V8_BLK - 1) / V8_BLK + 1) * (size_t)(W / V8_TW + 2) * sizeof(int);
+}
+
+// Interior fast path: fused_kernel_v8 on the rows / strips whose whole neighbourhood lies inside the raster (and
+// inside the DEM rows the caller holds), fused_kernel_v6 on the four border rectangles and on the 256-row
+// blocks v8 flagged (NaN or Inf in reach).  Returns 1 when the launch was taken, 0 when v8 does not apply.
+static int launch_fused_v8(FusedParams& fp, int* flags, size_t flag_bytes, cudaStream_t s, int* rc_out) {
+  *rc_out = FSG_OK;
+  const int64_t H = fp.H, W = fp.W;
+  if (fp.n_terms < 3 || fp.n_terms > 3 + V8_MAXC || !fp.bulk_ok || !flags) return 0;
+  if (fp.terms[0].kind != TERM_BOX_FUSED || fp.terms[0].r != 2 || fp.terms[1].kind != TERM_BOX_FUSED ||
+      fp.terms[1].r != 8 || fp.terms[2].kind != TERM_BOX_FUSED || fp.terms[2].r != 32)
+    return 0;
+  for (int i = 3; i < fp.n_terms; ++i)   // decimated terms only, decimation >= 4 (staged coarse cells: V8_CROWS x V8_CCOLS)
+    if (fp.terms[i].kind != TERM_COARSE || fp.terms[i].cscale > 0.25 || fp.terms[i].rscale > 0.25) return 0;
+  const int64_t R0 = fp.out_row0, R1 = fp.out_row0 + fp.out_rows;
+  int64_t C0 = 0, C1 = W;
+  if (fp.roi_cols > 0 && fp.roi_cols < W) { C0 = fp.roi_col0; C1 = fp.roi_col0 + fp.roi_cols; }
+  const int64_t lo = fp.dem_row0 > 0 ? fp.dem_row0 : 0;
+  const int64_t hi = fp.dem_row0 + fp.dem_rows < H ? fp.dem_row0 + fp.dem_rows : H;
+  // rows: the window of row y needs rows y - 32 .. y + 32 (a batch of 16 rows: the five ring groups around it)
+  int64_t Ya = R0 > lo + V8_RH ? R0 : lo + V8_RH;
+  int64_t ymax = R1 < hi - V8_RH ? R1 : hi - V8_RH;
+  int64_t Yb = Ya + (ymax - Ya) / V8_NB * V8_NB;
+  // columns: strips of V8_TW from a multiple of 4 (16-byte aligned bulk copies) with 32 columns on either side
+  int64_t Xa = C0 > V8_RH ? C0 : V8_RH;
+  Xa = (Xa + 3) / 4 * 4;
+  int64_t xmax = C1 < W - V8_RH ? C1 : W - V8_RH;
+  const int64_t n8 = xmax > Xa ? (xmax - Xa) / V8_TW : 0;
+  const int64_t Xb = Xa + n8 * V8_TW;
+  if (n8 < 1 || Yb - Ya < 4 * V8_NB) return 0;
+  const int64_t nblk = (Yb - Ya + V8_BLK - 1) / V8_BLK;
+  if ((size_t)nblk * (size_t)n8 * sizeof(int) > flag_bytes) return 0;
+
+  int slot = prof_begin(PROF_TOPOUSM_FUSED, s);
+  auto done = [&](int rc) { prof_end(slot, s); *rc_out = rc; return 1; };
+  if (cudaMemsetAsync(flags, 0, (size_t)nblk * (size_t)n8 * sizeof(int), s) != cudaSuccess)
+    return done(fail(FSG_E_CUDA, "fsg_topousm_fast: clearing the block flags failed"));
+  fp.v8_col0 = (int)Xa; fp.v8_row0 = Ya; fp.v8_row1 = Yb; fp.v8_flags = flags;
+  fp.col0 = 0; fp.col_end = 0; fp.tile_flags = nullptr; fp.strip0 = 0;
+  int64_t band_rows = fused_band_rows(Yb - Ya, n8, V8_RH, V8_BLK);
+  fp.band_rows = (int)band_rows;
+  const int64_t bands = (Yb - Ya + band_rows - 1) / band_rows;
+  if (bands > 65535) return done(fail(FSG_E_UNSUPPORTED, "fsg_topousm_fast: raster too tall"));
+  void (*kern)(FusedParams) = fp.n_terms == 3 ? fused_kernel_v8<0> : (fp.n_terms == 4 ? fused_kernel_v8<1> : (fp.n_terms == 5 ? fused_kernel_v8<2> : fused_kernel_v8<3>));
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V8Smem::BYTES) != cudaSuccess)
+    return done(fail(FSG_E_CUDA, "fsg_topousm_fast: shared-memory attribute of the v8 kernel"));
+  kern<<<dim3((unsigned)n8, (unsigned)bands), V8_THREADS, V8Smem::BYTES, s>>>(fp);
+  count_launch();
+  if (cudaPeekAtLastError() != cudaSuccess)
+    return done(fail(FSG_E_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(cudaPeekAtLastError()), __FILE__, __LINE__));
+  // blocks v8 flagged: same tiles on v6
+  {
+    FusedParams tp = fp;
+    tp.tile_flags = flags; tp.tile_w = V8_TW; tp.tile_rows = V8_BLK; tp.tile_row0 = Ya; tp.tile_row1 = Yb;
+    tp.col0 = (int)Xa; tp.col_end = (int)Xb;
+    const size_t smem = V6Geom<32, V6CfgA>::BYTES;
+    if (cudaFuncSetAttribute(fused_kernel_v6<32, V6CfgA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return done(fail(FSG_E_CUDA, "fsg_topousm_fast: shared-memory attribute of the v6 kernel"));
+    fused_kernel_v6<32, V6CfgA><<<dim3((unsigned)n8, (unsigned)nblk), V6Geom<32, V6CfgA>::THREADS, smem, s>>>(tp);
+    count_launch();
+    if (cudaPeekAtLastError() != cudaSuccess)
+      return done(fail(FSG_E_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(cudaPeekAtLastError()), __FILE__, __LINE__));
+  }
+  // raster borders (and rows / columns outside the v8 grid)
+  int rc;
+  if ((rc = launch_v6_rect(fp, R0, Ya, C0, C1, s))) return done(rc);
+  if ((rc = launch_v6_rect(fp, Yb, R1, C0, C1, s))) return done(rc);
+  if ((rc = launch_v6_rect(fp, Ya, Yb, C0, Xa, s))) return done(rc);
+  if ((rc = launch_v6_rect(fp, Ya, Yb, Xb, C1, s))) return done(rc);
+  return done(FSG_OK);
+}
+
+// Fills the per-launch fields of `fp` (kernel variant, grid, shared memory) and launches the fused pass
+// over global output rows [fp.out_row0, +fp.out_rows).  `v8_flags` (may be NULL): scratch for the interior
+// fast path.
+static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t s, int* v8_flags = nullptr,
+                        size_t v8_flag_cap = 0) {
+  const int64_t H = fp.H, W = fp.W;
+  const FusedSwitches& sw = fused_switches();
+  fp.R = fused_R;
+  fp.n_lvls = n_levels;
+  fp.col0 = 0; fp.col_end = 0; fp.tile_flags = nullptr;
+  if (fp.out_rows <= 0) return FSG_OK;
+  const bool fast_ok = H >= fused_R + 2 && W >= fused_R + 2 && W < (1 << 30) && !sw.force_generic;
+  const size_t smem_cap = 227 * 1024;
+  int nb = 0;   // rows per batch of the fast kernel (0: general kernel)
+  int n_fused = 0;
+  for (int i = 0; i < fp.n_terms; ++i) n_fused += fp.terms[i].kind == TERM_BOX_FUSED;
+  const bool v6_ok = fast_ok && fused_R <= 32 && n_levels <= V6_MAXLV && n_fused <= V6_MAXF && !sw.v5;
+  fp.bulk_ok = (((uintptr_t)fp.dem & 15) == 0 && fp.ld_in % 4 == 0 && !sw.no_bulk) ? 1 : 0;
+  {
+    const size_t esz = out_elem_size(fp.enc.kind);
+    const uintptr_t need = fp.enc.kind == FSG_OUT_F32 ? 15 : 3;
+    fp.out_vec_ok = (((uintptr_t)fp.out & need) == 0 && fp.ld_out % 4 == 0 && esz != 2) ? 1 : 0;
+  }
+  // v6 geometry B (640 threads, 12-pixel segments) needs decimation >= 4 for its coarse cell slots
+  bool v6b_ok = v6_ok && sw.cfgb;
+  for (int l = 0; l < n_levels; ++l) v6b_ok = v6b_ok && fp.lvl_cscale[l] <= 0.25;
+  if (v6_ok && !v6b_ok && !sw.no_v8 && fused_R == 32) {
+    int rc;
+    if (launch_fused_v8(fp, v8_flags, v8_flag_cap, s, &rc)) return rc;
+  }
+  if (v6b_ok) nb = 62;
+  else if (v6_ok) nb = 6;
+  else if (fast_ok && fused_fast_smem_bytes<32>(fused_R, n_levels) <= smem_cap) nb = 32;
+  else if (fast_ok && fused_fast_smem_bytes<16>(fused_R, n_levels) <= smem_cap) nb = 16;
+  const int64_t rows = fp.out_rows;
+  const int tw = nb == 62 ? V6CfgB::TW : FK_TW;
+  int64_t strips = (W + tw - 1) / tw;
+  fp.strip0 = 0;
+  if (fp.roi_cols > 0 && fp.roi_cols < W) {   // only the strips that overlap the requested columns
+    const int64_t s_lo = fp.roi_col0 / tw, s_hi = (fp.roi_col0 + fp.roi_cols + tw - 1) / tw;
+    fp.strip0 = (int)s_lo;
+    strips = s_hi - s_lo;
+  }
+  const int64_t band_rows = fused_band_rows(rows, strips, fused_R, FK_NB);
   fp.band_rows = (int)band_rows;
   int64_t bands = (rows + band_rows - 1) / band_rows;
   if (bands > 65535) return fail(FSG_E_UNSUPPORTED, "fsg_topousm_fast: raster too tall");
@@ -1312,16 +1467,13 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
                          : (nb == 16 ? fused_fast_smem_bytes<16>(fused_R, n_levels) : fused_smem_bytes(fused_R));
   if (nb == 6) smem = V6Geom<32, V6CfgA>::BYTES;
   if (nb == 62) smem = V6Geom<32, V6CfgB>::BYTES;
-  if (nb == 7) smem = V7Geom<32>::BYTES;
-  if (nb == 7) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v7<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else if (nb == 6) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v6<32, V6CfgA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (nb == 6) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v6<32, V6CfgA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (nb == 62) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_v6<32, V6CfgB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (nb == 32) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (nb == 16) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int slot = prof_begin(PROF_TOPOUSM_FUSED, s);
-  if (nb == 7) fused_kernel_v7<32><<<grid, V7_THREADS, smem, s>>>(fp);
-  else if (nb == 6) fused_kernel_v6<32, V6CfgA><<<grid, V6Geom<32, V6CfgA>::THREADS, smem, s>>>(fp);
+  if (nb == 6) fused_kernel_v6<32, V6CfgA><<<grid, V6Geom<32, V6CfgA>::THREADS, smem, s>>>(fp);
   else if (nb == 62) fused_kernel_v6<32, V6CfgB><<<grid, V6Geom<32, V6CfgB>::THREADS, smem, s>>>(fp);
   else if (nb == 32) fused_kernel_fast<32><<<grid, FK_THREADS, smem, s>>>(fp);
   else if (nb == 16) fused_kernel_fast<16><<<grid, FK_THREADS, smem, s>>>(fp);
@@ -1412,15 +1564,15 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
       d.grid = mean; d.gh = H; d.gw = W;
     }
   }
-  return launch_fused(fp, plan.fused_R, plan.n_levels, s);
+  return launch_fused(fp, plan.fused_R, plan.n_levels, s, (int*)(base + plan.off_v8flags), plan.v8flag_bytes);
 }
 
 // ---- row-band shard entry points (multi-GPU; see fujishadergpu_b200/core/sharding.py) ------------
 static int run_fused_band(const float* dem, int64_t dem_row0, int64_t dem_rows, int64_t H, int64_t W, int64_t ld_in,
                           void* out, int64_t out_row0, int64_t out_rows, int64_t ld_out, const int32_t* radii,
                           const float* weights, int n, double pixel_size, const float* const* grids,
-                          const int64_t* grow0, const int64_t* grows, double norm_scale, const fsg_encode* enc,
-                          cudaStream_t s) {
+                          const int64_t* grow0, const int64_t* grows, double norm_scale, const float* norm_scale_dev,
+                          const fsg_encode* enc, void* ws, size_t ws_bytes, cudaStream_t s) {
   HostPlan plan;
   int rc = make_plan(H, W, radii, n, pixel_size, &plan);
   if (rc) return rc;
@@ -1439,6 +1591,7 @@ static int run_fused_band(const float* dem, int64_t dem_row0, int64_t dem_rows, 
   fp.n_terms = n;
   fp.enc = make_encode(enc);
   set_norm(fp, norm_scale);
+  if (norm_scale_dev) { fp.norm_mode = 3; fp.norm_scale_dev = norm_scale_dev; }
   for (int i = 0; i < n; ++i) {
     const HostTerm& t = plan.terms[i];
     DevTerm& d = fp.terms[i];
@@ -1469,7 +1622,9 @@ static int run_fused_band(const float* dem, int64_t dem_row0, int64_t dem_rows, 
       }
     }
   }
-  return launch_fused(fp, plan.fused_R, plan.n_levels, s);
+  const size_t need = v8_flag_bytes(out_rows, W);
+  const bool ws_ok = ws && ws_bytes >= need && ((uintptr_t)ws & 3) == 0;
+  return launch_fused(fp, plan.fused_R, plan.n_levels, s, ws_ok ? (int*)ws : nullptr, ws_ok ? need : 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1736,7 +1891,28 @@ int fsg_topousm_fused_band(const float* dem, int64_t dem_row0, int64_t dem_rows,
   if (ld_in < W || ld_out < W) return fsg::fail(FSG_E_INVALID, "fsg_topousm_fused_band: row stride smaller than width");
   return fsg::run_fused_band(dem, dem_row0, dem_rows, H, W, ld_in, out, out_row0, out_rows, ld_out, radii_host,
                              weights_host, n_radii, pixel_size, term_grids_host, term_grow0_host, term_grows_host,
-                             norm_scale, enc, (cudaStream_t)stream);
+                             norm_scale, nullptr, enc, nullptr, 0, (cudaStream_t)stream);
+}
+
+#ifdef FSG_V8_TIMERS
+int fsg_debug_v8_timers(unsigned long long* out48) {
+  return cudaMemcpyFromSymbol(out48, fsg::v8_timers, sizeof(unsigned long long) * 48) == cudaSuccess ? 0 : -1;
+}
+#endif
+
+size_t fsg_topousm_fused_band_workspace_bytes(int64_t out_rows, int64_t W) { return fsg::v8_flag_bytes(out_rows, W); }
+
+int fsg_topousm_fused_band_ws(const float* dem, int64_t dem_row0, int64_t dem_rows, int64_t H, int64_t W, int64_t ld_in,
+                              void* out, int64_t out_row0, int64_t out_rows, int64_t ld_out,
+                              const int32_t* radii_host, const float* weights_host, int n_radii, double pixel_size,
+                              const float* const* term_grids_host, const int64_t* term_grow0_host,
+                              const int64_t* term_grows_host, double norm_scale, const float* norm_scale_dev,
+                              const fsg_encode* enc, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!radii_host || !weights_host) return fsg::fail(FSG_E_INVALID, "fsg_topousm_fused_band: radii/weights are NULL");
+  if (ld_in < W || ld_out < W) return fsg::fail(FSG_E_INVALID, "fsg_topousm_fused_band: row stride smaller than width");
+  return fsg::run_fused_band(dem, dem_row0, dem_rows, H, W, ld_in, out, out_row0, out_rows, ld_out, radii_host,
+                             weights_host, n_radii, pixel_size, term_grids_host, term_grow0_host, term_grows_host,
+                             norm_scale, norm_scale_dev, enc, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 

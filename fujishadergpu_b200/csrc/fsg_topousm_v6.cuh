@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(V6Geom<RH, CFG>::THREADS, 1) fused_kernel_v6(F
   constexpr int NB = V6_NB, SEG = G::SEG, SW = G::SW, RS = G::RS, PS = G::PS, NRING = G::NRING;
   constexpr int FK_TW = G::TW, FK_THREADS = G::THREADS, V6_KMAX = G::KMAX;   // (shadow the v5 constants)
   extern __shared__ __align__(16) unsigned char smraw[];
+  const NormDev nd = resolve_norm(p);
   float* ring = reinterpret_cast<float*>(smraw);
   double* plane64 = reinterpret_cast<double*>(smraw + G::OFF_PLANE);
   float* plane32 = reinterpret_cast<float*>(smraw + G::OFF_PLANE);
@@ -106,11 +107,19 @@ __global__ void __launch_bounds__(V6Geom<RH, CFG>::THREADS, 1) fused_kernel_v6(F
   const int tid = threadIdx.x;
   const int W = (int)p.W;
   const int64_t H = p.H;
-  const int x0 = ((int)blockIdx.x + p.strip0) * FK_TW;
-  const int cs0 = x0 - RH;
+  int x0 = p.col0 + ((int)blockIdx.x + p.strip0) * FK_TW;
+  int Wc = p.col_end > 0 ? p.col_end : W;   // output columns stop here (rectangle launches)
   const int64_t out_end = p.out_row0 + p.out_rows;
-  const int64_t yb0 = p.out_row0 + (int64_t)blockIdx.y * p.band_rows;
-  const int64_t yb1 = (yb0 + p.band_rows < out_end) ? yb0 + p.band_rows : out_end;
+  int64_t yb0 = p.out_row0 + (int64_t)blockIdx.y * p.band_rows;
+  int64_t yb1 = (yb0 + p.band_rows < out_end) ? yb0 + p.band_rows : out_end;
+  if (p.tile_flags) {   // flagged tiles only (blocks the interior fast path gave up on)
+    if (p.tile_flags[(size_t)blockIdx.y * gridDim.x + blockIdx.x] == 0) return;
+    x0 = p.col0 + (int)blockIdx.x * p.tile_w;
+    if (x0 + p.tile_w < Wc) Wc = x0 + p.tile_w;
+    yb0 = p.tile_row0 + (int64_t)blockIdx.y * p.tile_rows;
+    yb1 = (yb0 + p.tile_rows < p.tile_row1) ? yb0 + p.tile_rows : p.tile_row1;
+  }
+  const int cs0 = x0 - RH;
   const bool edge_strip = (cs0 < 0) || (cs0 + SW > W);
   const bool bulk = p.bulk_ok && !edge_strip;
 
@@ -130,7 +139,7 @@ __global__ void __launch_bounds__(V6Geom<RH, CFG>::THREADS, 1) fused_kernel_v6(F
   const int hg = tid / NB;     // column segment
   const int hj0 = hg * SEG;
   int hjn = SEG;
-  if (x0 + hj0 + hjn > W) hjn = (W - x0 - hj0 > 0) ? (W - x0 - hj0) : 0;
+  if (x0 + hj0 + hjn > Wc) hjn = (Wc - x0 - hj0 > 0) ? (Wc - x0 - hj0) : 0;
 
   // Column tables of the coarse levels (same for every row of the strip) and the first coarse column of
   // this thread's segment.
@@ -546,9 +555,9 @@ __global__ void __launch_bounds__(V6Geom<RH, CFG>::THREADS, 1) fused_kernel_v6(F
     float* stage = plane32;   // NB x (FK_TW + 1) floats, inside the plane region
     if (hrow_ok && hjn > 0) {
       float* sp = stage + hi * (FK_TW + 1) + hj0;
-      if (p.norm_mode == 1) {
+      if (nd.mode == 1) {
         // v / s, correctly rounded: q = v*rinv, one FMA residual correction (Markstein); NaN stays NaN
-        const float sc = p.norm_scale, rinv = p.norm_rinv;
+        const float sc = nd.sc, rinv = nd.rinv;
 #pragma unroll
         for (int jj = 0; jj < SEG; ++jj) {
           if (jj < hjn) {
@@ -557,7 +566,7 @@ __global__ void __launch_bounds__(V6Geom<RH, CFG>::THREADS, 1) fused_kernel_v6(F
             sp[jj] = fmaf(rem, rinv, q);
           }
         }
-      } else if (p.norm_mode == 2) {
+      } else if (nd.mode == 2) {
 #pragma unroll
         for (int jj = 0; jj < SEG; ++jj) if (jj < hjn) sp[jj] = (acc[jj] != acc[jj]) ? acc[jj] : 0.f;
       } else {
@@ -567,7 +576,7 @@ __global__ void __launch_bounds__(V6Geom<RH, CFG>::THREADS, 1) fused_kernel_v6(F
     }
     __syncthreads();
     {
-      const int ncols = (W - x0) < FK_TW ? (W - x0) : FK_TW;
+      const int ncols = (Wc - x0) < FK_TW ? (Wc - x0) : FK_TW;
       for (int rr = tid / 32; rr < nrows_b; rr += FK_THREADS / 32) {   // one warp per output row
         const float* srow = stage + rr * (FK_TW + 1) + (tid & 31);
         const int64_t obase = (y + rr - p.out_row0) * p.ld_out + x0 + (tid & 31);

@@ -512,9 +512,11 @@ def grid_void_fill(grid, inplace: bool = False) -> torch.Tensor:
 
 def topousm_fused_band(dem_ext, dem_row0: int, H: int, out_row0: int, out_rows: int, *, radii, weights=None,
                        pixel_size=1.0, term_grids=None, term_grow0=None, norm_scale=None, output_dtype="float32",
-                       qp=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       qp=None, out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+                       norm_scale_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fused pass over one row band.  term_grids[i] is None for fused terms, else a window of the term's
-    mean grid whose first row is global grid row term_grow0[i]."""
+    mean grid whose first row is global grid row term_grow0[i].  norm_scale_dev: one f32 on the device that
+    replaces norm_scale at kernel time (the launch does not wait for the statistics pre-pass)."""
     t = dev.as_f32_2d(dem_ext)
     W = int(t.shape[1])
     rr, ww = _radii_weights(radii, weights)
@@ -526,12 +528,25 @@ def topousm_fused_band(dem_ext, dem_row0: int, H: int, out_row0: int, out_rows: 
     ptrs = (C.c_void_p * n)(*[(g.data_ptr() if g is not None else None) for g in grids])
     g0 = (C.c_int64 * n)(*[int(v) if v is not None else 0 for v in (term_grow0 or [0] * n)])
     gn = (C.c_int64 * n)(*[int(g.shape[0]) if g is not None else 0 for g in grids])
-    check(_lib.load().fsg_topousm_fused_band(
+    lib = _lib.load()
+    need = int(lib.fsg_topousm_fused_band_workspace_bytes(int(out_rows), W))
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(max(need, 256), dtype=torch.uint8, device=t.device)
+    if norm_scale_dev is not None and (norm_scale_dev.dtype != torch.float32 or not norm_scale_dev.is_cuda):
+        raise TypeError("norm_scale_dev must be a float32 CUDA tensor")
+    check(lib.fsg_topousm_fused_band_ws(
         _ptr(t), int(dem_row0), int(t.shape[0]), int(H), W, int(t.stride(0)), _ptr(out), int(out_row0), int(out_rows),
         int(out.stride(0)), rr.ctypes.data_as(C.POINTER(C.c_int32)), ww.ctypes.data_as(C.POINTER(C.c_float)), n,
-        float(pixel_size), ptrs, g0, gn, opt(norm_scale), C.byref(enc), C.c_void_p(dev.stream_ptr(t))),
-        "fsg_topousm_fused_band")
+        float(pixel_size), ptrs, g0, gn, opt(norm_scale),
+        C.c_void_p(norm_scale_dev.data_ptr()) if norm_scale_dev is not None else None, C.byref(enc),
+        _ptr(workspace), workspace.numel() * workspace.element_size(), C.c_void_p(dev.stream_ptr(t))),
+        "fsg_topousm_fused_band_ws")
     return out
+
+
+def reload_debug_switches() -> None:
+    """Re-read the FSG_* environment switches (read once per process otherwise)."""
+    _lib.load().fsg_debug_reload_switches()
 
 
 def _chunk_args(views):

@@ -157,7 +157,22 @@ int fsg_topousm_fused_band(const float* dem, int64_t dem_row0, int64_t dem_rows,
                            const float* const* term_grids_host, const int64_t* term_grow0_host,
                            const int64_t* term_grows_host, double norm_scale, const fsg_encode* enc, void* stream);
 
+/* fsg_topousm_fused_band with (1) a scratch area (fsg_topousm_fused_band_workspace_bytes) that lets the interior
+ * fast path run (without it the general kernel does the whole band) and (2) optionally the normalisation scale
+ * read from device memory at kernel time (norm_scale_dev != NULL: *norm_scale_dev replaces norm_scale; NaN: no
+ * normalisation, <= 0: zeros), so that the launch can be enqueued before the p99 of the statistics pre-pass
+ * (algorithms/_norm_stats.py:176-298) has reached the host. */
+size_t fsg_topousm_fused_band_workspace_bytes(int64_t out_rows, int64_t W);
+int fsg_topousm_fused_band_ws(const float* dem, int64_t dem_row0, int64_t dem_rows, int64_t H, int64_t W, int64_t ld_in,
+                              void* out, int64_t out_row0, int64_t out_rows, int64_t ld_out,
+                              const int32_t* radii_host, const float* weights_host, int n_radii, double pixel_size,
+                              const float* const* term_grids_host, const int64_t* term_grow0_host,
+                              const int64_t* term_grows_host, double norm_scale, const float* norm_scale_dev,
+                              const fsg_encode* enc, void* workspace, size_t workspace_bytes, void* stream);
+
 int fsg_grid_void_fill(float* grid, int64_t gh, int64_t gw, void* workspace, size_t workspace_bytes, void* stream);
+/* Re-reads the FSG_* debug environment switches (they are otherwise read once per process). */
+void fsg_debug_reload_switches(void);
 
 /* ---- overview large-radius part (algorithms/_impl_topousm_fast.py:158-186,
  *      algorithms/_nan_utils.py:255-281): out = f32(w_large)*block - bilinear(field) */

@@ -1,0 +1,4 @@
+set -x
+mkdir -p gpurun_out
+cd fujishadergpu_b200/csrc && for f in *.cu; do nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC --expt-relaxed-constexpr -DFSG_V8_TIMERS -I ../../include -c $f -o /tmp/$f.o & done; wait; nvcc -shared -o ../lib/libfsg_b200.so /tmp/*.cu.o -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -cudart shared; cd ../..
+python scratch/v8_timers.py 8192 > gpurun_out/v8_timers.log 2>&1; cat gpurun_out/v8_timers.log
