@@ -58,6 +58,8 @@ _SIGNATURES = {
                                        C.POINTER(C.c_float), _I, _D, C.POINTER(_P), C.POINTER(_L), C.POINTER(_L),
                                        _D, _P, C.POINTER(Encode), _P, C.c_size_t, _P]),
     "fsg_debug_reload_switches": (None, []),
+    "fsg_select_finish_scale": (_I, [_P, _I, C.c_float, C.c_float, _P, _P]),
+    "fsg_valid_bbox": (_I, [_P, _L, _L, _L, _L, _L, _L, _P, _P]),
     "fsg_topousm_large_part": (_I, [_P, _P, _L, _L, _L, _L, _P, _L, _L, _L, _L, _L, _L, _L, _D, _P]),
     "fsg_openness": (_I, [_P, _P, C.POINTER(Window), _I, _I, _I, _D, _D, _D, _D, _D, C.POINTER(Encode), _P]),
     "fsg_ambient_occlusion_workspace_bytes": (C.c_size_t, [_L, _L]),

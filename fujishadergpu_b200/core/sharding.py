@@ -191,9 +191,11 @@ def topousm_fast_sharded(band: torch.Tensor, H: int, rank: int, world: int, *, r
 
 
 def topousm_sharded_prepare(band: torch.Tensor, H: int, rank: int, world: int, *, radii, pixel_size=1.0, dist=None,
-                            backend=None, dem_ext: Optional[torch.Tensor] = None) -> dict:
+                            backend=None, dem_ext: Optional[torch.Tensor] = None, spec: Optional["Speculation"] = None) -> dict:
     """Everything of the sharded main pass that does not depend on the normalisation scale: DEM halo rows,
-    pyramid levels, their halo rows, the coarse means.  topousm_sharded_finish() runs the fused pass."""
+    pyramid levels, their halo rows, the coarse means.  topousm_sharded_finish() runs the fused pass.
+    spec: plan with the remembered "level holds an all-NoData cell" flags instead of reading this step's flags
+    back (the read-back is checked after the step; see Speculation)."""
     backend = backend or CudaBackend()
     W = int(band.shape[1])
     own = band_bounds(H, world)
@@ -238,7 +240,10 @@ def topousm_sharded_prepare(band: torch.Tensor, H: int, rank: int, world: int, *
         else:
             void = flags.clone().to(torch.int32)
             dist.all_reduce(void, op=dist.ReduceOp.MAX)
-            void = void.cpu().tolist()
+            if spec is not None:
+                void = spec.guess(("void", H, W, world, tuple(levels)), void, [0] * len(levels))
+            else:
+                void = void.cpu().tolist()
         for li, f in enumerate(levels):
             gh, gw = (H + f - 1) // f, (W + f - 1) // f
             g_own = [((a + f - 1) // f if b > a else 0, (b + f - 1) // f if b > a else 0) for (a, b) in own]
@@ -282,7 +287,7 @@ def topousm_sharded_prepare(band: torch.Tensor, H: int, rank: int, world: int, *
 
 
 def topousm_sharded_finish(prep: dict, *, weights=None, norm_scale=None, output_dtype="float32", qp=None,
-                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                           out: Optional[torch.Tensor] = None, norm_scale_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """---- 3. fused pass over the own rows (the only part that needs the scale)."""
     r0, r1, W, band = prep["r0"], prep["r1"], prep["W"], prep["band"]
     if r1 <= r0:
@@ -291,7 +296,37 @@ def topousm_sharded_finish(prep: dict, *, weights=None, norm_scale=None, output_
     return prep["backend"].fused(prep["dem_ext"], prep["dem_row0"], prep["H"], r0, r1 - r0, radii=prep["radii"],
                                  weights=weights, pixel_size=prep["pixel_size"], term_grids=prep["term_grids"],
                                  term_grow0=prep["term_grow0"], norm_scale=norm_scale, output_dtype=output_dtype,
-                                 qp=qp, out=out)
+                                 qp=qp, out=out, **({"norm_scale_dev": norm_scale_dev} if norm_scale_dev is not None else {}))
+
+
+def topousm_fast_sharded_step(band: torch.Tensor, H: int, rank: int, world: int, *, radii, weights=None,
+                              pixel_size=1.0, output_dtype="float32", qp=None, dist=None,
+                              out: Optional[torch.Tensor] = None, dem_ext: Optional[torch.Tensor] = None):
+    """One step (statistics pre-pass + main pass) enqueued WITHOUT any host synchronisation: the p99 scale stays on
+    the device (the fused pass reads it there), the data-dependent planning values are speculated (Speculation).
+    -> (out, scale_dev, spec): scale_dev is one f32 (NaN = no valid statistics, output not normalised); the caller
+    must call spec.ok() once the step is enqueued and repeat the step when it returns False."""
+    dev = band.device
+    spec = Speculation()
+    scale_dev = torch.empty(1, dtype=torch.float32, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    key = (dev.index, "prep")
+    if key not in _PREP_STREAMS:
+        _PREP_STREAMS[key] = torch.cuda.Stream(device=dev)
+    side = _PREP_STREAMS[key]
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        prep = topousm_sharded_prepare(band, H, rank, world, radii=radii, pixel_size=pixel_size, dist=dist, dem_ext=dem_ext,
+                                       spec=spec)
+    sharded_topousm_scale(band, H, rank, world, radii=radii, weights=weights, pixel_size=pixel_size, dist=dist,
+                          spec=spec, scale_out=scale_dev)
+    cur.wait_stream(side)
+    for t in [prep["dem_ext"]] + [g for g in prep["term_grids"] if g is not None]:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            t.record_stream(cur)
+    res = topousm_sharded_finish(prep, weights=weights, norm_scale=None, norm_scale_dev=scale_dev,
+                                 output_dtype=output_dtype, qp=qp, out=out)
+    return res, scale_dev, spec
 
 
 def topousm_fast_sharded_with_stats(band: torch.Tensor, H: int, rank: int, world: int, *, radii, weights=None,
@@ -309,21 +344,14 @@ def topousm_fast_sharded_with_stats(band: torch.Tensor, H: int, rank: int, world
         return topousm_fast_sharded(band, H, rank, world, radii=radii, weights=weights, pixel_size=pixel_size,
                                     norm_scale=scale, output_dtype=output_dtype, qp=qp, dist=dist, out=out,
                                     dem_ext=dem_ext, backend=backend), scale
-    cur = torch.cuda.current_stream(dev)
-    key = (dev.index, "prep")
-    if key not in _PREP_STREAMS:
-        _PREP_STREAMS[key] = torch.cuda.Stream(device=dev)
-    side = _PREP_STREAMS[key]
-    side.wait_stream(cur)
-    with torch.cuda.stream(side):
-        prep = topousm_sharded_prepare(band, H, rank, world, radii=radii, pixel_size=pixel_size, dist=dist, dem_ext=dem_ext)
-    scale = sharded_topousm_scale(band, H, rank, world, radii=radii, weights=weights, pixel_size=pixel_size, dist=dist)
-    cur.wait_stream(side)
-    for t in [prep["dem_ext"]] + [g for g in prep["term_grids"] if g is not None]:
-        if isinstance(t, torch.Tensor) and t.is_cuda:
-            t.record_stream(cur)
-    res = topousm_sharded_finish(prep, weights=weights, norm_scale=scale, output_dtype=output_dtype, qp=qp, out=out)
-    return res, scale
+    for _attempt in range(3):
+        res, scale_dev, spec = topousm_fast_sharded_step(band, H, rank, world, radii=radii, weights=weights,
+                                                         pixel_size=pixel_size, output_dtype=output_dtype, qp=qp,
+                                                         dist=dist, out=out, dem_ext=dem_ext)
+        if spec.ok():
+            break
+    scale = float(scale_dev.item())
+    return res, (scale if scale == scale else None)
 
 
 _PREP_STREAMS: dict = {}
@@ -341,7 +369,7 @@ def _np_lerp_percentile(lo: float, hi: float, n: int, q: float) -> Tuple[int, ob
 
 
 def distributed_percentile(chunks, q: float, *, take_abs: bool, finite_only: bool, device, dist=None,
-                           hist_fn=None, rank_info_fn=None, key_to_float=None) -> float:
+                           hist_fn=None, rank_info_fn=None, key_to_float=None, scale_out=None):
     """np.percentile over the union of every rank's `chunks`; all ranks return the same float.
     Exact: 3-level radix select on order-preserving keys, histograms summed with all_reduce."""
     multi = dist is not None and dist.is_initialized() and dist.get_world_size() > 1
@@ -354,7 +382,7 @@ def distributed_percentile(chunks, q: float, *, take_abs: bool, finite_only: boo
             dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MIN)
 
         return k.staged_percentile(chunks, q, take_abs=take_abs, finite_only=finite_only, device=device,
-                                   all_reduce=all_reduce if multi else None)
+                                   all_reduce=all_reduce if multi else None, scale_out=scale_out)
 
     def allsum(t):
         if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
@@ -396,6 +424,50 @@ def distributed_percentile(chunks, q: float, *, take_abs: bool, finite_only: boo
 
 
 # ------------------------------------------------------------------------------------------------
+# planning without host round trips
+# ------------------------------------------------------------------------------------------------
+class Speculation:
+    """A few small, data-dependent integers steer the host-side planning of a step (the valid-data bounding box
+    picks the statistics windows, the all-NoData-cell flags pick the halo geometry of a pyramid level).  Reading
+    them back costs a device synchronisation in the middle of the step.  Instead the step is planned with the values
+    the previous step saw (first step: the dense-raster values), the device values are copied to pinned memory
+    asynchronously, and ok() compares them after everything has been enqueued: a mismatch updates the memory and the
+    caller repeats the step (at most once per change of the data).  The compared values are all-reduced, so every
+    rank takes the same decision."""
+
+    _memory: dict = {}
+    _pinned: dict = {}
+
+    def __init__(self):
+        self.pending = []
+
+    def guess(self, key, dev_values: torch.Tensor, default):
+        dev_values = dev_values.to(torch.int32).contiguous()
+        n = int(dev_values.numel())
+        slot = (key, len(self.pending))
+        pool = Speculation._pinned.setdefault(slot, [])
+        host = pool.pop() if pool else torch.empty(n, dtype=torch.int32, pin_memory=True)
+        host.copy_(dev_values, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev_values.device))
+        val = list(Speculation._memory.get(key, default))
+        self.pending.append((key, slot, host, ev, val))
+        return val
+
+    def ok(self) -> bool:
+        good = True
+        for key, slot, host, ev, val in self.pending:
+            ev.synchronize()
+            seen = [int(v) for v in host.tolist()]
+            Speculation._pinned.setdefault(slot, []).append(host)
+            if seen != [int(v) for v in val]:
+                Speculation._memory[key] = seen
+                good = False
+        self.pending = []
+        return good
+
+
+# ------------------------------------------------------------------------------------------------
 # sharded statistics pre-pass (reference: algorithms/_norm_stats.py:176-298)
 # ------------------------------------------------------------------------------------------------
 def assign_window_owners(wins, own) -> List[int]:
@@ -421,10 +493,13 @@ def assign_window_owners(wins, own) -> List[int]:
 
 
 def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, radii, weights, pixel_size=1.0,
-                          dist=None, grid: int = 3, block_fn=None, select_fns=None) -> Optional[float]:
+                          dist=None, grid: int = 3, block_fn=None, select_fns=None, spec: Optional[Speculation] = None,
+                          scale_out: Optional[torch.Tensor] = None):
     """p99(|raw topousm_fast|) over the reference's stratified full-resolution windows.  Each window is
     evaluated whole by ONE rank (assign_window_owners) after gathering its rows from the owning bands; the
-    percentile over all windows is an exact distributed selection."""
+    percentile over all windows is an exact distributed selection.
+    spec + scale_out (product path): no host synchronisation -- the bounding box is a guess checked later
+    (Speculation) and the scale stays on the device (scale_out, NaN = no scale); returns scale_out."""
     from ..algorithms._norm_stats import _norm_stat_window_geometry, stratified_windows
     W = int(band.shape[1])
     own = band_bounds(H, world)
@@ -433,9 +508,23 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
     # valid-data bounding box from a <=512 px nearest overview of the own rows
     cov = max(1, max(W, H) // 512)
     big = 1 << 40
-    box = torch.tensor([big, -1, big, -1], dtype=torch.int64, device=band.device)  # ymin, ymax, xmin, xmax
     first = ((r0 + cov - 1) // cov) * cov
-    if r1 > first and first // cov < max(1, H // cov):
+    if spec is not None:
+        from .. import kernels as k
+        n_rows = 0
+        if r1 > first and first // cov < max(1, H // cov):
+            n_rows = max(0, min((r1 - first + cov - 1) // cov, max(1, H // cov) - first // cov))
+        n_cols = min((W + cov - 1) // cov, max(1, W // cov))
+        boxd = k.valid_bbox(band, first - r0, cov, n_rows, n_cols, first // cov)
+        if dist is not None and world > 1:
+            dist.all_reduce(boxd, op=dist.ReduceOp.MAX)
+        full = [0, max(1, H // cov) - 1, 0, n_cols - 1]
+        g = spec.guess(("bbox", H, W, world), boxd, [-full[0], full[1], -full[2], full[3]])
+        ymin, ymax, xmin, xmax = -g[0], g[1], -g[2], g[3]
+        box = None
+    else:
+        box = torch.tensor([big, -1, big, -1], dtype=torch.int64, device=band.device)  # ymin, ymax, xmin, xmax
+    if box is not None and r1 > first and first // cov < max(1, H // cov):
         ov = band[first - r0::cov, ::cov][:, : max(1, W // cov)]
         ov = ov[: max(0, min(ov.shape[0], max(1, H // cov) - first // cov))]
         ok = torch.isfinite(ov)
@@ -443,13 +532,17 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
             rows = torch.nonzero(ok.any(dim=1)).flatten() + first // cov
             cols = torch.nonzero(ok.any(dim=0)).flatten()
             box = torch.stack([rows.min(), rows.max(), cols.min(), cols.max()]).to(torch.int64)
-    if dist is not None and world > 1:
-        mn = box[[0, 2]].clone(); mx = box[[1, 3]].clone()
-        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        box = torch.stack([mn[0], mx[0], mn[1], mx[1]])
-    ymin, ymax, xmin, xmax = [int(v) for v in box.cpu().tolist()]
+    if box is not None:
+        if dist is not None and world > 1:
+            mn = box[[0, 2]].clone(); mx = box[[1, 3]].clone()
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            box = torch.stack([mn[0], mx[0], mn[1], mx[1]])
+        ymin, ymax, xmin, xmax = [int(v) for v in box.cpu().tolist()]
     if ymax < 0:
+        if scale_out is not None:
+            scale_out.fill_(float("nan"))
+            return scale_out
         return None
     by0, by1 = ymin * cov, min(H, (ymax + 1) * cov)
     bx0, bx1 = xmin * cov, min(W, (xmax + 1) * cov)
@@ -488,6 +581,9 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
     from .. import _device as _dev
     pooled = [r for r in _dev.run_concurrently([job_for(w) for w in mine], band.device) if r.numel()]
     kw = select_fns(pooled) if select_fns is not None else {}   # tests inject stand-ins for the kernels
+    if scale_out is not None:
+        return distributed_percentile(pooled, 99.0, take_abs=True, finite_only=False, device=band.device, dist=dist,
+                                      scale_out=scale_out)
     s = distributed_percentile(pooled, 99.0, take_abs=True, finite_only=False, device=band.device, dist=dist, **kw)
     if not (s == s) or s <= 1e-9:
         return None
@@ -511,16 +607,23 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
     out = torch.empty((r1 - r0, W), dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
 
-    def step():
-        _res, scale = topousm_fast_sharded_with_stats(band, H, rank, world, radii=radii, weights=weights, dist=dist,
-                                                      out=out, dem_ext=ext)
-        return scale
+    redo = [0]
+
+    def step():   # no host synchronisation inside (see topousm_fast_sharded_step); a wrong guess repeats the step
+        for _attempt in range(3):
+            _res, scale_dev, spec = topousm_fast_sharded_step(band, H, rank, world, radii=radii, weights=weights, dist=dist,
+                                                              out=out, dem_ext=ext)
+            if spec.ok():
+                break
+            redo[0] += 1
+        return scale_dev
 
     for _ in range(a.warmup):
         step()
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
+    redo[0] = 0
     k.reset_launch_count()
     sampler = clock_sampler(dev.index or 0) if (clock_sampler is not None and rank == 0) else None
     if sampler is not None:
@@ -529,9 +632,15 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.steps):
-        scale = step()
+        scale_dev = step()
     ev1.record()
     torch.cuda.synchronize()
+    scale = float(scale_dev.item())
+    csum = torch.zeros(1, dtype=torch.int64, device=dev)
+    for r in range(0, r1 - r0, 8192):
+        csum += out[r:r + 8192].view(torch.int32).sum(dtype=torch.int64)
+    dist.all_reduce(csum, op=dist.ReduceOp.SUM)
+    checksum = int(csum.item()) & ((1 << 64) - 1)
     prof = k.profile_read()
     k.profile_enable(False)
     clocks = sampler.stop() if sampler is not None else None
@@ -582,13 +691,14 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
         px = H * W
         # roofline of the dominant kernel on rank 0: the fused full-resolution kernel over this rank's band
         roofline = None
-        fused = sorted(ms_ for tag, ms_ in prof if tag == 1)
-        if fused and peak is not None:
-            main_fused = fused[-a.steps:]
+        main_fused = [ms_ for tag, ms_ in prof if tag == 1]
+        if main_fused and peak is not None:
+            if len(main_fused) != a.steps + redo[0]:
+                raise RuntimeError(f"profiler recorded {len(main_fused)} main fused passes for {a.steps} steps")
             fms = sum(main_fused) / len(main_fused)
             ach = 8.0 * (r1 - r0) * W / (fms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": ach, "peak": peak[0], "unit": "GB/s", "frac": ach / peak[0],
-                        "traffic": None, "kernel": "fsg::fused_kernel_v6<32> (rank 0 band)", "peak_source": peak[1],
+                        "traffic": None, "kernel": "fsg::fused_kernel_v8<3> + v6 borders (rank 0 band)", "peak_source": peak[1],
                         "algorithmic_bytes_per_px": 8.0, "fused_kernel_ms": fms}
         line = {
             "metric": metric, "value": px / (ms_step * 1e-3) / 1e6, "unit": unit, "n_gpus": world, "steps": a.steps,
@@ -599,7 +709,8 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
                                    "stats pre-pass + main pass per step", "radii": radii, "size": S,
                        "l2_policy": "per-GPU band far larger than the 126 MB L2", "main_pass_ms": main_ms,
                        "stats_prepass_ms": ms_step - main_ms, "main_pass_mpx_s": px / (main_ms * 1e-3) / 1e6,
-                       "scale_p99": scale, "band_rows": r1 - r0},
+                       "scale_p99": scale, "band_rows": r1 - r0, "respeculated_steps": redo[0],
+                       "out_checksum": f"{checksum:016x}"},
             "roofline": roofline, "cpu_baseline": None, "clocks": clocks,
             "e2e": {"value": px / float(dt.item()) / 1e6, "unit": unit, "h2d_bytes_per_step": px * 4,
                     "d2h_bytes_per_step": px, "ms_per_step": float(dt.item()) * 1e3, "output_dtype": "uint8"},

@@ -33,7 +33,7 @@ int gauss_half_taps(double sigma, double* w, int max_radius) {
 // ---- optional per-thread kernel timing (bench.py's roofline measurement) -------------------
 // When enabled, instrumented call sites bracket their dominant kernel with CUDA events recorded on
 // the launch stream; fsg_profile_read() synchronises the events and returns the durations.
-constexpr int PROF_MAX = 256;
+constexpr int PROF_MAX = 4096;   // (a bench step records ~20 launches; 20 steps overflowed the 256 of round 1)
 struct ProfState {
   int enabled = 0;
   int n = 0;

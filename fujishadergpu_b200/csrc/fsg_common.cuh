@@ -19,7 +19,8 @@ void count_launch(int n = 1);
 int fail(int code, const char* fmt, ...);
 int prof_begin(int tag, cudaStream_t s);   // returns a slot (or -1 when profiling is off)
 void prof_end(int slot, cudaStream_t s);
-enum { PROF_TOPOUSM_FUSED = 1, PROF_TOPOUSM_PYRAMID = 2, PROF_TOPOUSM_COARSE = 3, PROF_GRADIENT = 4, PROF_OPENNESS = 5 };
+enum { PROF_TOPOUSM_FUSED = 1, PROF_TOPOUSM_PYRAMID = 2, PROF_TOPOUSM_COARSE = 3, PROF_GRADIENT = 4, PROF_OPENNESS = 5,
+       PROF_TOPOUSM_FUSED_ROI = 6 /* fused pass of a region of interest (statistics windows) */ };
 
 #define FSG_CUDA_OK(expr)                                                              \
   do {                                                                                 \

@@ -414,6 +414,60 @@ __global__ void sel_finish_kernel(const SelState* st, const unsigned long long* 
   result[3] = (double)st->n;
 }
 
+// np.percentile(..., method 'linear') of an f32 sample, finished on the device: virtual index, gamma and the lerp
+// in f32 exactly as NumPy evaluates them (python-int / python-float operands are weak: (n - 1) * q32, diff * gamma
+// and 1 - gamma are f32 operations), then the rule of topousm_fast_stat_func (_normalization.py:22-32): a NaN or
+// a scale <= 1e-9 means "no global scale" -> NaN (the fused kernels read NaN as "do not normalise").
+__global__ void sel_finish_scale_kernel(const SelState* st, const unsigned long long* x, int take_abs, float q32,
+                                        float min_valid, float* scale) {
+  if (threadIdx.x != 0) return;
+  float out = nanf("");
+  if (st->n != 0) {
+    const unsigned long long k = (unsigned long long)st->out[2];
+    const float ak = key_value(st->key_k, take_abs);
+    float ak1 = ak;
+    if (k + 1 < st->n && x[SEL_X_LE] < k + 2) ak1 = key_value((unsigned int)x[SEL_X_NEXT], take_abs);
+    const float vi = __fmul_rn(__ull2float_rn(st->n - 1ull), q32);
+    const float gamma = __fsub_rn(vi, floorf(vi));
+    const float diff = __fsub_rn(ak1, ak);
+    out = __fadd_rn(ak, __fmul_rn(diff, gamma));
+    if (gamma >= 0.5f) out = __fsub_rn(ak1, __fmul_rn(diff, __fsub_rn(1.f, gamma)));
+    if (!(out == out) || out <= min_valid) out = nanf("");
+  }
+  scale[0] = out;
+}
+
+// Bounding box of the finite samples of a strided overview of a row band (algorithms/_norm_stats.py:254-264 looks
+// at a <= 512 px overview): box = (max of -row, max row, max of -col, max col) in overview indices, so that one
+// MAX all-reduce merges the ranks; the caller presets the four words to INT_MIN.
+__global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ band, int64_t ld, int64_t first_row,
+                                                   int64_t cov, int64_t n_rows, int64_t n_cols, int64_t row_index0,
+                                                   int* box) {
+  const int64_t r = blockIdx.x;
+  if (r >= n_rows) return;
+  const float* row = band + (first_row + r * cov) * ld;
+  int cmin = 0x7fffffff, cmax = -1;
+  for (int64_t c = threadIdx.x; c < n_cols; c += 256) {
+    const float v = row[c * cov];
+    if (isfinite(v)) {
+      cmin = cmin < (int)c ? cmin : (int)c;
+      cmax = cmax > (int)c ? cmax : (int)c;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const int a = __shfl_xor_sync(0xffffffffu, cmin, o), b = __shfl_xor_sync(0xffffffffu, cmax, o);
+    cmin = a < cmin ? a : cmin;
+    cmax = b > cmax ? b : cmax;
+  }
+  if ((threadIdx.x & 31) == 0 && cmax >= 0) {
+    const int ri = (int)(row_index0 + r);
+    atomicMax(&box[0], -ri);
+    atomicMax(&box[1], ri);
+    atomicMax(&box[2], -cmin);
+    atomicMax(&box[3], cmax);
+  }
+}
+
 static int fill_chunks(Chunks& c, const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
                        const int64_t* ld_host, int n_chunks, int64_t* total) {
   c.n = n_chunks;
@@ -644,6 +698,27 @@ int fsg_select_finish(void* workspace, int take_abs, double* result_dev, void* s
   using namespace fsg;
   if (!workspace || !result_dev) return fail(FSG_E_INVALID, "fsg_select_finish: bad argument");
   sel_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sel_state(workspace), (const unsigned long long*)workspace, take_abs, result_dev);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_select_finish_scale(void* workspace, int take_abs, float q32, float min_valid, float* scale_dev, void* stream) {
+  using namespace fsg;
+  if (!workspace || !scale_dev) return fail(FSG_E_INVALID, "fsg_select_finish_scale: bad argument");
+  sel_finish_scale_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sel_state(workspace), (const unsigned long long*)workspace,
+                                                              take_abs, q32, min_valid, scale_dev);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_valid_bbox(const float* band, int64_t ld, int64_t first_row, int64_t cov, int64_t n_rows, int64_t n_cols,
+                   int64_t row_index0, int32_t* box_dev, void* stream) {
+  using namespace fsg;
+  if (!band || !box_dev || cov < 1 || n_cols < 0 || n_rows < 0) return fail(FSG_E_INVALID, "fsg_valid_bbox: bad argument");
+  FSG_CUDA_OK(cudaMemsetAsync(box_dev, 0x80, 4 * sizeof(int32_t), (cudaStream_t)stream));   // 0x80808080 < any index
+  if (n_rows == 0 || n_cols == 0) return FSG_OK;
+  if (n_rows > 0x7fffffff) return fail(FSG_E_UNSUPPORTED, "fsg_valid_bbox: overview too tall");
+  bbox_kernel<<<(unsigned)n_rows, 256, 0, (cudaStream_t)stream>>>(band, ld, first_row, cov, n_rows, n_cols, row_index0, box_dev);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }

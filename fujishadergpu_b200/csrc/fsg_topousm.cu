@@ -1376,7 +1376,8 @@ static int launch_fused_v8(FusedParams& fp, int* flags, size_t flag_bytes, cudaS
   const int64_t nblk = (Yb - Ya + V8_BLK - 1) / V8_BLK;
   if ((size_t)nblk * (size_t)n8 * sizeof(int) > flag_bytes) return 0;
 
-  int slot = prof_begin(PROF_TOPOUSM_FUSED, s);
+  const bool is_roi = (fp.roi_cols > 0 && fp.roi_cols < W) || (fp.dem_rows == H && fp.out_rows < H);
+  int slot = prof_begin(is_roi ? PROF_TOPOUSM_FUSED_ROI : PROF_TOPOUSM_FUSED, s);
   auto done = [&](int rc) { prof_end(slot, s); *rc_out = rc; return 1; };
   if (cudaMemsetAsync(flags, 0, (size_t)nblk * (size_t)n8 * sizeof(int), s) != cudaSuccess)
     return done(fail(FSG_E_CUDA, "fsg_topousm_fast: clearing the block flags failed"));
@@ -1472,7 +1473,8 @@ static int launch_fused(FusedParams& fp, int fused_R, int n_levels, cudaStream_t
   else if (nb == 32) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (nb == 16) FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel_fast<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else FSG_CUDA_OK(cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int slot = prof_begin(PROF_TOPOUSM_FUSED, s);
+  const bool is_roi = (fp.roi_cols > 0 && fp.roi_cols < W) || (fp.dem_rows == H && fp.out_rows < H);
+  int slot = prof_begin(is_roi ? PROF_TOPOUSM_FUSED_ROI : PROF_TOPOUSM_FUSED, s);
   if (nb == 6) fused_kernel_v6<32, V6CfgA><<<grid, V6Geom<32, V6CfgA>::THREADS, smem, s>>>(fp);
   else if (nb == 62) fused_kernel_v6<32, V6CfgB><<<grid, V6Geom<32, V6CfgB>::THREADS, smem, s>>>(fp);
   else if (nb == 32) fused_kernel_fast<32><<<grid, FK_THREADS, smem, s>>>(fp);

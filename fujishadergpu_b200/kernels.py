@@ -544,6 +544,18 @@ def topousm_fused_band(dem_ext, dem_row0: int, H: int, out_row0: int, out_rows: 
     return out
 
 
+def valid_bbox(band, first_row: int, cov: int, n_rows: int, n_cols: int, row_index0: int,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int32[4] on the device: (max of -row, max row, max of -col, max col) over the finite samples of the overview
+    band[first_row + i * cov, j * cov] (row indices offset by row_index0); INT_MIN-like when nothing is finite."""
+    t = dev.as_f32_2d(band)
+    if out is None:
+        out = torch.empty(4, dtype=torch.int32, device=t.device)
+    check(_lib.load().fsg_valid_bbox(_ptr(t), int(t.stride(0)), int(first_row), int(cov), int(n_rows), int(n_cols),
+                                     int(row_index0), _ptr(out), C.c_void_p(dev.stream_ptr(t))), "fsg_valid_bbox")
+    return out
+
+
 def reload_debug_switches() -> None:
     """Re-read the FSG_* environment switches (read once per process otherwise)."""
     _lib.load().fsg_debug_reload_switches()
@@ -585,11 +597,14 @@ def key_to_float(key: int, take_abs: bool) -> float:
     return float(_lib.load().fsg_key_to_float(int(key), 1 if take_abs else 0))
 
 
-def staged_percentile(chunks, q: float, *, take_abs: bool, finite_only: bool, device, all_reduce=None) -> float:
+def staged_percentile(chunks, q: float, *, take_abs: bool, finite_only: bool, device, all_reduce=None,
+                      scale_out: Optional[torch.Tensor] = None, min_valid: float = 1e-9):
     """np.percentile(sample, q) (method 'linear', f32 sample) of the union of every rank's chunks with the
     selection state kept on the device: the host only enqueues the radix-select stages and, between them,
     `all_reduce(tensor, op)` (op in {"sum", "min"}) of the exchange area -- no host round trip until the
-    4-double result is read.  all_reduce=None: single device.  (reference: _normalization.py:22-32)"""
+    4-double result is read.  all_reduce=None: single device.  (reference: _normalization.py:22-32)
+    scale_out (one f32 on the device): the value is finished on the device (NumPy's f32 lerp; NaN when the sample
+    is empty or the value is NaN / <= min_valid) and NO host synchronisation happens; returns scale_out."""
     lib = _lib.load()
     views = _pooled_views(chunks) if chunks else []
     nx = int(lib.fsg_select_exchange_words())
@@ -609,6 +624,12 @@ def staged_percentile(chunks, q: float, *, take_abs: bool, finite_only: bool, de
     if all_reduce is not None:
         all_reduce(ws[2049:2050], "sum")
         all_reduce(ws[2050:2051], "min")
+    if scale_out is not None:
+        if scale_out.dtype != torch.float32 or not scale_out.is_cuda:
+            raise TypeError("scale_out must be a float32 CUDA tensor")
+        check(lib.fsg_select_finish_scale(_ptr(ws), ta, C.c_float(float(q32)), C.c_float(float(min_valid)),
+                                          _ptr(scale_out), stream), "fsg_select_finish_scale")
+        return scale_out
     check(lib.fsg_select_finish(_ptr(ws), ta, _ptr(res), stream), "fsg_select_finish")
     a_k, a_k1, rank_dev, n = [float(v) for v in res.cpu().tolist()]   # the only host synchronisation
     n = int(n)

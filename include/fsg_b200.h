@@ -286,6 +286,16 @@ int fsg_select_pick(int level, float q32, void* workspace, void* stream);
 int fsg_select_next(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
                     const int64_t* ld_host, int n_chunks, int take_abs, int finite_only, void* workspace, void* stream);
 int fsg_select_finish(void* workspace, int take_abs, double* result_dev, void* stream);
+/* Same selection, finished on the device: scale_dev[0] = np.percentile(sample, 100 * q32) (method 'linear', NumPy's
+ * f32 arithmetic), or NaN when the sample is empty or the value is NaN / <= min_valid (topousm_fast_stat_func,
+ * algorithms/_normalization.py:22-32) -- the value fsg_topousm_fused_band_ws takes as norm_scale_dev, so that the
+ * statistics pre-pass needs no host round trip. */
+int fsg_select_finish_scale(void* workspace, int take_abs, float q32, float min_valid, float* scale_dev, void* stream);
+/* Bounding box of the finite samples of the overview band[first_row + i * cov, j * cov], i < n_rows, j < n_cols
+ * (algorithms/_norm_stats.py:254-264): box_dev = (max of -(row_index0 + i), max of row_index0 + i, max of -j, max of j),
+ * INT_MIN-like words when no sample is finite; one MAX all-reduce merges the row bands of several ranks. */
+int fsg_valid_bbox(const float* band, int64_t ld, int64_t first_row, int64_t cov, int64_t n_rows, int64_t n_cols,
+                   int64_t row_index0, int32_t* box_dev, void* stream);
 
 
 /* synthetic DEM generator used by bench/tests: eight sinusoid octaves +
