@@ -141,7 +141,10 @@ def check(rc: int, what: str = "") -> None:
 
 def make_encode(output_dtype: str = "float32", qp: dict | None = None) -> Encode:
     kind = _KIND[str(output_dtype)]
-    if kind == FSG_OUT_F32 or qp is None:
+    if kind != FSG_OUT_F32 and qp is None:
+        # the kernels would store 4-byte floats into a 1- / 2-byte-per-pixel buffer
+        raise ValueError(f"output_dtype={output_dtype!r} needs quantisation parameters (qp=quantize_params(...))")
+    if kind == FSG_OUT_F32:
         return Encode(FSG_OUT_F32, 0, 0, 0, 1.0, 0.0)
     return Encode(kind, int(qp["dn_min"]), int(qp["dn_max"]), 0, float(qp["a_coef"]), float(qp["b_coef"]))
 

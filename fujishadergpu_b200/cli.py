@@ -170,14 +170,16 @@ def run(args) -> dict:
     result = algo.process(d, **params)
     if hasattr(result, "ndim") and result.ndim == 3:
         raise NotImplementedError("--agg stack produces a multi-band raster; the COG writer is single-band")
+    # final NoData re-mask for every output dtype, before the quantisation (core/dask_processor.py:1479-1547):
+    # the spatial-mode smoothing fills voids, and a filled void must not become a valid DN
+    nanmask = torch.isnan(d)
+    result = torch.where(nanmask if result.ndim == 2 else nanmask.unsqueeze(0), torch.full_like(result, float("nan")), result)
     if args.output_dtype != "float32":
         override = _parse_output_range(args.output_range)
         rng = resolve_output_range(args.algorithm, params=params, override=override)
         if rng is None:
             raise ValueError(f"{args.algorithm}: --output-dtype {args.output_dtype} needs --output-range lo,hi")
         result = quantize_array(result, quantize_params(rng[0], rng[1], args.output_dtype), args.output_dtype)
-    else:
-        result = torch.where(torch.isnan(d), torch.full_like(result, float("nan")), result)   # final NoData re-mask
     torch.cuda.synchronize(dev)
     t_gpu = time.perf_counter() - t0 - t_read
     stats = write_cog(args.output, result, transform=meta.get("transform"), epsg=meta.get("epsg"))

@@ -314,19 +314,50 @@ def topousm_fast_sharded_step(band: torch.Tensor, H: int, rank: int, world: int,
     if key not in _PREP_STREAMS:
         _PREP_STREAMS[key] = torch.cuda.Stream(device=dev)
     side = _PREP_STREAMS[key]
+    trace = STEP_TRACE is not None
+    if trace:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        evs[0].record(cur)
     side.wait_stream(cur)
-    with torch.cuda.stream(side):
-        prep = topousm_sharded_prepare(band, H, rank, world, radii=radii, pixel_size=pixel_size, dist=dist, dem_ext=dem_ext,
-                                       spec=spec)
+    box = {}
+
+    def start_prep():
+        with torch.cuda.stream(side):
+            box["prep"] = topousm_sharded_prepare(band, H, rank, world, radii=radii, pixel_size=pixel_size, dist=dist,
+                                                  dem_ext=dem_ext, spec=spec)
+            if trace:
+                evs[1].record(side)
+
     sharded_topousm_scale(band, H, rank, world, radii=radii, weights=weights, pixel_size=pixel_size, dist=dist,
-                          spec=spec, scale_out=scale_dev)
+                          spec=spec, scale_out=scale_dev, after_gather=start_prep)
+    prep = box["prep"]
+    if trace:
+        evs[2].record(cur)
     cur.wait_stream(side)
     for t in [prep["dem_ext"]] + [g for g in prep["term_grids"] if g is not None]:
         if isinstance(t, torch.Tensor) and t.is_cuda:
             t.record_stream(cur)
     res = topousm_sharded_finish(prep, weights=weights, norm_scale=None, norm_scale_dev=scale_dev,
                                  output_dtype=output_dtype, qp=qp, out=out)
+    if trace:
+        evs[3].record(cur)
+        STEP_TRACE.append(evs)
     return res, scale_dev, spec
+
+
+PREPASS_TRACE: Optional[list] = None   # debugging: [(phase name, event)] of the statistics pre-pass
+STEP_TRACE: Optional[list] = None   # debugging: set to [] to collect (start, prep done, scale done, fused done) events
+
+
+def step_trace_summary() -> dict:
+    """Milliseconds from the start of a step to: preparation done (side stream), scale done, fused pass done."""
+    torch.cuda.synchronize()
+    rows = [[e[0].elapsed_time(x) for x in e[1:]] for e in (STEP_TRACE or [])]
+    if not rows:
+        return {}
+    n = len(rows)
+    return {"steps": n, "prep_done_ms": sum(r[0] for r in rows) / n, "scale_done_ms": sum(r[1] for r in rows) / n,
+            "fused_done_ms": sum(r[2] for r in rows) / n}
 
 
 def topousm_fast_sharded_with_stats(band: torch.Tensor, H: int, rank: int, world: int, *, radii, weights=None,
@@ -494,17 +525,27 @@ def assign_window_owners(wins, own) -> List[int]:
 
 def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, radii, weights, pixel_size=1.0,
                           dist=None, grid: int = 3, block_fn=None, select_fns=None, spec: Optional[Speculation] = None,
-                          scale_out: Optional[torch.Tensor] = None):
+                          scale_out: Optional[torch.Tensor] = None, after_gather=None):
     """p99(|raw topousm_fast|) over the reference's stratified full-resolution windows.  Each window is
     evaluated whole by ONE rank (assign_window_owners) after gathering its rows from the owning bands; the
     percentile over all windows is an exact distributed selection.
     spec + scale_out (product path): no host synchronisation -- the bounding box is a guess checked later
-    (Speculation) and the scale stays on the device (scale_out, NaN = no scale); returns scale_out."""
+    (Speculation) and the scale stays on the device (scale_out, NaN = no scale); returns scale_out.
+    after_gather: called once the window gather is enqueued (the step starts the main-pass preparation there: the
+    communication library runs its operations in issue order, so the bounding-box all-reduce and the window gather
+    go first and the halo exchange, which has to wait for the pyramid kernel anyway, last)."""
     from ..algorithms._norm_stats import _norm_stat_window_geometry, stratified_windows
     W = int(band.shape[1])
     own = band_bounds(H, world)
     r0, r1 = own[rank]
     margin, tile = _norm_stat_window_geometry("topousm_fast", {"radii": list(radii)})
+
+    def _mark(name):
+        if PREPASS_TRACE is not None and band.is_cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(band.device))
+            PREPASS_TRACE.append((name, ev))
+    _mark("start")
     # valid-data bounding box from a <=512 px nearest overview of the own rows
     cov = max(1, max(W, H) // 512)
     big = 1 << 40
@@ -540,6 +581,8 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
             box = torch.stack([mn[0], mx[0], mn[1], mx[1]])
         ymin, ymax, xmin, xmax = [int(v) for v in box.cpu().tolist()]
     if ymax < 0:
+        if after_gather is not None:
+            after_gather()
         if scale_out is not None:
             scale_out.fill_(float("nan"))
             return scale_out
@@ -555,6 +598,7 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
             raw = k.topousm_fast(a, radii=radii, weights=weights, pixel_size=pixel_size,
                                  roi=(m, int(a.shape[0]) - 2 * m, m, int(a.shape[1]) - 2 * m) if m > 0 else None)
             return raw[m:-m, m:-m] if m > 0 else raw
+    _mark("bbox")
     # 1. move every window's rows to its owner ...
     owners = assign_window_owners(wins, own)
     plans, mine_idx = [], []
@@ -568,6 +612,9 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
             mine_idx.append(wi)
     outs = run_exchanges(plans, dist)          # all nine gathers in one point-to-point batch
     mine = [outs[wi] for wi in mine_idx]
+    _mark("gather")
+    if after_gather is not None:
+        after_gather()
     # 2. ... then every rank evaluates its own windows, all ranks at the same time
     def job_for(win):
         def job():
@@ -580,6 +627,7 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
 
     from .. import _device as _dev
     pooled = [r for r in _dev.run_concurrently([job_for(w) for w in mine], band.device) if r.numel()]
+    _mark("windows")
     kw = select_fns(pooled) if select_fns is not None else {}   # tests inject stand-ins for the kernels
     if scale_out is not None:
         return distributed_percentile(pooled, 99.0, take_abs=True, finite_only=False, device=band.device, dist=dist,
@@ -629,12 +677,29 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
     if sampler is not None:
         sampler.start()
     k.profile_enable(True)
+    import os as _os
+    global STEP_TRACE
+    global PREPASS_TRACE
+    if _os.environ.get("FSG_STEP_TRACE"):
+        STEP_TRACE = []
+        PREPASS_TRACE = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.steps):
         scale_dev = step()
     ev1.record()
     torch.cuda.synchronize()
+    if STEP_TRACE is not None:
+        import sys as _sys
+        print(f"[rank {rank}] step trace: {step_trace_summary()}", file=_sys.stderr)
+        acc = {}
+        tr = PREPASS_TRACE
+        for i in range(1, len(tr)):
+            if tr[i][0] != "start":
+                acc.setdefault(tr[i][0], []).append(tr[i - 1][1].elapsed_time(tr[i][1]))
+        print(f"[rank {rank}] pre-pass phases (ms): " + ", ".join(f"{k_} {sum(v) / len(v):.2f}" for k_, v in acc.items()), file=_sys.stderr)
+        STEP_TRACE = None
+        PREPASS_TRACE = None
     scale = float(scale_dev.item())
     csum = torch.zeros(1, dtype=torch.int64, device=dev)
     for r in range(0, r1 - r0, 8192):

@@ -45,6 +45,9 @@ struct GradParams {
   AxisCoef y1, x1;  // first derivatives (|step|)
   AxisCoef y2, x2;  // second derivatives (signed step; curvature only)
   float lx, ly, lz, sgx, sgy;  // hillshade light vector / orientation signs
+  // interior pixels work on the raw central differences d = f[i+1] - f[i-1] (see grad_interior): light vector and
+  // signs folded with 1/(2h), squared reciprocal steps
+  float kx, ky, ix2, iy2;
   int sub;                     // slope unit or curvature type
   double gw[5];                // sigma=1 Gaussian half taps (centre..outer)
   EncodeDev enc;
@@ -93,7 +96,27 @@ __device__ __noinline__ float gap_fill(const GradParams& p, int64_t gy, int64_t 
 
 // x^1.5 for x >= 0 as x*sqrt(x): two correctly rounded ops (<= 1.5 ulp; the reference's powf is not
 // correctly rounded either) instead of the ~100-instruction powf
-__device__ __forceinline__ float pow15(float x) { return x * sqrtf(x); }
+__device__ __forceinline__ float sfu_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sfu_rcp(float x) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sfu_ex2(float x) {
+  float r;
+  asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sfu_lg2(float x) {
+  float r;
+  asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float pow15(float x) { return x * sfu_sqrt(x); }
 
 // derivative along one axis of a shared-memory plane; `g` is the global index along the axis,
 // `n` the raster extent, `s` the element stride along that axis.
@@ -113,22 +136,98 @@ __device__ __forceinline__ float curv_result(const GradParams& p, float dy, floa
     float s = (dxy + dyx) / 2.f;
     float den = pow15((1.f + pp * pp) + q * q);
     float num = ((1.f + q * q) * r - ((2.f * pp) * q) * s) + (1.f + pp * pp) * t;
-    k = (-num) / (2.f * den + 1e-10f);
+    k = (-num) * sfu_rcp(2.f * den + 1e-10f);
   } else if (p.sub == FSG_CURV_GAUSSIAN) {
     float b = (1.f + dx * dx) + dy * dy;
-    k = (dxx * dyy - dxy * dxy) / (b * b);
+    k = (dxx * dyy - dxy * dxy) * sfu_rcp(b * b);
   } else if (p.sub == FSG_CURV_PLANFORM) {
     float num = ((dy * dy) * dxx - ((2.f * dx) * dy) * dxy) + (dx * dx) * dyy;
-    k = (-num) / (pow15(dx * dx + dy * dy) + 1e-10f);
+    k = (-num) * sfu_rcp(pow15(dx * dx + dy * dy) + 1e-10f);
   } else {
     float num = ((dx * dx) * dxx + ((2.f * dx) * dy) * dxy) + (dy * dy) * dyy;
     float g2 = dx * dx + dy * dy;
-    k = (-num) / (g2 * pow15((1.f + dx * dx) + dy * dy) + 1e-10f);
+    k = (-num) * sfu_rcp(g2 * pow15((1.f + dx * dx) + dy * dy) + 1e-10f);
   }
-  float t = tanhf(k * 100.f);
-  // x^(1/2.2) for x in [0, 1] as exp2f(c * log2f(x)) (log2f <= 1 ulp, exp2f <= 2 ulp: <= 4e-7 relative for
-  // x >= 1e-3, the range the 1e-5 bar applies to; 0 -> 0, NaN -> NaN) instead of the ~100-instruction powf
-  return exp2f((float)(1 / 2.2) * log2f((t + 1.f) / 2.f));
+  // display value ((tanh(100 k) + 1) / 2)^(1/2.2): (tanh(z) + 1) / 2 = 1 / (1 + e^(-2 z)), so the value is
+  // 2^(-c * log2(1 + 2^(-200 log2(e) k))) -- three SFU operations instead of tanhf, a division, log2f and exp2f, and
+  // accurate in RELATIVE terms where tanh saturates at -1 (the f32 tanh of the reference is not; the parity
+  // test compares that range before the gamma).  The divisions above are reciprocal-multiplies (<= 2 ulp).
+  // k = +-inf / NaN behave like the reference: 1, 0, NaN.
+  const float E = sfu_ex2(k * -288.53900817779268f);
+  return sfu_ex2((float)(-1 / 2.2) * sfu_lg2(1.f + E));
+}
+
+// Approximate SFU forms.  The contract for these outputs is 1e-5 relative / 1e-6 absolute against the reference
+// (BASELINE.json north_star), not bit-identity: rsqrt.approx / sqrt.approx / rcp.approx are within 2 ulp
+// (<= 2.4e-7 relative), the arctangent polynomial within 1.7e-7 relative -- measured maxima against the oracle are
+// asserted in tests/test_gpu_parity.py.  IEEE sqrt, division and the library atanf cost ~45 of the former
+// 75 instructions per pixel and kept the stencil at 41 % of the HBM roofline.
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// arctan(x) for x >= 0 (NaN -> NaN): atan(t) = t * P(t^2) on [0, 1] (degree-8 least-squares fit on Chebyshev nodes,
+// 1.7e-7 relative in f32), atan(x) = pi/2 - atan(1/x) above 1
+__device__ __forceinline__ float fast_atan_pos(float x) {
+  const bool big = x > 1.f;
+  const float t = big ? fast_rcp(x) : x;
+  const float u = t * t;
+  float a = 0.0028340641874819994f;
+  a = fmaf(a, u, -0.016005029901862144f);
+  a = fmaf(a, u, 0.042587608098983765f);
+  a = fmaf(a, u, -0.07495445758104324f);
+  a = fmaf(a, u, 0.10636754333972931f);
+  a = fmaf(a, u, -0.14202570915222168f);
+  a = fmaf(a, u, 0.19992484152317047f);
+  a = fmaf(a, u, -0.3333306610584259f);
+  a = fmaf(a * u, t, t);   // t * (1 + u * q(u))
+  return big ? 1.57079637050628662f - a : a;
+}
+
+template <int CLASS>
+__device__ __forceinline__ float grad_result(const GradParams& p, float dy, float dx) {
+  if (CLASS == 0) {
+    float e = dx * p.sgx, n = dy * p.sgy;
+    float hs = (((-e) * p.lx + (-n) * p.ly) + p.lz) * fast_rsqrt((e * e + n * n) + 1.0f);
+    return fminf(fmaxf(hs, 0.f), 1.f);
+  } else {
+    const float g = fast_sqrt(dx * dx + dy * dy);
+    if (p.sub == FSG_SLOPE_PERCENT) return g * 100.f;   // tan(arctan(g)) * 100 (_impl_slope.py:30-31)
+    const float s = fast_atan_pos(g);
+    if (p.sub == FSG_SLOPE_DEGREE) return s * (180.0f / 3.14159274101257324f);  // npy_rad2degf
+    return s;
+  }
+}
+
+// Interior pixels (both neighbours exist on both axes) from the raw central differences dyr = f[y+1] - f[y-1],
+// dxr = f[x+1] - f[x-1]: the reciprocal steps, the orientation signs and the light vector are folded into
+// constants (host, f64 -> f32) and the sums are fused multiply-adds -- ~12 instead of ~30 instructions per pixel, same
+// 1e-5 / 1e-6 contract (measured: <= 3e-7 relative).  Used by the streaming AND the tile kernel, so a pixel does
+// not depend on which of the two computed it (row-band calls == whole-raster call).
+template <int CLASS>
+__device__ __forceinline__ float grad_interior(const GradParams& p, float dyr, float dxr) {
+  const float g2 = fmaf(dxr * dxr, p.ix2, (dyr * dyr) * p.iy2);   // dx^2 + dy^2
+  if (CLASS == 0) {
+    const float num = fmaf(dxr, p.kx, fmaf(dyr, p.ky, p.lz));    // (-e) lx + (-n) ly + lz
+    return __saturatef(num * fast_rsqrt(g2 + 1.0f));
+  } else {
+    const float g = fast_sqrt(g2);
+    if (p.sub == FSG_SLOPE_PERCENT) return g * 100.f;
+    const float s = fast_atan_pos(g);
+    if (p.sub == FSG_SLOPE_DEGREE) return s * (180.0f / 3.14159274101257324f);
+    return s;
+  }
 }
 
 template <int CLASS>
@@ -195,20 +294,22 @@ __device__ __forceinline__ void grad_tile(const GradParams& p, int64_t ty0, int6
       res = nanf("");
     } else if (CLASS == 0) {
       const float* f = &F[(cy + HALO) * FW + (cx + HALO)];
-      float dy = deriv(f, FW, gy, p.H, p.y1);
-      float dx = deriv(f, 1, gx, p.W, p.x1);
-      float e = dx * p.sgx, n = dy * p.sgy;
-      float norm = sqrtf((e * e + n * n) + 1.0f);
-      float hs = (((-e) * p.lx + (-n) * p.ly) + p.lz) / norm;
-      res = fminf(fmaxf(hs, 0.f), 1.f);
+      if (gy > 0 && gy < p.H - 1 && gx > 0 && gx < p.W - 1) {
+        res = grad_interior<0>(p, f[FW] - f[-FW], f[1] - f[-1]);
+      } else {
+        float dy = deriv(f, FW, gy, p.H, p.y1);
+        float dx = deriv(f, 1, gx, p.W, p.x1);
+        res = grad_result<0>(p, dy, dx);
+      }
     } else if (CLASS == 1) {
       const float* f = &F[(cy + HALO) * FW + (cx + HALO)];
-      float dy = deriv(f, FW, gy, p.H, p.y1);
-      float dx = deriv(f, 1, gx, p.W, p.x1);
-      float s = atanf(sqrtf(dx * dx + dy * dy));
-      if (p.sub == FSG_SLOPE_DEGREE) res = s * (180.0f / 3.14159274101257324f);  // npy_rad2degf
-      else if (p.sub == FSG_SLOPE_PERCENT) res = tanf(s) * 100.f;
-      else res = s;
+      if (gy > 0 && gy < p.H - 1 && gx > 0 && gx < p.W - 1) {
+        res = grad_interior<1>(p, f[FW] - f[-FW], f[1] - f[-1]);
+      } else {
+        float dy = deriv(f, FW, gy, p.H, p.y1);
+        float dx = deriv(f, 1, gx, p.W, p.x1);
+        res = grad_result<1>(p, dy, dx);
+      }
     } else {
       const float* gyp = &DY[(cy + 2) * DW + (cx + 2)];
       const float* gxp = &DX[(cy + 2) * DW + (cx + 2)];
@@ -246,6 +347,7 @@ constexpr int GS_THREADS = G_THREADS;
 constexpr int GS_VEC = 4;
 constexpr int GS_COLS = GS_THREADS * GS_VEC;
 constexpr int GS_BAND = 64;
+constexpr int GS_SLOTS = 6;   // row slots of the hillshade / slope streaming kernel (registers)
 static_assert(GS_COLS % GT_W == 0 && GS_BAND % GT_H == 0, "the NaN redo walks whole tiles");
 
 __device__ __forceinline__ float filled_at(const GradParams& p, int64_t gy, int64_t gx) {
@@ -267,21 +369,6 @@ template <bool POW2>
 __device__ __forceinline__ float central_t(float hi, float lo, const AxisCoef& c) {
   if (POW2) return (hi - lo) * c.inv_two_h;
   return central(hi, lo, c);
-}
-
-template <int CLASS>
-__device__ __forceinline__ float grad_result(const GradParams& p, float dy, float dx) {
-  if (CLASS == 0) {
-    float e = dx * p.sgx, n = dy * p.sgy;
-    float norm = sqrtf((e * e + n * n) + 1.0f);
-    float hs = (((-e) * p.lx + (-n) * p.ly) + p.lz) / norm;
-    return fminf(fmaxf(hs, 0.f), 1.f);
-  } else {
-    float s = atanf(sqrtf(dx * dx + dy * dy));
-    if (p.sub == FSG_SLOPE_DEGREE) return s * (180.0f / 3.14159274101257324f);  // npy_rad2degf
-    if (p.sub == FSG_SLOPE_PERCENT) return tanf(s) * 100.f;
-    return s;
-  }
 }
 
 // one raster-edge pixel from global memory (one-sided second-order forms of np.gradient)
@@ -324,7 +411,7 @@ __device__ __forceinline__ void gs_issue(const GradParams& p, int64_t gy, int64_
 }
 
 template <int CLASS, bool POW2>
-__global__ void __launch_bounds__(GS_THREADS, 4) grad_stream_kernel(const __grid_constant__ GradParams p) {
+__global__ void __launch_bounds__(GS_THREADS, 3) grad_stream_kernel(const __grid_constant__ GradParams p) {
   __shared__ float F[TileGeom<CLASS>::FH * TileGeom<CLASS>::FW];
   __shared__ unsigned char M[GT_H * GT_W];
   const int64_t cx0 = (int64_t)blockIdx.x * GS_COLS;
@@ -336,51 +423,62 @@ __global__ void __launch_bounds__(GS_THREADS, 4) grad_stream_kernel(const __grid
   const bool live = c < p.W;
   float nanprobe = 0.f;   // becomes NaN as soon as one loaded value is NaN (or +-Inf)
   if (live) {
-    // prev / cur / next are the rows of the stencil; q1..q3 are rows whose loads are still in flight.
-    // The rotation is done with register moves (one loop body: the 6x unrolled form thrashed the
-    // instruction cache).
-    GsRow prev, cur, next, q1, q2, q3;
+    // GS_SLOTS row slots rotate through the roles (previous, current, next, GS_SLOTS - 4 rows whose loads are in
+    // flight, the row being requested): the loop is unrolled GS_SLOTS times, so the rotation is a renaming, not
+    // register moves.  (10 slots / 8 rows in flight at 2 CTAs per SM were measured: slower, 0.64 -> 0.73 ms.)
+    // (Handing the neighbour columns across lanes by shuffle instead of the two scalar loads was measured: slower,
+    // slope 0.78 -> 0.93 ms at 16384^2.)
+    constexpr int NS = GS_SLOTS, AHEAD = GS_SLOTS - 2;   // row y + AHEAD is requested while row y is computed
+    GsRow r[NS];
 #pragma unroll
-    for (int k = 0; k < GS_VEC + 2; ++k) prev.v[k] = cur.v[k] = next.v[k] = q1.v[k] = q2.v[k] = q3.v[k] = 0.f;
-    if (y0 > 0) gs_issue(p, y0 - 1, c, prev);
-    gs_issue(p, y0, c, cur);
-    if (y0 + 1 <= last_needed) gs_issue(p, y0 + 1, c, next);
-    if (y0 + 2 <= last_needed) gs_issue(p, y0 + 2, c, q1);
-    if (y0 + 3 <= last_needed) gs_issue(p, y0 + 3, c, q2);
+    for (int q = 0; q < NS; ++q)
+#pragma unroll
+      for (int k = 0; k < GS_VEC + 2; ++k) r[q].v[k] = 0.f;
+    if (y0 > 0) gs_issue(p, y0 - 1, c, r[0]);
+#pragma unroll
+    for (int q = 0; q < AHEAD; ++q)
+      if (y0 + q <= last_needed) gs_issue(p, y0 + q, c, r[1 + q]);
     const bool vec_out = (p.ld_out % 4 == 0) && (c + GS_VEC <= p.W);
     const bool scale = p.zscale != 1.0f;
-    nanprobe += ((prev.v[1] + prev.v[2]) + (prev.v[3] + prev.v[4]));
+    nanprobe += ((r[0].v[1] + r[0].v[2]) + (r[0].v[3] + r[0].v[4]));
 #pragma unroll 1
-    for (int64_t y = y0; y < y1; ++y) {
-      if (y + 4 <= last_needed) gs_issue(p, y + 4, c, q3);
-      float res[GS_VEC];
+    for (int64_t yb = y0; yb < y1; yb += NS) {
 #pragma unroll
-      for (int k = 0; k < GS_VEC; ++k) {
-        float up = prev.v[k + 1], dn = next.v[k + 1], lf = cur.v[k], rt = cur.v[k + 2];
-        if (scale) { up = up * p.zscale; dn = dn * p.zscale; lf = lf * p.zscale; rt = rt * p.zscale; }
-        float dy = central_t<POW2>(dn, up, p.y1);
-        float dx = central_t<POW2>(rt, lf, p.x1);
-        res[k] = grad_result<CLASS>(p, dy, dx);
-      }
-      nanprobe += ((cur.v[0] + cur.v[1]) + (cur.v[2] + cur.v[3])) + (cur.v[4] + cur.v[5]);
-      nanprobe *= 0.f;
-      const int64_t o = (y - p.out_row0) * p.ld_out + c;
-      if (vec_out && p.enc.kind == FSG_OUT_F32) {
-        *reinterpret_cast<float4*>((float*)p.out + o) = make_float4(res[0], res[1], res[2], res[3]);
-      } else if (vec_out && p.enc.kind == FSG_OUT_U8) {
-        uchar4 q = make_uchar4((unsigned char)(int)encode_dn(res[0], p.enc), (unsigned char)(int)encode_dn(res[1], p.enc),
-                               (unsigned char)(int)encode_dn(res[2], p.enc), (unsigned char)(int)encode_dn(res[3], p.enc));
-        *reinterpret_cast<uchar4*>((uint8_t*)p.out + o) = q;
-      } else {
+      for (int j = 0; j < NS; ++j) {
+        const int64_t y = yb + j;
+        if (y < y1) {
+          GsRow& prev = r[j];
+          GsRow& cur = r[(j + 1) % NS];
+          GsRow& next = r[(j + 2) % NS];
+          if (y + AHEAD <= last_needed) gs_issue(p, y + AHEAD, c, r[(j + 1 + AHEAD) % NS]);
+          float res[GS_VEC];
 #pragma unroll
-        for (int k = 0; k < GS_VEC; ++k)
-          if (c + k < p.W) store_out(p.out, o + k, res[k], p.enc);
+          for (int k = 0; k < GS_VEC; ++k) {
+            float up = prev.v[k + 1], dn = next.v[k + 1], lf = cur.v[k], rt = cur.v[k + 2];
+            if (scale) { up = up * p.zscale; dn = dn * p.zscale; lf = lf * p.zscale; rt = rt * p.zscale; }
+            res[k] = grad_interior<CLASS>(p, dn - up, rt - lf);
+          }
+          nanprobe += ((cur.v[0] + cur.v[1]) + (cur.v[2] + cur.v[3])) + (cur.v[4] + cur.v[5]);
+          nanprobe *= 0.f;
+          const int64_t o = (y - p.out_row0) * p.ld_out + c;
+          if (vec_out && p.enc.kind == FSG_OUT_F32) {
+            *reinterpret_cast<float4*>((float*)p.out + o) = make_float4(res[0], res[1], res[2], res[3]);
+          } else if (vec_out && p.enc.kind == FSG_OUT_U8) {
+            uchar4 q = make_uchar4((unsigned char)(int)encode_dn(res[0], p.enc), (unsigned char)(int)encode_dn(res[1], p.enc),
+                                   (unsigned char)(int)encode_dn(res[2], p.enc), (unsigned char)(int)encode_dn(res[3], p.enc));
+            *reinterpret_cast<uchar4*>((uint8_t*)p.out + o) = q;
+          } else {
+#pragma unroll
+            for (int k = 0; k < GS_VEC; ++k)
+              if (c + k < p.W) store_out(p.out, o + k, res[k], p.enc);
+          }
+          if (y + 1 == y1) {   // the row below the block was read as `next` of the last row
+            nanprobe += ((next.v[1] + next.v[2]) + (next.v[3] + next.v[4]));
+            nanprobe *= 0.f;
+          }
+        }
       }
-      prev = cur; cur = next; next = q1; q1 = q2; q2 = q3;
     }
-    // the row below the block (read as `next` of the last row) is `cur` after the final rotation
-    nanprobe += ((cur.v[1] + cur.v[2]) + (cur.v[3] + cur.v[4]));
-    nanprobe *= 0.f;
   }
   // ---- cold paths ----
   if (__syncthreads_or((int)(nanprobe != nanprobe))) {
@@ -613,6 +711,8 @@ int fsg_hillshade(const float* dem, void* out, const fsg_window* win, double azi
   p.lx = (float)(sin(az) * cos(alt)); p.ly = (float)(cos(az) * cos(alt)); p.lz = (float)sin(alt);
   p.sgx = (is_none(psx) || psx >= 0.0) ? 1.f : -1.f;
   p.sgy = (is_none(psy) || psy >= 0.0) ? 1.f : -1.f;
+  p.kx = (float)(-(double)p.sgx * (double)p.lx / (2.0 * sx)); p.ky = (float)(-(double)p.sgy * (double)p.ly / (2.0 * sy));
+  p.ix2 = (float)(1.0 / (4.0 * sx * sx)); p.iy2 = (float)(1.0 / (4.0 * sy * sy));
   return run_grad(0, dem, out, win, p, enc, stream, "fsg_hillshade");
 }
 
@@ -625,6 +725,7 @@ int fsg_slope(const float* dem, void* out, const fsg_window* win, int unit, doub
   resolve_steps(pixel_size, psx, psy, false, &sy, &sx);
   p.y1 = make_axis(sy); p.x1 = make_axis(sx); p.y2 = p.y1; p.x2 = p.x1;
   p.zscale = 1.f; p.sub = unit;
+  p.ix2 = (float)(1.0 / (4.0 * sx * sx)); p.iy2 = (float)(1.0 / (4.0 * sy * sy));
   return run_grad(1, dem, out, win, p, enc, stream, "fsg_slope");
 }
 

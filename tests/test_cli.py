@@ -128,3 +128,22 @@ def test_cli_end_to_end_against_oracle(tmp_path):
     assert main([src, out, "--algorithm", "ambient_occlusion", "--mode", "local", "--radius", "8", "--output-dtype", "int16"]) == 0
     got, meta = read_geotiff(out)
     assert got.dtype == np.int16 and meta["predictor"] == 2 and np.array_equal(got == 0, np.isnan(dem))
+
+
+@pytest.mark.gpu
+def test_cli_spatial_integer_output_keeps_nodata(tmp_path):
+    """--mode spatial smooths with a void-filling Gaussian: the final NoData re-mask must run for integer outputs
+    too (core/dask_processor.py:1479-1547), so DN 0 <=> input NoData."""
+    pytest.importorskip("torch")
+    from fujishadergpu_b200.cli import main
+    from fujishadergpu_b200.io.geotiff_reader import read_geotiff
+    dem = orc.synth_dem(700, 900, seed=62, nodata=True)
+    dem[300:340, 400:470] = np.nan
+    src = str(tmp_path / "dem.tif")
+    _write_input(src, dem)
+    for algo, dtype in (("hillshade", "uint8"), ("slope", "int16"), ("curvature", "uint8")):
+        out = str(tmp_path / f"{algo}.tif")
+        assert main([src, out, "--algorithm", algo, "--mode", "spatial", "--radii", "2,8", "--output-dtype", dtype]) == 0
+        got, meta = read_geotiff(out)
+        assert meta["nodata"] == 0.0
+        assert np.array_equal(got == 0, np.isnan(dem)), algo

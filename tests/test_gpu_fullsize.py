@@ -87,8 +87,20 @@ def test_config2_topousm_32768_properties(monkeypatch):
     del neg
     # (b) p99 scale of the production pre-pass == exact selection over the same windows done by torch
     from fujishadergpu_b200.algorithms._norm_stats import compute_norm_stats_device
+    from fujishadergpu_b200.algorithms._norm_stats import _norm_stat_window_geometry, stratified_windows
     st = compute_norm_stats_device(d, "topousm_fast", {"radii": radii, "weights": w, "pixel_size": 1.0})
-    assert st is not None and 1.0 < st[0] < 100.0
+    margin, tile = _norm_stat_window_geometry("topousm_fast", {"radii": radii})
+    wins = stratified_windows(S, S, 0, S, 0, S, grid=3, tile=min(tile, S))   # dense raster: bounding box = raster
+    assert len(set(wins)) == 9
+    pooled = []
+    for (wy0, wx0, tw, th) in wins:      # every window evaluated whole (no region of interest), trimmed, pooled
+        r = k.topousm_fast(d[wy0:wy0 + th, wx0:wx0 + tw], radii=radii, weights=w)
+        m = int(min(margin, th // 3, tw // 3))
+        pooled.append(_np(r[m:-m, m:-m].abs()).ravel())
+        del r
+    want = np.percentile(np.concatenate(pooled), 99.0)
+    del pooled
+    assert st is not None and np.float32(st[0]) == np.float32(want), (st, want)
     # (c) the full-resolution radii depend on +-32 px only: oracle on crops (corners / edges / centre)
     near = k.topousm_fast(d, radii=[2, 8, 32], weights=[4 / 7, 2 / 7, 1 / 7], workspace=ws)
     side, m = 768, 40

@@ -146,3 +146,31 @@ def test_sync_free_step_equals_sequential_calls():
         assert np.float32(scale_dev.item()) == np.float32(st[0])
         want = k.topousm_fast(d, radii=radii, weights=w, norm_scale=float(st[0]))
         assert _same_bits(res, want)
+
+
+def test_stats_prepass_nine_windows_vs_oracle():
+    """6144^2 with radii <= 128: margin 144, tile 2048 -> the 3 x 3 grid yields nine distinct windows; the scale of
+    the device pre-pass (regions of interest, v8 + v6) equals the oracle's window-by-window p99 (reference:
+    _compute_norm_stats_tiled, algorithms/_norm_stats.py:176-298), and so does the synchronisation-free step."""
+    from fujishadergpu_b200 import kernels as k
+    from fujishadergpu_b200.algorithms._norm_stats import compute_norm_stats_device
+    from fujishadergpu_b200.core import sharding as sh
+    S = 6144
+    radii, w = [2, 8, 32, 128], [0.4, 0.3, 0.2, 0.1]
+    d = k.synth_dem((S, S), seed=12, nodata=False)
+    dem = d.cpu().numpy()
+    margin, tile = orc.stats_window_geometry("topousm_fast", {"radii": radii})
+    wins = orc.stats_windows(S, S, 0, S, 0, S, grid=3, tile=min(tile, S))
+    assert len(set(wins)) == 9 and tile == 2048
+    pooled = []
+    for (wy0, wx0, tw, th) in wins:
+        r = orc.topousm_fast_block(dem[wy0:wy0 + th, wx0:wx0 + tw], radii=radii, weights=w)
+        m = int(min(margin, th // 3, tw // 3))
+        r = r[m:-m, m:-m]
+        pooled.append(r[~np.isnan(r)])
+    want = orc.abs_p99_scale(np.concatenate(pooled))[0]
+    st = compute_norm_stats_device(d, "topousm_fast", {"radii": radii, "weights": w, "pixel_size": 1.0})
+    assert np.float32(st[0]) == np.float32(want), (st, want)
+    sh.Speculation._memory.clear()
+    _res, scale_dev, spec = sh.topousm_fast_sharded_step(d, S, 0, 1, radii=radii, weights=w)
+    assert spec.ok() and np.float32(scale_dev.item()) == np.float32(want)

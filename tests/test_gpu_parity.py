@@ -503,3 +503,29 @@ def test_streamed_host_pipeline_equals_whole_raster_call():
             HostTilePipeline(shape, "topousm_fast", params, output_dtype=od).run(hin, whole)
             StreamedTopoPipeline(shape, params, output_dtype=od, chunk_rows=512).run(hin, banded)
             assert np.array_equal(whole.numpy(), banded.numpy(), equal_nan=True), (nod, od)
+
+
+def test_gradient_fast_math_error_budget():
+    """hillshade / slope / curvature use approximate SFU forms (rsqrt, sqrt, rcp, ex2, lg2) and a polynomial
+    arctangent: the contract is 1e-5 relative / 1e-6 absolute against the reference, and the measured distance to the
+    oracle stays far inside it (B200, 2048^2 synthetic DEM: <= 0.06 of the bar for hillshade / slope, <= 0.3 for
+    the curvature display value)."""
+    from fujishadergpu_b200 import kernels as k
+    d = k.synth_dem((2048, 2048), seed=7, nodata=False)
+    dem = _np(d)
+    nup = dict(pixel_scale_x=1.0, pixel_scale_y=-1.0)
+
+    def frac_of_bar(got, want):
+        got, want = _np(got).astype(np.float64), want.astype(np.float64)
+        return float(np.max(np.abs(got - want) / (1e-6 + 1e-5 * np.abs(want))))
+
+    assert frac_of_bar(k.hillshade(d, **nup), orc.hillshade_block(dem, **nup)) <= 0.1
+    assert frac_of_bar(k.hillshade(d, pixel_scale_x=30.0, pixel_scale_y=-30.0),
+                       orc.hillshade_block(dem, pixel_scale_x=30.0, pixel_scale_y=-30.0)) <= 0.1
+    for unit in ("degree", "radian", "percent"):
+        assert frac_of_bar(k.slope(d, unit=unit, **nup), orc.slope_block(dem, unit=unit, **nup)) <= 0.1, unit
+    for ctype in ("mean", "gaussian", "planform", "profile"):
+        g = _np(k.curvature(d, curvature_type=ctype, **nup)).astype(np.float64)
+        w = orc.curvature_block(dem, curvature_type=ctype, **nup).astype(np.float64)
+        ok = w >= 0.05
+        assert np.max(np.abs(g[ok] - w[ok]) / (1e-6 + 1e-5 * w[ok])) <= 0.5, ctype
