@@ -109,13 +109,27 @@ def plan_exchange(local: torch.Tensor, own: Sequence[Tuple[int, int]], need: Seq
     return out, ops, keep
 
 
+EXCHANGE_LOG: Optional[dict] = None   # accounting (config 5 report): set to {"sent": 0, "received": 0, "events": []}
+
+
 def run_exchanges(plans, dist=None) -> list:
     """Issue the point-to-point operations of several plan_exchange() results as one batch; returns the outs.
     Every rank must pass the plans in the same order (sends and receives between a pair match in issue order)."""
     ops = [op for (_out, o, _keep) in plans for op in o]
     if ops and dist is not None:
+        log = EXCHANGE_LOG
+        if log is not None:
+            for op in ops:
+                nbytes = op.tensor.numel() * op.tensor.element_size()
+                log["sent" if op.op is dist.isend else "received"] += nbytes
+            if op.tensor.is_cuda:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(torch.cuda.current_stream(op.tensor.device))
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+        if log is not None and ops[-1].tensor.is_cuda:
+            e1.record(torch.cuda.current_stream(ops[-1].tensor.device))
+            log["events"].append((e0, e1))
     return [out for (out, _o, _keep) in plans]
 
 

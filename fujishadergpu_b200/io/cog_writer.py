@@ -206,24 +206,12 @@ def _sample_format(dt: np.dtype) -> int:
     return {"u": 1, "i": 2, "f": 3}[dt.kind]
 
 
-def write_tiff_pyramid(path: str, levels: Sequence, *, nodata=None, transform=None, epsg=None, blocksize: int = 512,
-                       compress: str = "zstd", level: int = 1, bigtiff: bool = True, num_threads: Optional[int] = None,
-                       row_reader=None, gdal_ghost: bool = True) -> dict:
-    """Write levels[0] (full resolution) and levels[1:] (overviews, each a NumPy array or any object with .shape /
-    .dtype whose rows `row_reader(level_obj, r0, r1)` returns as a NumPy array) as one tiled (Big)TIFF."""
-    comp = {"zstd": COMPRESSION_ZSTD, "deflate": COMPRESSION_DEFLATE, "none": COMPRESSION_NONE}[compress]
-    if row_reader is None:
-        row_reader = lambda a, r0, r1: np.asarray(a[r0:r1])
-    dt = np.dtype(str(levels[0].dtype).replace("torch.", ""))
-    if dt not in (np.dtype("uint8"), np.dtype("int16"), np.dtype("float32")):
-        raise ValueError(f"unsupported sample type {dt}")
-    pred = predictor_for_dtype(dt) if comp != COMPRESSION_NONE else 1
-    bs = int(blocksize)
-    fill = np.nan if dt.kind == "f" else (0 if nodata is None else nodata)
+def _make_ifds(shapes, dt, comp, pred, bs, bigtiff, nodata, transform, epsg, gdal_ghost):
+    """IFDs of a pyramid (level 0 first) with reserved tile tables -> (ifds, [(h, w, tiles_y, tiles_x)], IFD offsets,
+    offset of the first tile byte)."""
     ifds: List[_Ifd] = []
     grids = []
-    for li, lv in enumerate(levels):
-        h, w = int(lv.shape[0]), int(lv.shape[1])
+    for li, (h, w) in enumerate(shapes):
         ty, tx = (h + bs - 1) // bs, (w + bs - 1) // bs
         grids.append((h, w, ty, tx))
         ifd = _Ifd(bigtiff)
@@ -257,7 +245,59 @@ def write_tiff_pyramid(path: str, levels: Sequence, *, nodata=None, transform=No
         ifd_off.append(pos)
         pos += ifd.size()
         pos = (pos + 15) // 16 * 16
-    data_start = pos
+    return ifds, grids, ifd_off, pos
+
+
+def _write_header_and_ifds(fh, ifds, ifd_off, bigtiff, gdal_ghost) -> None:
+    fh.seek(0)
+    fh.write(struct.pack("<2sHHHQ", b"II", 43, 8, 0, ifd_off[0]) if bigtiff else struct.pack("<2sHI", b"II", 42, ifd_off[0]))
+    if gdal_ghost:
+        fh.write(GDAL_GHOST)
+    for i, ifd in enumerate(ifds):
+        fh.seek(ifd_off[i])
+        fh.write(ifd.serialise(ifd_off[i], ifd_off[i + 1] if i + 1 < len(ifds) else 0))
+
+
+def encode_tile_rows(band: np.ndarray, dt, bs: int, fill, pred: int, comp: int, level: int, pool) -> list:
+    """Compressed blobs of the tiles of `band` (a whole number of tile rows, except the last row of the raster), row
+    major; edge tiles are padded to full blocks."""
+    def enc(tile):
+        raw = apply_predictor(tile, pred)
+        if comp == COMPRESSION_ZSTD:
+            return zstd_compress(raw, level)
+        if comp == COMPRESSION_DEFLATE:
+            return zlib.compress(raw, max(1, min(9, int(level))))
+        return raw
+
+    h, w = band.shape
+    tiles = []
+    for r0 in range(0, h, bs):
+        for c0 in range(0, w, bs):
+            t = band[r0:r0 + bs, c0:c0 + bs]
+            if t.shape != (bs, bs):
+                full = np.full((bs, bs), fill, dtype=dt)
+                full[: t.shape[0], : t.shape[1]] = t
+                t = full
+            tiles.append(np.ascontiguousarray(t))
+    return list(pool.map(enc, tiles))
+
+
+def write_tiff_pyramid(path: str, levels: Sequence, *, nodata=None, transform=None, epsg=None, blocksize: int = 512,
+                       compress: str = "zstd", level: int = 1, bigtiff: bool = True, num_threads: Optional[int] = None,
+                       row_reader=None, gdal_ghost: bool = True) -> dict:
+    """Write levels[0] (full resolution) and levels[1:] (overviews, each a NumPy array or any object with .shape /
+    .dtype whose rows `row_reader(level_obj, r0, r1)` returns as a NumPy array) as one tiled (Big)TIFF."""
+    comp = {"zstd": COMPRESSION_ZSTD, "deflate": COMPRESSION_DEFLATE, "none": COMPRESSION_NONE}[compress]
+    if row_reader is None:
+        row_reader = lambda a, r0, r1: np.asarray(a[r0:r1])
+    dt = np.dtype(str(levels[0].dtype).replace("torch.", ""))
+    if dt not in (np.dtype("uint8"), np.dtype("int16"), np.dtype("float32")):
+        raise ValueError(f"unsupported sample type {dt}")
+    pred = predictor_for_dtype(dt) if comp != COMPRESSION_NONE else 1
+    bs = int(blocksize)
+    fill = np.nan if dt.kind == "f" else (0 if nodata is None else nodata)
+    ifds, grids, ifd_off, data_start = _make_ifds([(int(lv.shape[0]), int(lv.shape[1])) for lv in levels], dt, comp, pred,
+                                                  bs, bigtiff, nodata, transform, epsg, gdal_ghost)
 
     def encode_tile(tile: np.ndarray) -> bytes:
         raw = apply_predictor(tile, pred)
@@ -306,13 +346,7 @@ def write_tiff_pyramid(path: str, levels: Sequence, *, nodata=None, transform=No
             stats["levels"].append({"level": li, "shape": (h, w), "tiles": ty * tx, "bytes": int(sum(cnts))})
         if not bigtiff and cur >= 2 ** 32:
             raise ValueError("file exceeds 4 GiB: use bigtiff=True")
-        fh.seek(0)
-        fh.write(struct.pack("<2sHHHQ", b"II", 43, 8, 0, ifd_off[0]) if bigtiff else struct.pack("<2sHI", b"II", 42, ifd_off[0]))
-        if gdal_ghost:
-            fh.write(GDAL_GHOST)
-        for i, ifd in enumerate(ifds):
-            fh.seek(ifd_off[i])
-            fh.write(ifd.serialise(ifd_off[i], ifd_off[i + 1] if i + 1 < len(ifds) else 0))
+        _write_header_and_ifds(fh, ifds, ifd_off, bigtiff, gdal_ghost)
         stats["bytes"] = cur
     stats["levels"].reverse()
     stats.update(compression=compress, predictor=pred, blocksize=bs, bigtiff=bool(bigtiff))

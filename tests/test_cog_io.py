@@ -200,3 +200,67 @@ def test_topousm_uint8_to_cog_end_to_end(tmp_path):
     assert np.array_equal(got == 0, want == 0)
     assert np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1
     assert meta["nodata"] == 0.0 and meta["levels"] == 9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_sharded_cog_writer_equals_single_writer(tmp_path, world):
+    """io/cog_sharded.write_cog_sharded (config 5: every rank compresses the tiles of its own band, distributed
+    overview levels, gathered small levels) writes byte for byte the file of io/cog_writer.write_cog.  The ranks are
+    played one after the other by a stand-in `dist` (real NCCL: tests/test_gpu_sharding.py, profiles/tools/run_config5.py)."""
+    torch = pytest.importorskip("torch")
+    import threading
+    from fujishadergpu_b200.io.cog_sharded import tile_aligned_bounds, write_cog_sharded
+    from fujishadergpu_b200.io.cog_writer import write_cog
+    H, W = 5 * 1024 + 300, 2100
+    g = torch.Generator(device="cuda").manual_seed(5)
+    full = (torch.rand((H, W), generator=g, device="cuda") * 255).to(torch.uint8)
+    full[1000:1300, 500:900] = 0
+    ref = str(tmp_path / "ref.tif")
+    write_cog(ref, full)
+    out = str(tmp_path / f"sharded{world}.tif")
+    own = tile_aligned_bounds(H, world)
+
+    class FakeDist:   # threads play the ranks; all_gather_object / barrier through a shared table
+        def __init__(self):
+            self.lock = threading.Condition()
+            self.round = {}
+            self.tl = threading.local()
+
+        def _collect(self, key, value):
+            with self.lock:
+                slot = self.round.setdefault(key, {})
+                slot[self.tl.rank] = value
+                self.lock.notify_all()
+                self.lock.wait_for(lambda: len(self.round[key]) == world)
+                return [self.round[key][q] for q in range(world)]
+
+        def all_gather_object(self, out_list, obj):
+            self.tl.n = getattr(self.tl, "n", 0) + 1
+            out_list[:] = self._collect(("g", self.tl.n), obj)
+
+        def barrier(self):
+            self.tl.n = getattr(self.tl, "n", 0) + 1
+            self._collect(("b", self.tl.n), None)
+
+    fd = FakeDist()
+    errs = []
+
+    def run(rank):
+        try:
+            fd.tl.rank = rank
+            torch.cuda.set_device(0)
+            a, b = own[rank]
+            write_cog_sharded(out, full[a:b].contiguous(), H, rank, world, dist=fd if world > 1 else None)
+        except Exception as exc:   # pragma: no cover
+            errs.append(exc)
+            with fd.lock:
+                fd.lock.notify_all()
+
+    threads = [threading.Thread(target=run, args=(q,)) for q in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=300)
+    assert not errs, errs
+    assert open(out, "rb").read() == open(ref, "rb").read()
