@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(256) ao_raw_kernel(const float* __restrict__ d
         const AoSample sm = tab.s[k];
         const float v = __ldg(pc + ((int64_t)sm.oy * ld + sm.ox));
         const float d = v - c;
-        if (d > 0.f) {
-          float o = div_const(atanf(div_const(d, sm.dist, sm.rinv)), max_angle, inv_ma);
+        if (d > 0.f) {   // (approximate SFU forms, fsg_common.cuh: contract 1e-5 relative / 1e-6 absolute)
+          float o = fast_atan_pos(d * sm.rinv) * inv_ma;
           o = fminf(o, 1.0f);
           total = total + o * sm.factor;
         }
@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(256) ao_raw_kernel(const float* __restrict__ d
         const int64_t sy = clamp_index(y + sm.oy, H), sx = clamp_index(x + sm.ox, W);
         const float v = __ldg(dem + sy * ld + sx);
         if (v == v) {
-          float o = fmaxf(0.f, atanf((v - c) / sm.dist)) / max_angle;
+          const float d = v - c;
+          float o = d > 0.f ? fast_atan_pos(d * sm.rinv) * (1.0f / max_angle) : 0.f;
           o = fminf(o, 1.0f);
           total = total + o * sm.factor;
           count = count + 1.f;
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) ao_finish_kernel(const float* __restrict_
   if (x >= W) return;
   for (int64_t y = blockIdx.y; y < H; y += gridDim.y) {
     const float c = dem[y * ld_in + x];
-    float r = powf(sm[y * W + x], (float)(1 / 2.2));
+    float r = fast_gamma22(sm[y * W + x]);
     if (stretch) r = fmaxf((r - lo) / scale, 0.f);
     if (c != c) r = nanf("");
     store_out(out, y * ld_out + x, r, enc);

@@ -97,6 +97,37 @@ __device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
 }
 __device__ __forceinline__ int64_t clamp_index(int64_t i, int64_t n) { return i < 0 ? 0 : (i >= n ? n - 1 : i); }
 
+// ---- approximate SFU forms ------------------------------------------------------------------------
+// For the outputs whose contract is 1e-5 relative / 1e-6 absolute against the reference (hillshade, slope,
+// curvature, openness, ambient occlusion) -- NOT for topousm_fast, whose window means must be exact.
+// rsqrt / sqrt / rcp / ex2 / lg2 .approx are within 2 ulp (<= 2.4e-7 relative); the arctangent polynomial within
+// 1.7e-7 relative.  The measured distance to the oracle is asserted in tests/test_gpu_parity.py.
+__device__ __forceinline__ float sfu_rsqrt(float x) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sfu_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sfu_rcp(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sfu_ex2(float x) { float r; asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sfu_lg2(float x) { float r; asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// arctan(x) for x >= 0 (NaN -> NaN, +inf -> pi/2): atan(t) = t * P(t^2) on [0, 1] (degree-8 least-squares fit on
+// Chebyshev nodes), atan(x) = pi/2 - atan(1/x) above 1
+__device__ __forceinline__ float fast_atan_pos(float x) {
+  const bool big = x > 1.f;
+  const float t = big ? sfu_rcp(x) : x;
+  const float u = t * t;
+  float a = 0.0028340641874819994f;
+  a = fmaf(a, u, -0.016005029901862144f);
+  a = fmaf(a, u, 0.042587608098983765f);
+  a = fmaf(a, u, -0.07495445758104324f);
+  a = fmaf(a, u, 0.10636754333972931f);
+  a = fmaf(a, u, -0.14202570915222168f);
+  a = fmaf(a, u, 0.19992484152317047f);
+  a = fmaf(a, u, -0.3333306610584259f);
+  a = fmaf(a * u, t, t);   // t * (1 + u * q(u))
+  return big ? 1.57079637050628662f - a : a;
+}
+__device__ __forceinline__ float fast_atan(float x) { return copysignf(fast_atan_pos(fabsf(x)), x); }
+// x^(1/2.2) for x in [0, 1] (0 -> 0, NaN -> NaN)
+__device__ __forceinline__ float fast_gamma22(float x) { return sfu_ex2((float)(1 / 2.2) * sfu_lg2(x)); }
+
 // Correctly rounded f64 quotient s/n for a small positive integer n given inv = 1/n (rounded):
 // one Newton correction of the rounded product (Markstein).
 __device__ __forceinline__ double div_by_count(double s, double n, double inv) {

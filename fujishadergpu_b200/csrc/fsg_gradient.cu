@@ -96,26 +96,6 @@ __device__ __noinline__ float gap_fill(const GradParams& p, int64_t gy, int64_t 
 
 // x^1.5 for x >= 0 as x*sqrt(x): two correctly rounded ops (<= 1.5 ulp; the reference's powf is not
 // correctly rounded either) instead of the ~100-instruction powf
-__device__ __forceinline__ float sfu_sqrt(float x) {
-  float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float sfu_rcp(float x) {
-  float r;
-  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float sfu_ex2(float x) {
-  float r;
-  asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float sfu_lg2(float x) {
-  float r;
-  asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
 __device__ __forceinline__ float pow15(float x) { return x * sfu_sqrt(x); }
 
 // derivative along one axis of a shared-memory plane; `g` is the global index along the axis,
@@ -157,52 +137,15 @@ __device__ __forceinline__ float curv_result(const GradParams& p, float dy, floa
   return sfu_ex2((float)(-1 / 2.2) * sfu_lg2(1.f + E));
 }
 
-// Approximate SFU forms.  The contract for these outputs is 1e-5 relative / 1e-6 absolute against the reference
-// (BASELINE.json north_star), not bit-identity: rsqrt.approx / sqrt.approx / rcp.approx are within 2 ulp
-// (<= 2.4e-7 relative), the arctangent polynomial within 1.7e-7 relative -- measured maxima against the oracle are
-// asserted in tests/test_gpu_parity.py.  IEEE sqrt, division and the library atanf cost ~45 of the former
-// 75 instructions per pixel and kept the stencil at 41 % of the HBM roofline.
-__device__ __forceinline__ float fast_rsqrt(float x) {
-  float r;
-  asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float fast_sqrt(float x) {
-  float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float fast_rcp(float x) {
-  float r;
-  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-// arctan(x) for x >= 0 (NaN -> NaN): atan(t) = t * P(t^2) on [0, 1] (degree-8 least-squares fit on Chebyshev nodes,
-// 1.7e-7 relative in f32), atan(x) = pi/2 - atan(1/x) above 1
-__device__ __forceinline__ float fast_atan_pos(float x) {
-  const bool big = x > 1.f;
-  const float t = big ? fast_rcp(x) : x;
-  const float u = t * t;
-  float a = 0.0028340641874819994f;
-  a = fmaf(a, u, -0.016005029901862144f);
-  a = fmaf(a, u, 0.042587608098983765f);
-  a = fmaf(a, u, -0.07495445758104324f);
-  a = fmaf(a, u, 0.10636754333972931f);
-  a = fmaf(a, u, -0.14202570915222168f);
-  a = fmaf(a, u, 0.19992484152317047f);
-  a = fmaf(a, u, -0.3333306610584259f);
-  a = fmaf(a * u, t, t);   // t * (1 + u * q(u))
-  return big ? 1.57079637050628662f - a : a;
-}
-
+// (approximate SFU forms and the arctangent polynomial: fsg_common.cuh)
 template <int CLASS>
 __device__ __forceinline__ float grad_result(const GradParams& p, float dy, float dx) {
   if (CLASS == 0) {
     float e = dx * p.sgx, n = dy * p.sgy;
-    float hs = (((-e) * p.lx + (-n) * p.ly) + p.lz) * fast_rsqrt((e * e + n * n) + 1.0f);
+    float hs = (((-e) * p.lx + (-n) * p.ly) + p.lz) * sfu_rsqrt((e * e + n * n) + 1.0f);
     return fminf(fmaxf(hs, 0.f), 1.f);
   } else {
-    const float g = fast_sqrt(dx * dx + dy * dy);
+    const float g = sfu_sqrt(dx * dx + dy * dy);
     if (p.sub == FSG_SLOPE_PERCENT) return g * 100.f;   // tan(arctan(g)) * 100 (_impl_slope.py:30-31)
     const float s = fast_atan_pos(g);
     if (p.sub == FSG_SLOPE_DEGREE) return s * (180.0f / 3.14159274101257324f);  // npy_rad2degf
@@ -220,9 +163,9 @@ __device__ __forceinline__ float grad_interior(const GradParams& p, float dyr, f
   const float g2 = fmaf(dxr * dxr, p.ix2, (dyr * dyr) * p.iy2);   // dx^2 + dy^2
   if (CLASS == 0) {
     const float num = fmaf(dxr, p.kx, fmaf(dyr, p.ky, p.lz));    // (-e) lx + (-n) ly + lz
-    return __saturatef(num * fast_rsqrt(g2 + 1.0f));
+    return __saturatef(num * sfu_rsqrt(g2 + 1.0f));
   } else {
-    const float g = fast_sqrt(g2);
+    const float g = sfu_sqrt(g2);
     if (p.sub == FSG_SLOPE_PERCENT) return g * 100.f;
     const float s = fast_atan_pos(g);
     if (p.sub == FSG_SLOPE_DEGREE) return s * (180.0f / 3.14159274101257324f);

@@ -19,6 +19,7 @@
 namespace fsg {
 
 constexpr int OP_MAX_SAMPLES = 64 * 10;
+constexpr int OPI_ROWS = 8;    // rows of an interior tile (128 columns x 8 rows, four pixels per thread)
 
 struct OpenParams {
   const float* dem;
@@ -27,15 +28,17 @@ struct OpenParams {
   int n_dirs;
   int negative;
   int stretch;
-  float stretch_lo, stretch_scale;
+  float stretch_lo, stretch_scale, stretch_rinv;
   EncodeDev enc;
+  int64_t rx0, ry0, rx1, ry1;   // openness_kernel: the rectangle of pixels this launch covers (global coordinates)
 };
 
 struct OpenSample {
   short ox, oy;
   float dist;  // f32(max(hypot(ox*sx, oy*sy), 1e-9))
   int off;     // oy * ld_in + ox (elements)
-  float rinv;  // f32(1 / dist): division by the constant distance = multiply + one FMA correction
+  float rinv;  // f32(1 / dist): the division by the constant distance is a multiplication (<= 1.5 ulp; the contract
+               // of this output is 1e-5 relative / 1e-6 absolute, tests/test_gpu_parity.py asserts the measured error)
 };
 
 // Passed BY VALUE as a kernel parameter (read through the constant bank, broadcast to the warp):
@@ -45,16 +48,26 @@ struct OpenTable {
   OpenSample s[OP_MAX_SAMPLES];
 };
 
+// mean zenith / nadir angle -> display value: / (pi/2), clip, gamma 1/2.2, optional stretch (same ops in both kernels)
+__device__ __forceinline__ float open_finish(const OpenParams& p, float asum, float acnt) {
+  float o = asum * sfu_rcp(fmaxf(acnt, 1.f));
+  o = __saturatef(o * (float)(2.0 / 3.14159265358979323846));
+  float res = fast_gamma22(o);
+  if (p.stretch) res = fmaxf((res - p.stretch_lo) * p.stretch_rinv, 0.f);
+  return res;
+}
+
 __global__ void __launch_bounds__(256) openness_kernel(OpenParams p, const __grid_constant__ OpenTable tab, int fast_halo) {
   if (fast_halo >= 0) {   // interior 128 x 8 tiles are done by openness_interior_kernel
-    const int64_t tx0 = (int64_t)(blockIdx.x / 2) * 128, ty0 = p.out_row0 + (int64_t)(blockIdx.y / 2) * 8;
-    if (tx0 >= fast_halo && tx0 + 128 + fast_halo <= p.W && ty0 >= fast_halo && ty0 + 8 + fast_halo <= p.H &&
-        ty0 + 8 <= p.out_row0 + p.out_rows)
+    const int64_t px = p.rx0 + (int64_t)blockIdx.x * 64, py = p.ry0 + (int64_t)blockIdx.y * 4;
+    const int64_t tx0 = px / 128 * 128, ty0 = p.out_row0 + (py - p.out_row0) / OPI_ROWS * OPI_ROWS;
+    if (tx0 >= fast_halo && tx0 + 128 + fast_halo <= p.W && ty0 >= fast_halo && ty0 + OPI_ROWS + fast_halo <= p.H &&
+        ty0 + OPI_ROWS <= p.out_row0 + p.out_rows)
       return;
   }
-  const int64_t x = (int64_t)blockIdx.x * 64 + (threadIdx.x & 63);
-  const int64_t y = p.out_row0 + (int64_t)blockIdx.y * 4 + (threadIdx.x >> 6);
-  if (x >= p.W || y >= p.out_row0 + p.out_rows) return;
+  const int64_t x = p.rx0 + (int64_t)blockIdx.x * 64 + (threadIdx.x & 63);
+  const int64_t y = p.ry0 + (int64_t)blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= p.rx1 || y >= p.ry1) return;
   const float* base = p.dem - p.buf_row0 * p.ld_in;  // address of global row 0
   const float c = base[y * p.ld_in + x];
   float res;
@@ -72,52 +85,49 @@ __global__ void __launch_bounds__(256) openness_kernel(OpenParams p, const __gri
         if (sy < 0 || sy >= p.H || sx < 0 || sx >= p.W) continue;  // padded validity = False
         float v = base[sy * p.ld_in + sx];
         if (v != v) continue;
-        float t = (v - c) / sm.dist;
+        float t = (v - c) * sm.rinv;
         if (!seen) ext = t;
         else ext = p.negative ? fminf(ext, t) : fmaxf(ext, t);
         seen = true;
       }
       if (seen) {
         // np.maximum(ext, angle) starting from -pi/2 (f32): atan never drops below it
-        float a = atanf(ext);
+        float a = fast_atan(ext);
         a = p.negative ? fminf(half_pi, a) : fmaxf(-half_pi, a);
         float dang = p.negative ? half_pi + a : half_pi - a;
         asum = asum + dang;
         acnt = acnt + 1.f;
       }
     }
-    float o = asum / fmaxf(acnt, 1.f);
-    o = o / half_pi;
-    o = fminf(fmaxf(o, 0.f), 1.f);
-    res = powf(o, (float)(1 / 2.2));
-    if (p.stretch) res = fmaxf((res - p.stretch_lo) / p.stretch_scale, 0.f);
+    res = open_finish(p, asum, acnt);
   }
   store_out(p.out, (y - p.out_row0) * p.ld_out + x, res, p.enc);
 }
 
 
-// Interior tiles (every sample of every pixel lies inside the raster): no bounds checks, linear sample
-// offsets, and (v - c) / dist evaluated as q = d*rinv corrected by one FMA residual step, which returns
-// the correctly rounded quotient (Markstein) -- the same f32 value as the IEEE division of the generic
-// kernel, at a third of the instructions.  Four pixels per thread (2 x 2 at strides 64 / 4): more loads in flight,
-// and the per-sample constant loads, address arithmetic and loop bookkeeping are shared by four pixels.
+// Interior tiles (every sample of every pixel lies inside the raster): no bounds checks, linear sample offsets, the
+// division by the constant distance as a multiplication.  Four pixels per thread (2 columns 64 apart x 2 rows 4
+// apart).  The ncu profile of round 1's version showed the kernel issue bound (90 % issue-slot use, L1 28 %, L2
+// 31 %): 13 instructions per sample and pixel, 10 of 30 per sample on 64-bit address arithmetic.  Now: one add per
+// row pointer serves two loads, the quotient is one multiply.  (Eight pixels per thread, 128 x 16 tiles: measured
+// slower, 34 -> 52 ms at 32768^2 -- fewer resident warps, larger L1 footprint.)
 template <bool NEG>
 __global__ void __launch_bounds__(256) openness_interior_kernel(const __grid_constant__ OpenParams p,
                                                                 const __grid_constant__ OpenTable tab, int halo) {
-  const int64_t x0 = (int64_t)blockIdx.x * 128, y0 = p.out_row0 + (int64_t)blockIdx.y * 8;
+  const int64_t x0 = (int64_t)blockIdx.x * 128, y0 = p.out_row0 + (int64_t)blockIdx.y * OPI_ROWS;
   // tiles that touch the border band are left to openness_kernel (launched over the same area)
-  const bool interior = x0 >= halo && x0 + 128 + halo <= p.W && y0 >= halo && y0 + 8 + halo <= p.H &&
-                        y0 + 8 <= p.out_row0 + p.out_rows;
+  const bool interior = x0 >= halo && x0 + 128 + halo <= p.W && y0 >= halo && y0 + OPI_ROWS + halo <= p.H &&
+                        y0 + OPI_ROWS <= p.out_row0 + p.out_rows;
   if (!interior) return;
-  // this thread's four pixels: columns x and x + 64 (coalesced warp loads) of rows y and y + 4; the sample
-  // table entry (three constant-bank loads) and the loop bookkeeping are shared by the four
   const int64_t x = x0 + (threadIdx.x & 63);
   const int64_t y = y0 + (threadIdx.x >> 6);
-  const float* pc = p.dem + (y - p.buf_row0) * p.ld_in + x;
-  const int64_t down = 4 * p.ld_in;
-  constexpr int NP = 4;
+  constexpr int NR = OPI_ROWS / 4, NP = 2 * NR;
+  const float* pr[NR];   // this thread's rows y, y + 4 at column x
+#pragma unroll
+  for (int r = 0; r < NR; ++r) pr[r] = p.dem + (y + 4 * r - p.buf_row0) * p.ld_in + x;
   float c[NP], asum[NP], acnt[NP];
-  c[0] = __ldg(pc); c[1] = __ldg(pc + 64); c[2] = __ldg(pc + down); c[3] = __ldg(pc + down + 64);
+#pragma unroll
+  for (int r = 0; r < NR; ++r) { c[2 * r] = __ldg(pr[r]); c[2 * r + 1] = __ldg(pr[r] + 64); }
 #pragma unroll
   for (int j = 0; j < NP; ++j) { asum[j] = 0.f; acnt[j] = 0.f; }
   const float half_pi = (float)(3.14159265358979323846 / 2);
@@ -129,16 +139,18 @@ __global__ void __launch_bounds__(256) openness_interior_kernel(const __grid_con
     const int k1 = tab.dir_start[d + 1];
 #pragma unroll 5
     for (int k = tab.dir_start[d]; k < k1; ++k) {
-      const OpenSample sm = tab.s[k];
-      const float* ps = pc + sm.off;
+      const int off = tab.s[k].off;
+      const float rinv = tab.s[k].rinv;
       float v[NP];
-      v[0] = __ldg(ps); v[1] = __ldg(ps + 64); v[2] = __ldg(ps + down); v[3] = __ldg(ps + down + 64);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const float* ps = pr[r] + off;
+        v[2 * r] = __ldg(ps);
+        v[2 * r + 1] = __ldg(ps + 64);
+      }
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
-        const float dd = v[j] - c[j];
-        float q = dd * sm.rinv;
-        const float r = fmaf(-q, sm.dist, dd);
-        q = (r == r) ? fmaf(r, sm.rinv, q) : q;   // residual is NaN only for infinite / NaN quotients
+        const float q = (v[j] - c[j]) * rinv;
         // a NaN sample gives a NaN quotient, which fminf / fmaxf ignore: invalid samples drop out by themselves
         e[j] = NEG ? fminf(e[j], q) : fmaxf(e[j], q);
       }
@@ -146,23 +158,18 @@ __global__ void __launch_bounds__(256) openness_interior_kernel(const __grid_con
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       if (e[j] != start) {   // at least one valid sample in this direction
-        float a = atanf(e[j]);
+        float a = fast_atan(e[j]);
         a = NEG ? fminf(half_pi, a) : fmaxf(-half_pi, a);
         asum[j] = asum[j] + (NEG ? half_pi + a : half_pi - a);
         acnt[j] = acnt[j] + 1.f;
       }
     }
   }
-  const int64_t o = (y - p.out_row0) * p.ld_out + x;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    float oo = asum[j] / fmaxf(acnt[j], 1.f);
-    oo = oo / half_pi;
-    oo = fminf(fmaxf(oo, 0.f), 1.f);
-    float res = powf(oo, (float)(1 / 2.2));
-    if (p.stretch) res = fmaxf((res - p.stretch_lo) / p.stretch_scale, 0.f);
+    float res = open_finish(p, asum[j], acnt[j]);
     if (c[j] != c[j]) res = nanf("");
-    store_out(p.out, o + (j & 1) * 64 + (int64_t)(j >> 1) * 4 * p.ld_out, res, p.enc);
+    store_out(p.out, (y + 4 * (j >> 1) - p.out_row0) * p.ld_out + x + (j & 1) * 64, res, p.enc);
   }
 }
 
@@ -185,6 +192,7 @@ static int run_openness(const float* dem, void* out, const fsg_window* win, int 
   p.n_dirs = n_dirs; p.negative = negative ? 1 : 0;
   p.stretch = (!is_none(stretch_scale) && !is_none(stretch_lo) && stretch_scale > 1e-12) ? 1 : 0;
   p.stretch_lo = (float)stretch_lo; p.stretch_scale = (float)stretch_scale;
+  p.stretch_rinv = p.stretch ? (float)(1.0 / (double)p.stretch_scale) : 0.f;
   p.enc = make_encode(enc);
   if (p.out_rows == 0) return FSG_OK;
   dim3 grid((unsigned)((p.W + 63) / 64), (unsigned)((p.out_rows + 3) / 4));
@@ -194,20 +202,46 @@ static int run_openness(const float* dem, void* out, const fsg_window* win, int 
   bool fast = (double)p.ld_in * (double)(D + 1) < 2.0e9 && p.buf_row0 <= (p.out_row0 - D > 0 ? p.out_row0 - D : 0) &&
               p.buf_row0 + p.buf_rows >= (p.out_row0 + p.out_rows + D < p.H ? p.out_row0 + p.out_rows + D : p.H) &&
               !getenv("FSG_OPENNESS_GENERIC");
-  if (fast) {
-    OpenTable t2 = tab;
+  OpenTable t2 = tab;
+  {
     const int ns = t2.dir_start[n_dirs];
     for (int k = 0; k < ns; ++k) {
-      t2.s[k].off = (int)((int64_t)t2.s[k].oy * p.ld_in + t2.s[k].ox);
+      t2.s[k].off = fast ? (int)((int64_t)t2.s[k].oy * p.ld_in + t2.s[k].ox) : 0;
       t2.s[k].rinv = 1.0f / t2.s[k].dist;
     }
-    dim3 g2((unsigned)((p.W + 127) / 128), (unsigned)((p.out_rows + 7) / 8));
+  }
+  if (fast) {
+    dim3 g2((unsigned)((p.W + 127) / 128), (unsigned)((p.out_rows + OPI_ROWS - 1) / OPI_ROWS));
     if (p.negative) openness_interior_kernel<true><<<g2, 256, 0, (cudaStream_t)stream>>>(p, t2, D);
     else openness_interior_kernel<false><<<g2, 256, 0, (cudaStream_t)stream>>>(p, t2, D);
     FSG_LAUNCH_OK();
-    openness_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, t2, D);
+    // the border band (and whatever the tile grid leaves over): four rectangles of the generic kernel instead of a
+    // launch over the whole raster whose CTAs mostly exit at once (4.2 M empty CTAs at 32768^2)
+    const int64_t R0 = p.out_row0, R1 = p.out_row0 + p.out_rows;
+    int64_t XL = ((int64_t)D + 127) / 128 * 128, XR = p.W - D >= 128 ? (p.W - D) / 128 * 128 : 0;
+    if (XL > p.W) XL = p.W;
+    if (XR < XL) XR = XL;
+    // interior tile rows are anchored at out_row0: first row y with y >= D, last tile end <= min(H - D, R1)
+    int64_t YT = R0 + ((D > R0 ? D - R0 : 0) + OPI_ROWS - 1) / OPI_ROWS * OPI_ROWS;
+    const int64_t ylim = (p.H - D < R1 ? p.H - D : R1);
+    int64_t YB = ylim > R0 ? R0 + (ylim - R0) / OPI_ROWS * OPI_ROWS : R0;
+    if (YT > R1) YT = R1;
+    if (YB < YT) YB = YT;
+    auto rect = [&](int64_t x0, int64_t x1, int64_t y0, int64_t y1) {
+      if (x1 <= x0 || y1 <= y0) return;
+      OpenParams q = p;
+      q.rx0 = x0; q.rx1 = x1; q.ry0 = y0; q.ry1 = y1;
+      dim3 g((unsigned)((x1 - x0 + 63) / 64), (unsigned)((y1 - y0 + 3) / 4));
+      openness_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(q, t2, D);
+      count_launch();
+    };
+    rect(0, XL, R0, R1);
+    rect(XR, p.W, R0, R1);
+    rect(XL, XR, R0, YT);
+    rect(XL, XR, YB, R1);
   } else {
-    openness_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, tab, -1);
+    p.rx0 = 0; p.rx1 = p.W; p.ry0 = p.out_row0; p.ry1 = p.out_row0 + p.out_rows;
+    openness_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, t2, -1);
   }
   prof_end(slot, (cudaStream_t)stream);
   FSG_LAUNCH_OK();
