@@ -159,6 +159,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+PROF_TAGS = {1: "fused_main", 2: "pyramid", 3: "coarse_means", 6: "fused_stats_windows"}
+
+
+def kernel_breakdown(prof, steps):
+    """Device milliseconds per step of the library's profiler tags (events around the launches, own stream)."""
+    out = {}
+    for tag, ms in prof:
+        name = PROF_TAGS.get(tag)
+        if name:
+            out[name] = out.get(name, 0.0) + ms / max(1, steps)
+    return {k: round(v, 3) for k, v in out.items()}
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -338,7 +351,8 @@ def run_gpu_arm(a) -> None:
                    "radii": RADII, "size": S, "l2_policy": "inputs (16 GiB) far larger than the 126 MB L2",
                    "main_pass_ms": main_ms, "stats_prepass_ms": ms_step - main_ms,
                    "main_pass_mpx_s": H * W / (main_ms * 1e-3) / 1e6,
-                   "fused_kernel_ms": fused_ms, "scale_p99": float(st[0]), "respeculated_steps": redo[0],
+                   "fused_kernel_ms": fused_ms, "kernel_ms_per_step": kernel_breakdown(prof, a.steps),
+                   "scale_p99": float(st[0]), "respeculated_steps": redo[0],
                    "out_checksum": f"{checksum:016x}"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "fsg::fused_kernel_v8<3> + fused_kernel_v6 on the raster borders (whole fused pass of the main pass)", "peak_source": peak_src,

@@ -23,6 +23,7 @@ inject their own stand-in (tests/test_sharding_gloo.py); the product backend is 
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -183,14 +184,68 @@ def dem_halo_rows(H: int, world: int, rank: int, radii, pixel_size=1.0, backend=
     return mirror_need(a - halo, b - 1 + halo, H, reflect=True) if b > a else (0, 0)
 
 
-def haloed_band(H: int, W: int, world: int, rank: int, radii, pixel_size=1.0, device="cuda", backend=None):
+def haloed_band(H: int, W: int, world: int, rank: int, radii, pixel_size=1.0, device="cuda", backend=None,
+                peer_group=None):
     """(ext, band): `ext` holds the rows dem_halo_rows() names, `band` is the view of this rank's own rows inside
     it.  A loader that writes its rows into `band` and passes `dem_ext=ext` to topousm_fast_sharded spares the
-    per-call copy of the band into a halo buffer (2 x band bytes of HBM traffic per step)."""
+    per-call copy of the band into a halo buffer (2 x band bytes of HBM traffic per step).
+    peer_group (a NCCL process group, every rank calls): `ext` is allocated in symmetric memory, so that the other
+    ranks of the node can read this band directly over NVLink (PeerBands; the window gather of the statistics
+    pre-pass then needs no send / receive pairs).  Falls back to a private buffer when symmetric memory is not
+    available."""
     lo, hi = dem_halo_rows(H, world, rank, radii, pixel_size, backend)
     a, b = band_bounds(H, world)[rank]
+    if peer_group is not None and world > 1:
+        pb = PeerBands.create(H, W, world, rank, radii, pixel_size, device, peer_group, backend)
+        if pb is not None:
+            return pb.ext, pb.ext[a - lo:b - lo]
     ext = torch.empty((hi - lo, W), dtype=torch.float32, device=device)
     return ext, ext[a - lo:b - lo]
+
+
+class PeerBands:
+    """The DEM row bands of all ranks of one node, each in symmetric memory (torch.distributed._symmetric_memory:
+    CUDA virtual-memory handles exchanged at rendezvous, every rank maps every band).  band_of(q) is rank q's band as
+    a tensor on THIS device whose loads travel over NVLink / NVSwitch; barrier() orders the ranks on the stream
+    (8 us).  Found again from the halo buffer by of()."""
+
+    _by_ptr: dict = {}
+
+    def __init__(self, ext, hdl, views, rank, world):
+        self.ext, self.hdl, self.views, self.rank, self.world = ext, hdl, views, rank, world
+
+    @classmethod
+    def create(cls, H, W, world, rank, radii, pixel_size, device, group, backend=None):
+        try:
+            import torch.distributed._symmetric_memory as symm
+            spans = [dem_halo_rows(H, world, q, radii, pixel_size, backend) for q in range(world)]
+            rows = max(hi - lo for lo, hi in spans)          # symmetric allocations have one size on every rank
+            buf = symm.empty((rows, W), dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(buf, group)
+            own = band_bounds(H, world)
+            views = []
+            for q in range(world):
+                lo_q, _hi_q = spans[q]
+                whole = buf if q == rank else hdl.get_buffer(q, (rows, W), torch.float32)
+                views.append(whole[own[q][0] - lo_q:own[q][1] - lo_q])
+            lo, hi = spans[rank]
+            pb = cls(buf[: hi - lo], hdl, views, rank, world)
+            cls._by_ptr[pb.ext.data_ptr()] = pb
+            return pb
+        except Exception as e:   # no symmetric memory on this system: the point-to-point path is used instead
+            import warnings
+            warnings.warn(f"symmetric memory unavailable ({e!r}); window gather falls back to send / receive")
+            return None
+
+    @classmethod
+    def of(cls, dem_ext):
+        return cls._by_ptr.get(dem_ext.data_ptr()) if isinstance(dem_ext, torch.Tensor) and dem_ext.is_cuda else None
+
+    def band_of(self, q: int) -> torch.Tensor:
+        return self.views[q]
+
+    def barrier(self):
+        self.hdl.barrier()
 
 
 def topousm_fast_sharded(band: torch.Tensor, H: int, rank: int, world: int, *, radii, weights=None, pixel_size=1.0,
@@ -342,8 +397,10 @@ def topousm_fast_sharded_step(band: torch.Tensor, H: int, rank: int, world: int,
             if trace:
                 evs[1].record(side)
 
+    peers = PeerBands.of(dem_ext) if (dist is not None and world > 1) else None
+    start_prep.side_stream = side
     sharded_topousm_scale(band, H, rank, world, radii=radii, weights=weights, pixel_size=pixel_size, dist=dist,
-                          spec=spec, scale_out=scale_dev, after_gather=start_prep)
+                          spec=spec, scale_out=scale_dev, after_gather=start_prep, peers=peers)
     prep = box["prep"]
     if trace:
         evs[2].record(cur)
@@ -353,6 +410,8 @@ def topousm_fast_sharded_step(band: torch.Tensor, H: int, rank: int, world: int,
             t.record_stream(cur)
     res = topousm_sharded_finish(prep, weights=weights, norm_scale=None, norm_scale_dev=scale_dev,
                                  output_dtype=output_dtype, qp=qp, out=out)
+    if peers is not None:
+        peers.barrier()   # every rank has read what it needed of the other bands: they may be refilled now
     if trace:
         evs[3].record(cur)
         STEP_TRACE.append(evs)
@@ -402,6 +461,13 @@ def topousm_fast_sharded_with_stats(band: torch.Tensor, H: int, rank: int, world
 _PREP_STREAMS: dict = {}
 
 
+def _side_stream(device, name):
+    key = (device.index, name)
+    if key not in _PREP_STREAMS:
+        _PREP_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _PREP_STREAMS[key]
+
+
 # ------------------------------------------------------------------------------------------------
 # distributed exact percentile (np.percentile, method 'linear', f32 sample spread over the ranks)
 # ------------------------------------------------------------------------------------------------
@@ -413,8 +479,40 @@ def _np_lerp_percentile(lo: float, hi: float, n: int, q: float) -> Tuple[int, ob
     return prev, gamma
 
 
+class PeerExchange:
+    """The selection's exchange slots of every rank in symmetric memory (see fsg_select_peer_publish / _reduce)."""
+
+    _by_dev: dict = {}
+
+    def __init__(self, buf, hdl, world):
+        self.buf, self.hdl, self.world = buf, hdl, world
+        self.my_slots = int(buf.data_ptr())
+        self.peer_slots_dev = int(hdl.buffer_ptrs_dev)
+
+    @classmethod
+    def get(cls, device, group, world):
+        key = (device.index, id(group))
+        if key not in cls._by_dev:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                from .. import _lib
+                words = int(_lib.load().fsg_select_peer_slot_words())
+                buf = symm.empty((words,), dtype=torch.int64, device=device)
+                buf.zero_()
+                hdl = symm.rendezvous(buf, group)
+                cls._by_dev[key] = cls(buf, hdl, world)
+            except Exception as e:
+                import warnings
+                warnings.warn(f"symmetric memory unavailable ({e!r}); the selection uses all-reduce calls")
+                cls._by_dev[key] = None
+        return cls._by_dev[key]
+
+    def barrier(self):
+        self.hdl.barrier()
+
+
 def distributed_percentile(chunks, q: float, *, take_abs: bool, finite_only: bool, device, dist=None,
-                           hist_fn=None, rank_info_fn=None, key_to_float=None, scale_out=None):
+                           hist_fn=None, rank_info_fn=None, key_to_float=None, scale_out=None, peer_exchange=None):
     """np.percentile over the union of every rank's `chunks`; all ranks return the same float.
     Exact: 3-level radix select on order-preserving keys, histograms summed with all_reduce."""
     multi = dist is not None and dist.is_initialized() and dist.get_world_size() > 1
@@ -427,7 +525,8 @@ def distributed_percentile(chunks, q: float, *, take_abs: bool, finite_only: boo
             dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MIN)
 
         return k.staged_percentile(chunks, q, take_abs=take_abs, finite_only=finite_only, device=device,
-                                   all_reduce=all_reduce if multi else None, scale_out=scale_out)
+                                   all_reduce=all_reduce if multi else None, scale_out=scale_out,
+                                   peer_exchange=peer_exchange if multi else None)
 
     def allsum(t):
         if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
@@ -487,6 +586,16 @@ class Speculation:
         self.pending = []
 
     def guess(self, key, dev_values: torch.Tensor, default):
+        val = self.peek(key, default)
+        self.verify(key, dev_values, val)
+        return val
+
+    def peek(self, key, default):
+        """The value the planning uses (host only)."""
+        return list(Speculation._memory.get(key, default))
+
+    def verify(self, key, dev_values: torch.Tensor, val):
+        """Enqueue the copy of the device values that ok() compares with `val` (on the current stream)."""
         dev_values = dev_values.to(torch.int32).contiguous()
         n = int(dev_values.numel())
         slot = (key, len(self.pending))
@@ -495,9 +604,7 @@ class Speculation:
         host.copy_(dev_values, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev_values.device))
-        val = list(Speculation._memory.get(key, default))
-        self.pending.append((key, slot, host, ev, val))
-        return val
+        self.pending.append((key, slot, host, ev, list(val)))
 
     def ok(self) -> bool:
         good = True
@@ -515,31 +622,76 @@ class Speculation:
 # ------------------------------------------------------------------------------------------------
 # sharded statistics pre-pass (reference: algorithms/_norm_stats.py:176-298)
 # ------------------------------------------------------------------------------------------------
+_OWNER_MEMO: dict = {}
+
+
 def assign_window_owners(wins, own) -> List[int]:
-    """Owner rank of every statistics window: the rank that already holds most of the window's rows among
-    the ranks with the fewest windows so far (no rank gets more than ceil(n / world) windows), so that most
-    of a window does not travel at all.  Deterministic, identical on every rank."""
-    world = len(own)
-    cap = (len(wins) + world - 1) // world
+    """Owner rank of every statistics window: the assignment that lets the slowest rank finish first and, among
+    those, moves the fewest rows.  Cost of a window on a rank = one window evaluation + the time to fetch the rows
+    the rank lacks (measured on B200 / NVLink 5: 0.56 ms per 8256^2 window, ~500 GB/s per reader), in steps of 5 % of
+    a window so that bands differing by a few rows tie.  Exact (branch and bound: a window goes to a rank holding
+    part of it or to the least loaded of the others -- those are interchangeable).  Deterministic, identical on
+    every rank; the result of the pre-pass does not depend on it."""
+    key = (tuple(tuple(w) for w in wins), tuple(tuple(o) for o in own))
+    if key in _OWNER_MEMO:
+        return list(_OWNER_MEMO[key])
+    world, n = len(own), len(wins)
+    T_WIN_PER_PX = 0.56e-3 / (8256.0 * 8256.0)
+    BYTES_PER_S = 500e9
+
+    def cost(wi, q):
+        wy0, _wx0, tw, th = wins[wi]
+        ov = _overlap(own[q], (wy0, wy0 + th))
+        have = (ov[1] - ov[0]) if ov else 0
+        t_win = T_WIN_PER_PX * tw * th
+        return int(round((t_win + (th - have) * tw * 4 / BYTES_PER_S) / (0.05 * t_win)))
+
+    holders = [[q for q in range(world) if _overlap(own[q], (w[0], w[0] + w[3]))] for w in wins]
+    costs = [[cost(wi, q) for q in range(world)] for wi in range(n)]
+    # start: cheapest rank each (upper bound)
+    best_owner = [min(range(world), key=lambda q: (costs[wi][q], q)) for wi in range(n)]
+    load0 = [0] * world
+    for wi, q in enumerate(best_owner):
+        load0[q] += costs[wi][q]
+    best = [max(load0), sum(costs[wi][q] for wi, q in enumerate(best_owner))]
     load = [0] * world
-    owners = []
-    for (wy0, _wx0, _tw, th) in wins:
-        best, best_key = 0, None
-        for q in range(world):
-            if load[q] >= cap:
+    cur = [0] * n
+    rem_min = [0] * (n + 1)          # cheapest possible cost of the windows wi..n-1
+    for wi in range(n - 1, -1, -1):
+        rem_min[wi] = rem_min[wi + 1] + min(costs[wi])
+    budget = [200000]                # nodes; the best assignment found so far is used beyond (same on every rank)
+
+    def dfs(wi, total, top):
+        if wi == n:
+            if (top, total) < (best[0], best[1]):
+                best[0], best[1] = top, total
+                best_owner[:] = cur
+            return
+        cands = list(holders[wi])
+        others = [q for q in range(world) if q not in holders[wi]]
+        if others:
+            cands.append(min(others, key=lambda q: (load[q], q)))
+        for q in sorted(cands, key=lambda r: (costs[wi][r], r)):
+            c = costs[wi][q]
+            ntop = max(top, load[q] + c)
+            if (ntop, total + c + rem_min[wi + 1]) >= (best[0], best[1]) or budget[0] <= 0:
                 continue
-            ov = _overlap(own[q], (wy0, wy0 + th))
-            key = (-(ov[1] - ov[0]) if ov else 0, load[q], q)
-            if best_key is None or key < best_key:
-                best, best_key = q, key
-        owners.append(best)
-        load[best] += 1
-    return owners
+            budget[0] -= 1
+            load[q] += c
+            cur[wi] = q
+            dfs(wi + 1, total + c, ntop)
+            load[q] -= c
+
+    if n <= 32:
+        dfs(0, 0, 0)
+    _OWNER_MEMO[key] = list(best_owner)
+    return list(best_owner)
 
 
 def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, radii, weights, pixel_size=1.0,
                           dist=None, grid: int = 3, block_fn=None, select_fns=None, spec: Optional[Speculation] = None,
-                          scale_out: Optional[torch.Tensor] = None, after_gather=None):
+                          scale_out: Optional[torch.Tensor] = None, after_gather=None,
+                          peers: Optional["PeerBands"] = None):
     """p99(|raw topousm_fast|) over the reference's stratified full-resolution windows.  Each window is
     evaluated whole by ONE rank (assign_window_owners) after gathering its rows from the owning bands; the
     percentile over all windows is an exact distributed selection.
@@ -547,7 +699,10 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
     (Speculation) and the scale stays on the device (scale_out, NaN = no scale); returns scale_out.
     after_gather: called once the window gather is enqueued (the step starts the main-pass preparation there: the
     communication library runs its operations in issue order, so the bounding-box all-reduce and the window gather
-    go first and the halo exchange, which has to wait for the pyramid kernel anyway, last)."""
+    go first and the halo exchange, which has to wait for the pyramid kernel anyway, last).
+    peers (PeerBands): the bands live in symmetric memory -- a window owner copies the rows it lacks straight out of
+    the other ranks' bands (strided loads over NVLink, ~480 GB/s per reader, no packing, no send / receive pairing)
+    after one stream-ordered barrier; the caller issues the closing barrier before any band may change."""
     from ..algorithms._norm_stats import _norm_stat_window_geometry, stratified_windows
     W = int(band.shape[1])
     own = band_bounds(H, world)
@@ -571,12 +726,24 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
             n_rows = max(0, min((r1 - first + cov - 1) // cov, max(1, H // cov) - first // cov))
         n_cols = min((W + cov - 1) // cov, max(1, W // cov))
         boxd = k.valid_bbox(band, first - r0, cov, n_rows, n_cols, first // cov)
-        if dist is not None and world > 1:
-            dist.all_reduce(boxd, op=dist.ReduceOp.MAX)
+        box_ready = torch.cuda.Event()
+        box_ready.record(torch.cuda.current_stream(band.device))
         full = [0, max(1, H // cov) - 1, 0, n_cols - 1]
-        g = spec.guess(("bbox", H, W, world), boxd, [-full[0], full[1], -full[2], full[3]])
+        bkey = ("bbox", H, W, world)
+        g = spec.peek(bkey, [-full[0], full[1], -full[2], full[3]])
         ymin, ymax, xmin, xmax = -g[0], g[1], -g[2], g[3]
         box = None
+        bbox_pending = [True]
+
+        def check_bbox():
+            # the all-reduced box only CONFIRMS the guess the step is planned with, so its all-reduce is kept off the
+            # critical path: it is issued behind the window gather (every rank at the same point of its program), on
+            # the side stream of the main-pass preparation when there is one
+            if bbox_pending[0]:
+                bbox_pending[0] = False
+                if dist is not None and world > 1:
+                    dist.all_reduce(boxd, op=dist.ReduceOp.MAX)
+                spec.verify(bkey, boxd, g)
     else:
         box = torch.tensor([big, -1, big, -1], dtype=torch.int64, device=band.device)  # ymin, ymax, xmin, xmax
     if box is not None and r1 > first and first // cov < max(1, H // cov):
@@ -595,6 +762,8 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
             box = torch.stack([mn[0], mx[0], mn[1], mx[1]])
         ymin, ymax, xmin, xmax = [int(v) for v in box.cpu().tolist()]
     if ymax < 0:
+        if spec is not None:
+            check_bbox()
         if after_gather is not None:
             after_gather()
         if scale_out is not None:
@@ -615,18 +784,61 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
     _mark("bbox")
     # 1. move every window's rows to its owner ...
     owners = assign_window_owners(wins, own)
-    plans, mine_idx = [], []
-    for wi, (wy0, wx0, tw, th) in enumerate(wins):
-        owner = owners[wi]
-        need = [(0, 0)] * world
-        need[owner] = (wy0, wy0 + th)
-        cols = band[:, wx0:wx0 + tw]
-        plans.append(plan_exchange(cols, own, need, rank, dist))
-        if rank == owner:
-            mine_idx.append(wi)
-    outs = run_exchanges(plans, dist)          # all nine gathers in one point-to-point batch
-    mine = [outs[wi] for wi in mine_idx]
+    if peers is not None:
+        from .. import kernels as k
+        peers.barrier()          # every rank's band is in place
+        cur_s = torch.cuda.current_stream(band.device)
+        ce_s = _side_stream(band.device, "gather")
+        ce_s.wait_stream(cur_s)
+        mine, used_ce = [], False
+        for wi, (wy0, wx0, tw, th) in enumerate(wins):
+            if owners[wi] != rank:
+                continue
+            if r0 <= wy0 and wy0 + th <= r1:
+                mine.append(band[wy0 - r0:wy0 - r0 + th, wx0:wx0 + tw])      # a view, nothing moves
+                continue
+            win = torch.empty((th, tw), dtype=band.dtype, device=band.device)
+            for q in range(world):
+                ov = _overlap(own[q], (wy0, wy0 + th))
+                if not ov:
+                    continue
+                dst = win[ov[0] - wy0:ov[1] - wy0]
+                if q == rank:    # own rows: a copy kernel on this stream ...
+                    dst.copy_(band[ov[0] - r0:ov[1] - r0, wx0:wx0 + tw])
+                    continue
+                # ... rows of another band: the copy engines pull them over NVLink meanwhile
+                with torch.cuda.stream(ce_s):
+                    k.copy_rect(dst, peers.band_of(q)[ov[0] - own[q][0]:ov[1] - own[q][0], wx0:wx0 + tw])
+                win.record_stream(ce_s)
+                used_ce = True
+                if EXCHANGE_LOG is not None:
+                    EXCHANGE_LOG["received"] += (ov[1] - ov[0]) * tw * 4
+                    EXCHANGE_LOG["peer_read"] = EXCHANGE_LOG.get("peer_read", 0) + (ov[1] - ov[0]) * tw * 4
+            mine.append(win)
+        if used_ce:
+            cur_s.wait_stream(ce_s)
+    else:
+        plans, mine_idx = [], []
+        for wi, (wy0, wx0, tw, th) in enumerate(wins):
+            owner = owners[wi]
+            need = [(0, 0)] * world
+            need[owner] = (wy0, wy0 + th)
+            cols = band[:, wx0:wx0 + tw]
+            plans.append(plan_exchange(cols, own, need, rank, dist))
+            if rank == owner:
+                mine_idx.append(wi)
+        outs = run_exchanges(plans, dist)          # all nine gathers in one point-to-point batch
+        mine = [outs[wi] for wi in mine_idx]
     _mark("gather")
+    if spec is not None:
+        if after_gather is not None and getattr(after_gather, "side_stream", None) is not None:
+            side_s = after_gather.side_stream
+            side_s.wait_event(box_ready)   # (the box kernel ran on the caller's stream)
+            with torch.cuda.stream(side_s):
+                boxd.record_stream(side_s)
+                check_bbox()
+        else:
+            check_bbox()
     if after_gather is not None:
         after_gather()
     # 2. ... then every rank evaluates its own windows, all ranks at the same time
@@ -644,8 +856,11 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
     _mark("windows")
     kw = select_fns(pooled) if select_fns is not None else {}   # tests inject stand-ins for the kernels
     if scale_out is not None:
+        px = None
+        if peers is not None and dist is not None and world > 1:   # (every rank: same decision, same rendezvous order)
+            px = PeerExchange.get(band.device, dist.group.WORLD, world)
         return distributed_percentile(pooled, 99.0, take_abs=True, finite_only=False, device=band.device, dist=dist,
-                                      scale_out=scale_out)
+                                      scale_out=scale_out, peer_exchange=px)
     s = distributed_percentile(pooled, 99.0, take_abs=True, finite_only=False, device=band.device, dist=dist, **kw)
     if not (s == s) or s <= 1e-9:
         return None
@@ -655,6 +870,15 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
 # ------------------------------------------------------------------------------------------------
 # bench driver for N > 1 (called from bench.py under torchrun)
 # ------------------------------------------------------------------------------------------------
+def _breakdown(prof, steps):
+    names = {1: "fused_main", 2: "pyramid", 3: "coarse_means", 6: "fused_stats_windows"}
+    out = {}
+    for tag, ms in prof:
+        if tag in names:
+            out[names[tag]] = out.get(names[tag], 0.0) + ms / max(1, steps)
+    return {k_: round(v, 3) for k_, v in out.items()}
+
+
 def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None, peak=None):
     import json
     import time
@@ -664,18 +888,26 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
     H = W = S
     own = band_bounds(H, world)
     r0, r1 = own[rank]
-    ext, band = haloed_band(H, W, world, rank, radii, device=dev)   # the band lives inside its halo buffer
+    # the band lives inside its halo buffer, in symmetric memory (window gather by peer reads; FSG_NO_PEER=1: NCCL)
+    pg = None if os.environ.get("FSG_NO_PEER") else dist.group.WORLD
+    ext, band = haloed_band(H, W, world, rank, radii, device=dev, peer_group=pg)
     k.synth_dem((r1 - r0, W), seed=20261017 + 2, device=dev, row0=r0, h_global=H, out=band)
     out = torch.empty((r1 - r0, W), dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
 
     redo = [0]
+    host_t = [0.0, 0.0]   # seconds spent enqueueing / waiting for the speculated values
 
     def step():   # no host synchronisation inside (see topousm_fast_sharded_step); a wrong guess repeats the step
         for _attempt in range(3):
+            t_a = time.perf_counter()
             _res, scale_dev, spec = topousm_fast_sharded_step(band, H, rank, world, radii=radii, weights=weights, dist=dist,
                                                               out=out, dem_ext=ext)
-            if spec.ok():
+            t_b = time.perf_counter()
+            good = spec.ok()
+            host_t[0] += t_b - t_a
+            host_t[1] += time.perf_counter() - t_b
+            if good:
                 break
             redo[0] += 1
         return scale_dev
@@ -699,9 +931,11 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
         PREPASS_TRACE = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    host_t[0] = host_t[1] = 0.0
     for _ in range(a.steps):
         scale_dev = step()
     ev1.record()
+    host_ms = {"enqueue": round(host_t[0] * 1e3 / a.steps, 3), "wait_speculation": round(host_t[1] * 1e3 / a.steps, 3)}
     torch.cuda.synchronize()
     if STEP_TRACE is not None:
         import sys as _sys
@@ -747,7 +981,7 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
     hin = torch.empty((r1 - r0, W), dtype=torch.float32, pin_memory=True)
     hin.copy_(band)
     hout = torch.empty((r1 - r0, W), dtype=torch.uint8, pin_memory=True)
-    dext, dband = haloed_band(H, W, world, rank, radii, device=dev)
+    dext, dband = haloed_band(H, W, world, rank, radii, device=dev, peer_group=pg)
     out8 = torch.empty((r1 - r0, W), dtype=torch.uint8, device=dev)
 
     def e2e_step():
@@ -788,6 +1022,7 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
                                    "stats pre-pass + main pass per step", "radii": radii, "size": S,
                        "l2_policy": "per-GPU band far larger than the 126 MB L2", "main_pass_ms": main_ms,
                        "stats_prepass_ms": ms_step - main_ms, "main_pass_mpx_s": px / (main_ms * 1e-3) / 1e6,
+                       "kernel_ms_per_step_rank0": _breakdown(prof, a.steps), "host_enqueue_ms_per_step": host_ms,
                        "scale_p99": scale, "band_rows": r1 - r0, "respeculated_steps": redo[0],
                        "out_checksum": f"{checksum:016x}"},
             "roofline": roofline, "cpu_baseline": None, "clocks": clocks,

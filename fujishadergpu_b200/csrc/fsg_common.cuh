@@ -95,6 +95,12 @@ __device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
   if (i < 0) i += p;
   return i < n ? i : p - 1 - i;
 }
+// the same for an index at most one period outside [0, n) (the common case: window reach < n); falls back otherwise
+__device__ __forceinline__ int64_t reflect_near(int64_t i, int64_t n) {
+  int64_t j = i < 0 ? -i - 1 : i;
+  j = j >= n ? 2 * n - 1 - j : j;
+  return (j >= 0 && j < n) ? j : reflect_index(i, n);
+}
 __device__ __forceinline__ int64_t clamp_index(int64_t i, int64_t n) { return i < 0 ? 0 : (i >= n ? n - 1 : i); }
 
 // ---- approximate SFU forms ------------------------------------------------------------------------

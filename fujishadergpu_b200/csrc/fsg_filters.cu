@@ -155,6 +155,145 @@ __global__ void __launch_bounds__(256) box_axis1_kernel(const float* __restrict_
   }
 }
 
+
+// ---------------------------------------------------------------- box, both axes in one pass
+// The two passes above move the grid five times (read, two f32 planes out, two planes in, write).  This kernel keeps
+// the intermediate planes of a 16-row batch in shared memory: a CTA walks a strip of CW output columns down a band
+// of rows; phase V, one thread per input column (CW + size - 1 of them), advances the exact f64 running sum / valid
+// count of the column and leaves the f32-rounded axis-0 means of the batch in shared memory; phase H, thread =
+// (row, segment of CW / 16 outputs), slides the axis-1 window over them.  Same values as the two passes bit for bit
+// (the window sums are exact; each axis rounds once to f32; NaN-aware combine as in box_axis1_kernel).  A batch
+// whose columns are all NaN-free skips the weight plane (every weight is 1.0f, their mean is 1.0f).
+constexpr int B2_RB = 16;
+template <int CW, int MAXSIZE>
+struct Box2Geom {
+  static constexpr int NT = CW + MAXSIZE - 1;          // threads = input columns
+  static constexpr int P = NT + 1;                     // plane pitch (odd: rows fall on different banks)
+  static constexpr int SEG = CW / 16;
+  static constexpr int PO = CW + 1;
+  static constexpr size_t BYTES = (size_t)(2 * B2_RB * P + B2_RB * PO) * 4;
+};
+
+template <int CW, int MAXSIZE, int MINB>
+__global__ void __launch_bounds__(CW + MAXSIZE - 1, MINB)
+box_mean2d_kernel(Grid g, int size, float* __restrict__ out, int64_t oy0, int64_t oh, int band_rows) {
+  using G = Box2Geom<CW, MAXSIZE>;
+  extern __shared__ float sm[];
+  float* tvs = sm;
+  float* tws = sm + B2_RB * G::P;
+  float* so = tws + B2_RB * G::P;
+  const int tid = threadIdx.x;
+  const int lo = size / 2, hi = size - 1 - lo;
+  const int64_t x0 = (int64_t)blockIdx.x * CW;
+  const int64_t y0 = oy0 + (int64_t)blockIdx.y * band_rows;
+  const int64_t y1 = y0 + band_rows < oy0 + oh ? y0 + band_rows : oy0 + oh;
+  const double n = (double)size, inv = 1.0 / n;
+  const float nf = (float)size;
+  // phase V role
+  const bool v_on = tid < CW + size - 1;
+  const float* col = g.src + reflect_near(x0 - lo + tid, g.w) - g.row_off * g.ld;
+  double s = 0.0;
+  int cnt = 0;
+  if (v_on) {
+    double s1 = 0.0;
+    if (y0 - lo >= 0 && y0 + hi < g.h) {
+      const float* pk = col + (y0 - lo) * g.ld;
+      for (int k = 0; k < size; ++k) {
+        const float v = pk[(int64_t)k * g.ld];
+        const bool ok = v == v;
+        if (k & 1) s1 += ok ? (double)v : 0.0;
+        else s += ok ? (double)v : 0.0;
+        cnt += ok;
+      }
+    } else {
+      for (int k = -lo; k <= hi; ++k) {
+        const float v = col[reflect_near(y0 + k, g.h) * g.ld];
+        const bool ok = v == v;
+        if (k & 1) s1 += ok ? (double)v : 0.0;
+        else s += ok ? (double)v : 0.0;
+        cnt += ok;
+      }
+    }
+    s += s1;
+  }
+  // phase H role: warp = two segments 4 apart (SEG = 12: 48 columns = 16 banks), lanes 0-15 / 16-31 = the 16 rows
+  const bool h_on = tid < 256;
+  const int hr = tid & 15;
+  const int hseg = ((tid >> 5) & 3) + 8 * (tid >> 7) + 4 * ((tid >> 4) & 1);
+  const int j0 = hseg * G::SEG;
+
+  for (int64_t yb = y0; yb < y1; yb += B2_RB) {
+    const int nb = y1 - yb < B2_RB ? (int)(y1 - yb) : B2_RB;
+    int full = 1;
+    if (v_on) {
+      float vin[B2_RB], vout[B2_RB];
+      if (yb - lo >= 0 && yb + B2_RB + hi < g.h) {
+        const float* pin = col + (yb + hi + 1) * g.ld;
+        const float* pout = col + (yb - lo) * g.ld;
+#pragma unroll
+        for (int i = 0; i < B2_RB; ++i) {
+          vin[i] = i < nb ? pin[(int64_t)i * g.ld] : 0.f;
+          vout[i] = i < nb ? pout[(int64_t)i * g.ld] : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < B2_RB; ++i) {
+          vin[i] = i < nb ? col[reflect_near(yb + i + hi + 1, g.h) * g.ld] : 0.f;
+          vout[i] = i < nb ? col[reflect_near(yb + i - lo, g.h) * g.ld] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < B2_RB; ++i) {
+        tvs[i * G::P + tid] = (float)div_by_count(s, n, inv);
+        tws[i * G::P + tid] = cnt == size ? 1.f : (float)cnt / nf;
+        if (i < nb) full &= (int)(cnt == size);
+        const bool oin = vin[i] == vin[i], oout = vout[i] == vout[i];
+        s += (oin ? (double)vin[i] : 0.0) - (oout ? (double)vout[i] : 0.0);
+        cnt += (int)oin - (int)oout;
+      }
+    }
+    const int dense = __syncthreads_and(full);
+    if (h_on && hr < nb) {
+      const float* pv = tvs + hr * G::P + j0;
+      const float* pw = tws + hr * G::P + j0;
+      float* po = so + hr * G::PO + j0;
+      double sv = 0.0, sv1 = 0.0, sv2 = 0.0, sv3 = 0.0;   // (exact sums: any association)
+      int k = 0;
+      for (; k + 3 < size; k += 4) {
+        sv += (double)pv[k];
+        sv1 += (double)pv[k + 1];
+        sv2 += (double)pv[k + 2];
+        sv3 += (double)pv[k + 3];
+      }
+      for (; k < size; ++k) sv += (double)pv[k];
+      sv = (sv + sv1) + (sv2 + sv3);
+      if (dense) {
+#pragma unroll 4
+        for (int j = 0; j < G::SEG; ++j) {
+          po[j] = (float)div_by_count(sv, n, inv);
+          sv += (double)pv[j + size] - (double)pv[j];
+        }
+      } else {
+        double sw = 0.0;
+        for (int q = 0; q < size; ++q) sw += (double)pw[q];
+#pragma unroll 2
+        for (int j = 0; j < G::SEG; ++j) {
+          const float num = (float)div_by_count(sv, n, inv);
+          const float den = (float)div_by_count(sw, n, inv);
+          po[j] = den > 0.f ? num / den : 0.f;
+          sv += (double)pv[j + size] - (double)pv[j];
+          sw += (double)pw[j + size] - (double)pw[j];
+        }
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nb * CW; idx += G::NT) {
+      const int rr = idx / CW, c = idx - rr * CW;
+      if (x0 + c < g.w) out[(yb - oy0 + rr) * g.w + x0 + c] = so[rr * G::PO + c];
+    }
+  }
+}
+
 // ---------------------------------------------------------------- gaussian passes (direct)
 __global__ void gauss_taps_kernel(double sigma, int radius, double* w) {
   // one block; the normalising sum is accumulated by thread 0 in index order (deterministic)
@@ -267,6 +406,35 @@ int launch_box_axis1(const float* tv, const float* tw, int64_t h, int64_t w, int
   if (need(8) <= cap) return launch_a1<8>(tv, tw, h, w, size, out, s, need(8));
   if (need(1) <= cap) return launch_a1<1>(tv, tw, h, w, size, out, s, need(1));
   return fail(FSG_E_UNSUPPORTED, "box filter of %d taps exceeds the shared-memory tile budget", size);
+}
+
+
+template <int CW, int MAXSIZE, int MINB>
+static int launch_b2(const Grid& g, int size, float* out, int64_t oy0, int64_t oh, cudaStream_t s) {
+  using G = Box2Geom<CW, MAXSIZE>;
+  const int64_t strips = (g.w + CW - 1) / CW;
+  // bands: enough CTAs for ~2 waves of MINB CTAs per SM, at least 32 rows each (a band start costs `size` loads per
+  // column), rows in multiples of the batch
+  int64_t want = (148 * MINB * 2 + strips - 1) / strips;
+  int64_t band = (oh + want - 1) / want;
+  if (band < 32) band = 32;
+  band = (band + B2_RB - 1) / B2_RB * B2_RB;
+  const int64_t bands = (oh + band - 1) / band;
+  if (bands > 65535 || strips > 2147483647LL) return fail(FSG_E_UNSUPPORTED, "box mean: grid too large");
+  FSG_CUDA_OK(cudaFuncSetAttribute(box_mean2d_kernel<CW, MAXSIZE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BYTES));
+  box_mean2d_kernel<CW, MAXSIZE, MINB><<<dim3((unsigned)strips, (unsigned)bands), G::NT, G::BYTES, s>>>(g, size, out, oy0, oh, (int)band);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+// 1 = launched, 0 = the size is outside the single-pass kernel's range (caller falls back to the two passes)
+int launch_box_mean2d(const Grid& g, int size, float* out, int64_t oy0, int64_t oh, cudaStream_t s, int* rc) {
+  *rc = FSG_OK;
+  if (oh <= 0) return 1;
+  if (size < 3 || (size & 1) == 0) return 0;
+  if (size <= 65) { *rc = launch_b2<192, 65, 3>(g, size, out, oy0, oh, s); return 1; }
+  if (size <= 257) { *rc = launch_b2<512, 257, 1>(g, size, out, oy0, oh, s); return 1; }
+  return 0;
 }
 
 int launch_gauss_taps(double sigma, int radius, double* taps_dev, cudaStream_t s) {

@@ -34,6 +34,10 @@ int launch_box_axis1(const float* tv, const float* tw, int64_t h, int64_t w, int
 int launch_gauss_axis1(const float* tv, const float* tw, int64_t h, int64_t w, const double* taps_dev, int radius,
                        int combine, float* out, const int* run_flag, int* still_nan, cudaStream_t s);
 
+// both box passes in one kernel (intermediate planes of a 16-row batch in shared memory), sizes 3..257: returns 1
+// when launched (*rc = status), 0 when the size is out of range -- same values as axis0 + axis1 bit for bit
+int launch_box_mean2d(const Grid& g, int size, float* out, int64_t oy0, int64_t oh, cudaStream_t s, int* rc);
+
 // taps for sigma (device side, f64): w[0..radius]
 int launch_gauss_taps(double sigma, int radius, double* taps_dev, cudaStream_t s);
 

@@ -225,3 +225,16 @@ int fsg_synth_dem(float* out, int64_t H, int64_t W, int64_t row0, int64_t rows, 
 }
 
 }  // extern "C"
+
+int fsg_copy_rect_f32(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows, int64_t cols,
+                      void* stream) {
+  using namespace fsg;
+  if (rows < 0 || cols < 0 || ld_dst < cols || ld_src < cols) return fail(FSG_E_INVALID, "fsg_copy_rect_f32: bad shape");
+  if (rows == 0 || cols == 0) return FSG_OK;
+  if (!dst || !src) return fail(FSG_E_INVALID, "fsg_copy_rect_f32: NULL buffer");
+  cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)ld_dst * 4, src, (size_t)ld_src * 4, (size_t)cols * 4, (size_t)rows,
+                                    cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(FSG_E_CUDA, "fsg_copy_rect_f32: %s", cudaGetErrorString(e));
+  return FSG_OK;
+}
+

@@ -81,9 +81,23 @@ __device__ __forceinline__ void scan_chunks(const Chunks& c, F f) {
 // shared-memory histogram increment aggregated per warp: the keys of |x| cluster in a handful of bins
 // (same exponent), where plain atomics serialise 32-fold
 __device__ __forceinline__ void hist_add(unsigned int* sh, unsigned int bin, bool contrib) {
-  const unsigned int tag = contrib ? bin : 0xffffffffu;
-  const unsigned int m = __match_any_sync(0xffffffffu, tag);
-  if (contrib && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&sh[bin], (unsigned int)__popc(m));
+  unsigned int todo = __ballot_sync(0xffffffffu, contrib);
+  if (todo == 0u) return;   // levels 1 and 2: most warps hold no key of the selected bucket
+  const int lane = (int)(threadIdx.x & 31);
+  // two rounds of "the first pending lane collects everyone with its bin" (two ballots and a shuffle each -- much
+  // cheaper than match.any), the few lanes left use their own atomic
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    const int leader = __ffs(todo) - 1;
+    const unsigned int b0 = __shfl_sync(0xffffffffu, bin, leader);
+    const bool mine = contrib && bin == b0;
+    const unsigned int same = __ballot_sync(0xffffffffu, mine);
+    if (lane == leader) atomicAdd(&sh[b0], (unsigned int)__popc(same));
+    contrib = contrib && !mine;
+    todo &= ~same;
+    if (todo == 0u) return;
+  }
+  if (contrib) atomicAdd(&sh[bin], 1u);
 }
 
 // level: 0 -> bits 31..21 (2048 bins), 1 -> bits 20..10 (2048), 2 -> bits 9..0 (1024)
@@ -414,6 +428,31 @@ __global__ void sel_finish_kernel(const SelState* st, const unsigned long long* 
   result[3] = (double)st->n;
 }
 
+// ---- exchange over peer memory (NVLink / NVSwitch) instead of all-reduce calls --------------------------------
+// Every rank owns SEL_PEER_SLOTS slots of SEL_X_WORDS words in symmetric memory (mapped by all ranks of the node).
+// A stage publishes its part of the exchange area into the slot of the stage; after a stream-ordered barrier every
+// rank sums (word SEL_X_NEXT: minimum) the slots of all ranks into its own exchange area -- the same integers on
+// every rank, so all ranks take the same decisions.  Loads of peer memory bypass L1 (the slots are rewritten every
+// call at the same addresses).
+constexpr int SEL_PEER_SLOTS = 4;
+
+__global__ void sel_publish_kernel(const unsigned long long* __restrict__ x, unsigned long long* slot, int first, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) slot[first + i] = x[first + i];
+}
+
+__global__ void sel_peer_reduce_kernel(unsigned long long* x, const unsigned long long* const* peers, int world,
+                                       int slot_words0, int first, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int w = first + i;
+    unsigned long long acc = w == SEL_X_NEXT ? 0xffffffffffffffffull : 0ull;
+    for (int p = 0; p < world; ++p) {
+      const unsigned long long v = __ldcv(peers[p] + slot_words0 + w);
+      acc = w == SEL_X_NEXT ? (v < acc ? v : acc) : acc + v;
+    }
+    x[w] = acc;
+  }
+}
+
 // np.percentile(..., method 'linear') of an f32 sample, finished on the device: virtual index, gamma and the lerp
 // in f32 exactly as NumPy evaluates them (python-int / python-float operands are weak: (n - 1) * q32, diff * gamma
 // and 1 - gamma are f32 operations), then the rule of topousm_fast_stat_func (_normalization.py:22-32): a NaN or
@@ -690,6 +729,29 @@ int fsg_select_next(const float* const* chunks_host, const int64_t* rows_host, c
   if (blocks > 148 * 8) blocks = 148 * 8;
   sel_next_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(c, take_abs, finite_only, sel_state(workspace),
                                                             (unsigned long long*)workspace);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+size_t fsg_select_peer_slot_words(void) { return (size_t)fsg::SEL_PEER_SLOTS * fsg::SEL_X_WORDS; }
+
+int fsg_select_peer_publish(const void* workspace, void* my_slots, int stage, void* stream) {
+  using namespace fsg;
+  if (!workspace || !my_slots || stage < 0 || stage >= SEL_PEER_SLOTS) return fail(FSG_E_INVALID, "fsg_select_peer_publish: bad argument");
+  const int first = stage < 3 ? 0 : SEL_X_LE, n = stage == 0 ? SEL_X_COUNT + 1 : (stage < 3 ? SEL_X_COUNT : 2);
+  sel_publish_kernel<<<stage < 3 ? 4 : 1, 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)workspace,
+      (unsigned long long*)my_slots + (size_t)stage * SEL_X_WORDS, first, n);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_select_peer_reduce(void* workspace, const void* const* peer_slots_dev, int world, int stage, void* stream) {
+  using namespace fsg;
+  if (!workspace || !peer_slots_dev || world < 1 || stage < 0 || stage >= SEL_PEER_SLOTS)
+    return fail(FSG_E_INVALID, "fsg_select_peer_reduce: bad argument");
+  const int first = stage < 3 ? 0 : SEL_X_LE, n = stage == 0 ? SEL_X_COUNT + 1 : (stage < 3 ? SEL_X_COUNT : 2);
+  sel_peer_reduce_kernel<<<stage < 3 ? 9 : 1, 256, 0, (cudaStream_t)stream>>>((unsigned long long*)workspace,
+      (const unsigned long long* const*)peer_slots_dev, world, stage * SEL_X_WORDS, first, n);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }

@@ -19,6 +19,12 @@
 //                       in list order in f32; normalise; NaN restore; optional u8/i16 encoding.
 //      Algorithmic traffic: 4 B/px read + 4 B/px (f32) or 1 B/px (u8) written.
 #include <stdlib.h>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <queue>
+#include <utility>
+#include <vector>
 
 #include "fsg_filters.cuh"
 
@@ -1254,6 +1260,21 @@ namespace fsg {
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
+// Debug switches, read once per process (FSG_FORCE_GENERIC, FSG_FUSED_V5, FSG_NO_BULK, FSG_V6_CFGB, FSG_NO_V8).
+struct FusedSwitches {
+  bool force_generic, v5, no_bulk, cfgb, no_v8, no_side, box_two_pass;
+  FusedSwitches()
+      : force_generic(getenv("FSG_FORCE_GENERIC") != nullptr), v5(getenv("FSG_FUSED_V5") != nullptr),
+        no_bulk(getenv("FSG_NO_BULK") != nullptr), cfgb(getenv("FSG_V6_CFGB") != nullptr),
+        no_v8(getenv("FSG_NO_V8") != nullptr), no_side(getenv("FSG_NO_SIDE_STREAM") != nullptr),
+        box_two_pass(getenv("FSG_BOX_TWO_PASS") != nullptr) {}
+};
+static const FusedSwitches& fused_switches() {
+  static const FusedSwitches sw;
+  return sw;
+}
+extern "C" void fsg_debug_reload_switches(void) { const_cast<FusedSwitches&>(fused_switches()) = FusedSwitches(); }
+
 static int mean_on_grid(const Grid& g, int size, float* out, float* tv, float* tw, double* taps, int64_t oy0,
                         int64_t oh, cudaStream_t s) {
   int rc;
@@ -1262,8 +1283,15 @@ static int mean_on_grid(const Grid& g, int size, float* out, float* tv, float* t
     if ((rc = launch_gauss_axis0(g, taps, 4, tv, tw, nullptr, oy0, oh, s))) return rc;
     return launch_gauss_axis1(tv, tw, oh, g.w, taps, 4, COMBINE_MEAN, out, nullptr, nullptr, s);
   }
-  if ((rc = launch_box_axis0(g, size, tv, tw, oy0, oh, s))) return rc;
-  return launch_box_axis1(tv, tw, oh, g.w, size, out, s);
+  int slot = prof_begin(PROF_TOPOUSM_COARSE, s);
+  if (!fused_switches().box_two_pass && launch_box_mean2d(g, size, out, oy0, oh, s, &rc)) {
+    prof_end(slot, s);
+    return rc;
+  }
+  if ((rc = launch_box_axis0(g, size, tv, tw, oy0, oh, s))) { prof_end(slot, s); return rc; }
+  rc = launch_box_axis1(tv, tw, oh, g.w, size, out, s);
+  prof_end(slot, s);
+  return rc;
 }
 
 static int launch_pyramid(const float* dem, int64_t rows, int64_t W, int64_t ld, int n_levels, const int* factors,
@@ -1284,19 +1312,6 @@ static int launch_pyramid(const float* dem, int64_t rows, int64_t W, int64_t ld,
   return FSG_OK;
 }
 
-// Debug switches, read once per process (FSG_FORCE_GENERIC, FSG_FUSED_V5, FSG_NO_BULK, FSG_V6_CFGB, FSG_NO_V8).
-struct FusedSwitches {
-  bool force_generic, v5, no_bulk, cfgb, no_v8;
-  FusedSwitches()
-      : force_generic(getenv("FSG_FORCE_GENERIC") != nullptr), v5(getenv("FSG_FUSED_V5") != nullptr),
-        no_bulk(getenv("FSG_NO_BULK") != nullptr), cfgb(getenv("FSG_V6_CFGB") != nullptr),
-        no_v8(getenv("FSG_NO_V8") != nullptr) {}
-};
-static const FusedSwitches& fused_switches() {
-  static const FusedSwitches sw;
-  return sw;
-}
-extern "C" void fsg_debug_reload_switches(void) { const_cast<FusedSwitches&>(fused_switches()) = FusedSwitches(); }
 
 // Rows per CTA band: few enough that the (2R+1)-row warm-up per band stays small, enough CTAs (>= 6 per SM when
 // the raster allows) that the slower edge strips and the SM-to-SM spread average out.  (A "fewest waves" model
@@ -1317,7 +1332,8 @@ static int64_t fused_band_rows(int64_t rows, int64_t strips, int fused_R, int64_
 
 // One fused_kernel_v6 launch over output rows [r0, r1) x columns [c0, c1) of the raster (`base` describes the
 // whole call; its out pointer belongs to row base.out_row0).
-static int launch_v6_rect(const FusedParams& base, int64_t r0, int64_t r1, int64_t c0, int64_t c1, cudaStream_t s) {
+static int launch_v6_rect(const FusedParams& base, int64_t r0, int64_t r1, int64_t c0, int64_t c1, cudaStream_t s,
+                          bool spread = false) {
   if (r1 <= r0 || c1 <= c0) return FSG_OK;
   FusedParams fp = base;
   fp.out = (unsigned char*)base.out + (size_t)(r0 - base.out_row0) * (size_t)base.ld_out * out_elem_size(base.enc.kind);
@@ -1329,7 +1345,11 @@ static int launch_v6_rect(const FusedParams& base, int64_t r0, int64_t r1, int64
   fp.tile_flags = nullptr;
   if (c0 % 4 != 0) fp.bulk_ok = 0;
   const int64_t strips = (c1 - c0 + FK_TW - 1) / FK_TW;
-  const int64_t band_rows = fused_band_rows(fp.out_rows, strips, fp.R, FK_NB);
+  int64_t band_rows = fused_band_rows(fp.out_rows, strips, fp.R, FK_NB);
+  // a rectangle one or two strips wide next to a large launch (the left / right raster border): many short bands,
+  // so that it finishes inside the large launch instead of trailing it as a few long serial CTAs
+  while (spread && band_rows > 4 * (int64_t)(2 * fp.R + 1) && strips * ((fp.out_rows + band_rows - 1) / band_rows) < 148)
+    band_rows = ((band_rows + 1) / 2 + FK_NB - 1) / FK_NB * FK_NB;
   fp.band_rows = (int)band_rows;
   const int64_t bands = (fp.out_rows + band_rows - 1) / band_rows;
   if (bands > 65535) return fail(FSG_E_UNSUPPORTED, "fsg_topousm_fast: raster too tall");
@@ -1338,6 +1358,70 @@ static int launch_v6_rect(const FusedParams& base, int64_t r0, int64_t r1, int64
   fused_kernel_v6<32, V6CfgA><<<dim3((unsigned)strips, (unsigned)bands), V6Geom<32, V6CfgA>::THREADS, smem, s>>>(fp);
   FSG_LAUNCH_OK();
   return FSG_OK;
+}
+
+// Rows per CTA of the v8 launch (a multiple of the 256-row flag blocks).  One CTA per SM, CTAs handed out in launch
+// order: the makespan of the candidates is simulated with a CTA costing (rows + the rows a restart is worth) and
+// the shortest one wins -- at 8192 rows x 341 strips the difference between 9.2 waves of 2048-row CTAs and 6.9
+// waves of 2816-row CTAs is 5 % of the launch.
+static int64_t v8_band_rows(int64_t rows, int64_t strips) {
+  if (strips * ((rows + V8_BLK - 1) / V8_BLK) <= 148) return V8_BLK;
+  static std::mutex mu;
+  static std::map<std::pair<int64_t, int64_t>, int64_t> memo;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = memo.find({rows, strips});
+  if (it != memo.end()) return it->second;
+  const int64_t restart = 96;   // fill of five ring groups + the window sums, in rows of steady-state work
+  int64_t best = V8_BLK;
+  double best_t = 1e300;
+  for (int64_t br = V8_BLK; br <= 16 * V8_BLK; br += V8_BLK) {
+    const int64_t bands = (rows + br - 1) / br;
+    if (bands > 65535) continue;
+    const int64_t last = rows - (bands - 1) * br;
+    // list scheduling on 148 SMs: the next CTA (launch order) goes to the SM that frees up first
+    std::priority_queue<int64_t, std::vector<int64_t>, std::greater<int64_t>> sm;
+    for (int i = 0; i < 148; ++i) sm.push(0);
+    int64_t mk = 0;
+    for (int64_t b = 0; b < bands; ++b) {
+      const int64_t cost = (b + 1 == bands ? last : br) + restart;
+      for (int64_t c = 0; c < strips; ++c) {
+        const int64_t t = sm.top() + cost;
+        sm.pop();
+        sm.push(t);
+        mk = t > mk ? t : mk;
+      }
+    }
+    if ((double)mk < best_t) { best_t = (double)mk; best = br; }
+    if (bands == 1) break;
+  }
+  memo[{rows, strips}] = best;
+  return best;
+}
+
+// The border rectangles of a v8 launch run on a side stream (forked from / joined to the caller's stream with
+// events) so that their few CTAs share the chip with the interior launch instead of running after it.  One lane
+// per host thread and device.
+struct SideLane {
+  cudaStream_t st = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int dev = -1;
+};
+static SideLane* side_lane() {
+  thread_local SideLane lanes[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  SideLane& L = lanes[dev & 15];
+  if (L.st && L.dev == dev) return &L;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, hi) != cudaSuccess ||
+      cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming) != cudaSuccess) {
+    L.st = nullptr;
+    return nullptr;
+  }
+  L.dev = dev;
+  return &L;
 }
 
 // bytes of the v8 NaN-block flags for a raster (or band) of H x W
@@ -1383,7 +1467,24 @@ static int launch_fused_v8(FusedParams& fp, int* flags, size_t flag_bytes, cudaS
     return done(fail(FSG_E_CUDA, "fsg_topousm_fast: clearing the block flags failed"));
   fp.v8_col0 = (int)Xa; fp.v8_row0 = Ya; fp.v8_row1 = Yb; fp.v8_flags = flags;
   fp.col0 = 0; fp.col_end = 0; fp.tile_flags = nullptr; fp.strip0 = 0;
-  int64_t band_rows = fused_band_rows(Yb - Ya, n8, V8_RH, V8_BLK);
+  // raster borders (and rows / columns outside the v8 grid): on the side stream, ahead of the interior launch
+  SideLane* lane = fused_switches().no_side ? nullptr : side_lane();
+  {
+    cudaStream_t bs = s;
+    if (lane) {
+      if (cudaEventRecord(lane->fork, s) != cudaSuccess || cudaStreamWaitEvent(lane->st, lane->fork, 0) != cudaSuccess)
+        return done(fail(FSG_E_CUDA, "fsg_topousm_fast: forking the border stream failed"));
+      bs = lane->st;
+    }
+    int rc;
+    if ((rc = launch_v6_rect(fp, Ya, Yb, C0, Xa, bs, true))) return done(rc);
+    if ((rc = launch_v6_rect(fp, Ya, Yb, Xb, C1, bs, true))) return done(rc);
+    if ((rc = launch_v6_rect(fp, R0, Ya, C0, C1, bs))) return done(rc);
+    if ((rc = launch_v6_rect(fp, Yb, R1, C0, C1, bs))) return done(rc);
+    if (lane && cudaEventRecord(lane->join, lane->st) != cudaSuccess)
+      return done(fail(FSG_E_CUDA, "fsg_topousm_fast: joining the border stream failed"));
+  }
+  int64_t band_rows = v8_band_rows(Yb - Ya, n8);
   fp.band_rows = (int)band_rows;
   const int64_t bands = (Yb - Ya + band_rows - 1) / band_rows;
   if (bands > 65535) return done(fail(FSG_E_UNSUPPORTED, "fsg_topousm_fast: raster too tall"));
@@ -1407,12 +1508,8 @@ static int launch_fused_v8(FusedParams& fp, int* flags, size_t flag_bytes, cudaS
     if (cudaPeekAtLastError() != cudaSuccess)
       return done(fail(FSG_E_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(cudaPeekAtLastError()), __FILE__, __LINE__));
   }
-  // raster borders (and rows / columns outside the v8 grid)
-  int rc;
-  if ((rc = launch_v6_rect(fp, R0, Ya, C0, C1, s))) return done(rc);
-  if ((rc = launch_v6_rect(fp, Yb, R1, C0, C1, s))) return done(rc);
-  if ((rc = launch_v6_rect(fp, Ya, Yb, C0, Xa, s))) return done(rc);
-  if ((rc = launch_v6_rect(fp, Ya, Yb, Xb, C1, s))) return done(rc);
+  if (lane && cudaStreamWaitEvent(s, lane->join, 0) != cudaSuccess)
+    return done(fail(FSG_E_CUDA, "fsg_topousm_fast: joining the border stream failed"));
   return done(FSG_OK);
 }
 

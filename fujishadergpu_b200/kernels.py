@@ -496,6 +496,18 @@ def grid_mean_band(src, src_row0: int, gh: int, size: int, out_row0: int, out_ro
     return out
 
 
+def copy_rect(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """dst[:, :] = src[:, :] (2-D f32 views with unit column stride) on the copy engines; `src` may be another
+    GPU's band mapped through symmetric memory (core/sharding.PeerBands)."""
+    if dst.shape != src.shape or dst.ndim != 2 or dst.dtype != torch.float32 or src.dtype != torch.float32:
+        raise ValueError("copy_rect: two f32 2-D tensors of one shape expected")
+    if dst.stride(1) != 1 or src.stride(1) != 1:
+        raise ValueError("copy_rect: unit column stride expected")
+    check(_lib.load().fsg_copy_rect_f32(_ptr(dst), int(dst.stride(0)), _ptr(src), int(src.stride(0)), int(dst.shape[0]),
+                                        int(dst.shape[1]), C.c_void_p(dev.stream_ptr(dst))), "fsg_copy_rect_f32")
+    return dst
+
+
 def grid_void_fill(grid, inplace: bool = False) -> torch.Tensor:
     """Enclosed-void fill of a whole decimated grid (returns a filled copy, or fills `grid` itself).  The kernels
     are gated by a device-side "grid has NaN" flag, so the call is cheap on a grid without voids."""
@@ -598,13 +610,15 @@ def key_to_float(key: int, take_abs: bool) -> float:
 
 
 def staged_percentile(chunks, q: float, *, take_abs: bool, finite_only: bool, device, all_reduce=None,
-                      scale_out: Optional[torch.Tensor] = None, min_valid: float = 1e-9):
+                      scale_out: Optional[torch.Tensor] = None, min_valid: float = 1e-9, peer_exchange=None):
     """np.percentile(sample, q) (method 'linear', f32 sample) of the union of every rank's chunks with the
     selection state kept on the device: the host only enqueues the radix-select stages and, between them,
     `all_reduce(tensor, op)` (op in {"sum", "min"}) of the exchange area -- no host round trip until the
     4-double result is read.  all_reduce=None: single device.  (reference: _normalization.py:22-32)
     scale_out (one f32 on the device): the value is finished on the device (NumPy's f32 lerp; NaN when the sample
-    is empty or the value is NaN / <= min_valid) and NO host synchronisation happens; returns scale_out."""
+    is empty or the value is NaN / <= min_valid) and NO host synchronisation happens; returns scale_out.
+    peer_exchange (core/sharding.PeerExchange, instead of all_reduce): the exchange goes through symmetric memory --
+    publish, one 8 us stream barrier, every rank sums the slots of all ranks itself -- instead of five collectives."""
     lib = _lib.load()
     views = _pooled_views(chunks) if chunks else []
     nx = int(lib.fsg_select_exchange_words())
@@ -615,15 +629,29 @@ def staged_percentile(chunks, q: float, *, take_abs: bool, finite_only: bool, de
     ta, fo = 1 if take_abs else 0, 1 if finite_only else 0
     q32 = np.true_divide(q, np.float32(100))       # NumPy's own f32 quantile (python float / f32 -> f32)
     check(lib.fsg_select_begin(_ptr(ws), ws.numel() * 8, stream), "fsg_select_begin")
+    px = peer_exchange
+
+    def exchange(stage):
+        if px is not None:
+            check(lib.fsg_select_peer_publish(_ptr(ws), C.c_void_p(px.my_slots), stage, stream), "fsg_select_peer_publish")
+            px.barrier()
+            check(lib.fsg_select_peer_reduce(_ptr(ws), C.c_void_p(px.peer_slots_dev), px.world, stage, stream),
+                  "fsg_select_peer_reduce")
+        elif all_reduce is not None:
+            if stage < 3:
+                all_reduce(ws[:2049], "sum")
+            else:
+                all_reduce(ws[2049:2050], "sum")
+                all_reduce(ws[2050:2051], "min")
+
     for level in range(3):
         check(lib.fsg_select_hist(ptrs, rows, cols, lds, len(views), level, ta, fo, _ptr(ws), stream), "fsg_select_hist")
-        if all_reduce is not None:
-            all_reduce(ws[:2049], "sum")
+        exchange(level)
         check(lib.fsg_select_pick(level, float(q32), _ptr(ws), stream), "fsg_select_pick")
     check(lib.fsg_select_next(ptrs, rows, cols, lds, len(views), ta, fo, _ptr(ws), stream), "fsg_select_next")
-    if all_reduce is not None:
-        all_reduce(ws[2049:2050], "sum")
-        all_reduce(ws[2050:2051], "min")
+    exchange(3)
+    if px is not None:
+        px.barrier()   # the slots may be rewritten by the next call once every rank has read them
     if scale_out is not None:
         if scale_out.dtype != torch.float32 or not scale_out.is_cuda:
             raise TypeError("scale_out must be a float32 CUDA tensor")

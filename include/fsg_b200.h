@@ -286,6 +286,15 @@ int fsg_select_pick(int level, float q32, void* workspace, void* stream);
 int fsg_select_next(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
                     const int64_t* ld_host, int n_chunks, int take_abs, int finite_only, void* workspace, void* stream);
 int fsg_select_finish(void* workspace, int take_abs, double* result_dev, void* stream);
+/* The same exchange without collective calls, over peer memory (NVLink / NVSwitch): every rank owns
+ * fsg_select_peer_slot_words() int64 words of symmetric memory mapped by all ranks of the node.  After a stage
+ * (0..2: fsg_select_hist of that level, 3: fsg_select_next) a rank publishes its part of the exchange area into its
+ * own slots; after a stream-ordered barrier of the ranks, fsg_select_peer_reduce sums (smallest key: minimum) the
+ * slots of all `world` ranks (`peer_slots_dev`: device array of their base pointers, as mapped on this device) into
+ * the workspace, which then is what the all-reduce would have left there. */
+size_t fsg_select_peer_slot_words(void);
+int fsg_select_peer_publish(const void* workspace, void* my_slots, int stage, void* stream);
+int fsg_select_peer_reduce(void* workspace, const void* const* peer_slots_dev, int world, int stage, void* stream);
 /* Same selection, finished on the device: scale_dev[0] = np.percentile(sample, 100 * q32) (method 'linear', NumPy's
  * f32 arithmetic), or NaN when the sample is empty or the value is NaN / <= min_valid (topousm_fast_stat_func,
  * algorithms/_normalization.py:22-32) -- the value fsg_topousm_fused_band_ws takes as norm_scale_dev, so that the
@@ -302,6 +311,12 @@ int fsg_valid_bbox(const float* band, int64_t ld, int64_t first_row, int64_t cov
  * hash noise, optional NoData wedge/ellipses; rows [row0,row0+rows) of an H x W raster. */
 int fsg_synth_dem(float* out, int64_t H, int64_t W, int64_t row0, int64_t rows, int64_t ld,
                   uint64_t seed, int nodata, void* stream);
+
+/* rows x cols f32 rectangle, device to device on the copy engines (cudaMemcpy2DAsync): `src` may be another GPU's
+ * memory mapped into this process (symmetric memory; the window gather of the sharded statistics pre-pass,
+ * reference: algorithms/_norm_stats.py:176-298 reads its windows from the one Dask array).  Row strides in elements. */
+int fsg_copy_rect_f32(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows, int64_t cols,
+                      void* stream);
 
 #ifdef __cplusplus
 }

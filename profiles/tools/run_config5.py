@@ -47,7 +47,8 @@ def main():
     own = sh.band_bounds(H, world)
     assert own == tile_aligned_bounds(H, world), "band boundaries must be multiples of the 512-row COG blocks"
     r0, r1 = own[rank]
-    ext, band = sh.haloed_band(H, W, world, rank, radii, device=dev)
+    ext, band = sh.haloed_band(H, W, world, rank, radii, device=dev,
+                               peer_group=dist.group.WORLD if (world > 1 and not os.environ.get("FSG_NO_PEER")) else None)
     k.synth_dem((r1 - r0, W), seed=20261017 + 5, device=dev, row0=r0, h_global=H, out=band)
     qp = quantize_params(*resolve_output_range("topousm_fast"), "uint8")
     out8 = torch.empty((r1 - r0, W), dtype=torch.uint8, device=dev)

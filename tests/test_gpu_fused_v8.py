@@ -174,3 +174,77 @@ def test_stats_prepass_nine_windows_vs_oracle():
     sh.Speculation._memory.clear()
     _res, scale_dev, spec = sh.topousm_fast_sharded_step(d, S, 0, 1, radii=radii, weights=w)
     assert spec.ok() and np.float32(scale_dev.item()) == np.float32(want)
+
+
+def _grid_mean(k, g, size, two_pass, row_band=None):
+    os.environ.pop("FSG_BOX_TWO_PASS", None)
+    if two_pass:
+        os.environ["FSG_BOX_TWO_PASS"] = "1"
+    k.reload_debug_switches()
+    try:
+        gh = int(g.shape[0])
+        if row_band is None:
+            o = k.grid_mean_band(g, 0, gh, size, 0, gh)
+        else:   # a row band whose source rows carry the halo the pass needs (mirrored rows included)
+            a, b = row_band
+            reach = size // 2
+            lo, hi = max(0, a - reach), min(gh, b + reach)
+            if a - reach < 0:
+                hi = max(hi, min(gh, reach - a))
+            if b + reach > gh:
+                lo = min(lo, max(0, 2 * gh - (b + reach)))
+            o = k.grid_mean_band(g[lo:hi], lo, gh, size, a, b - a)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("FSG_BOX_TWO_PASS", None)
+        k.reload_debug_switches()
+    return o
+
+
+@pytest.mark.parametrize("shape", [(2064, 2064), (517, 1031), (96, 70), (1200, 193), (33, 4100)])
+def test_single_pass_box_mean_equals_two_passes(shape):
+    """box_mean2d_kernel (decimated-grid means of the large radii, one pass) == box_axis0 + box_axis1 bit for bit:
+    dense, isolated NaNs, a NaN block larger than the window, sizes of both kernel geometries, row bands."""
+    from fujishadergpu_b200 import kernels as k
+    gen = torch.Generator(device="cuda").manual_seed(shape[0] * 7 + shape[1])
+    base = torch.rand(shape, generator=gen, device="cuda") * 900.0 + 100.0
+    for variant in ("dense", "nan"):
+        g = base.clone()
+        if variant == "nan":
+            g[shape[0] // 3, shape[1] // 2] = float("nan")
+            g[shape[0] // 2: shape[0] // 2 + 90, shape[1] // 4: shape[1] // 4 + 300] = float("nan")
+            g[::37, ::53] = float("nan")
+        for size in (3, 33, 65, 129, 257):
+            if size // 2 >= min(shape):   # mirrored index would leave the grid twice: not a case the plan produces
+                continue
+            want = _grid_mean(k, g, size, True)
+            got = _grid_mean(k, g, size, False)
+            assert _same_bits(want, got), (shape, variant, size)
+            if shape[0] > 300:
+                for band in ((0, 160), (shape[0] // 2 - 7, shape[0] // 2 + 150), (shape[0] - 131, shape[0])):
+                    gb = _grid_mean(k, g, size, False, row_band=band)
+                    assert _same_bits(want[band[0]:band[1]], gb), (shape, variant, size, band)
+
+
+def test_single_pass_box_mean_vs_scipy():
+    """... and against the reference's own arithmetic: scipy.ndimage.uniform_filter(mode='reflect') on f32
+    (algorithms/_nan_utils.py:18-47, handle_nan_with_uniform: U(filled) / U(valid))."""
+    from scipy import ndimage
+    from fujishadergpu_b200 import kernels as k
+    rng = np.random.default_rng(4)
+    g = (rng.random((700, 900), dtype=np.float32) * 900 + 100).astype(np.float32)
+    for size in (65, 257):
+        got = _grid_mean(k, torch.from_numpy(g).cuda(), size, False).cpu().numpy()
+        want = ndimage.uniform_filter(g, size=size, mode="reflect")
+        assert np.array_equal(got, want), size
+    gn = g.copy()
+    gn[300:420, 200:520] = np.nan
+    gn[::41, ::29] = np.nan
+    valid = (~np.isnan(gn)).astype(np.float32)
+    filled = np.where(np.isnan(gn), np.float32(0), gn)
+    for size in (65, 257):
+        got = _grid_mean(k, torch.from_numpy(gn).cuda(), size, False).cpu().numpy()
+        num = ndimage.uniform_filter(filled, size=size, mode="reflect")
+        den = ndimage.uniform_filter(valid, size=size, mode="reflect")
+        want = np.where(den > 0, num / np.where(den > 0, den, 1), np.float32(0)).astype(np.float32)
+        assert np.array_equal(got, want), size

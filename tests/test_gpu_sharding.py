@@ -120,6 +120,14 @@ def _nccl_worker(rank, world, port, path, out_dir):
     out3, scale3 = sh.topousm_fast_sharded_with_stats(view, H, rank, world, radii=radii, weights=w, dist=dist, dem_ext=ext)
     assert scale3 == scale
     assert torch.equal(torch.nan_to_num(out, nan=-7777.0), torch.nan_to_num(out3, nan=-7777.0))
+    # bands in symmetric memory: the window gather reads the other ranks' bands directly over NVLink (PeerBands)
+    pext, pview = sh.haloed_band(H, dem.shape[1], world, rank, radii, device=band.device, peer_group=dist.group.WORLD)
+    assert sh.PeerBands.of(pext) is not None, "symmetric memory is expected to work on an NVLink node"
+    pview.copy_(band)
+    for _ in range(2):   # twice: the closing barrier of a step lets the next one refill / reread the bands
+        out4, scale4 = sh.topousm_fast_sharded_with_stats(pview, H, rank, world, radii=radii, weights=w, dist=dist, dem_ext=pext)
+        assert scale4 == scale
+        assert torch.equal(torch.nan_to_num(out, nan=-7777.0), torch.nan_to_num(out4, nan=-7777.0))
     np.save(os.path.join(out_dir, f"out_{rank}.npy"), out.cpu().numpy())
     if rank == 0:
         np.save(os.path.join(out_dir, "scale.npy"), np.array([scale]))
