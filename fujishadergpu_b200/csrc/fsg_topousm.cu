@@ -489,6 +489,7 @@ struct FusedParams {
   int64_t tile_row0, tile_row1;
   // v8 (interior fast path): strips of V8_TW columns from v8_col0, rows [v8_row0, v8_row1), NaN block flags
   int v8_col0;
+  int v8_xlast;   // first column of the last strip (the last strip may overlap its neighbour to end at the region's edge)
   int64_t v8_row0, v8_row1;
   int* v8_flags;
 };
@@ -1360,12 +1361,12 @@ static int launch_v6_rect(const FusedParams& base, int64_t r0, int64_t r1, int64
   return FSG_OK;
 }
 
-// Rows per CTA of the v8 launch (a multiple of the 256-row flag blocks).  One CTA per SM, CTAs handed out in launch
-// order: the makespan of the candidates is simulated with a CTA costing (rows + the rows a restart is worth) and
-// the shortest one wins -- at 8192 rows x 341 strips the difference between 9.2 waves of 2048-row CTAs and 6.9
-// waves of 2816-row CTAs is 5 % of the launch.
+// Rows per CTA of the v8 launch (a multiple of the 16-row batch; a CTA that meets a NaN flags the 256-row block
+// and restarts behind it, wherever its band ends).  One CTA per SM, CTAs handed out in launch order: the makespan of
+// every candidate is computed with a CTA costing (rows + the rows a restart is worth) and the shortest one wins --
+// at 8128 rows x 341 strips the difference between 9.2 waves of 2048-row CTAs and 29.95 waves of 640-row CTAs is
+// 8 % of the launch; a 4128^2 statistics window runs as one wave of 147 CTAs instead of 126.
 static int64_t v8_band_rows(int64_t rows, int64_t strips) {
-  if (strips * ((rows + V8_BLK - 1) / V8_BLK) <= 148) return V8_BLK;
   static std::mutex mu;
   static std::map<std::pair<int64_t, int64_t>, int64_t> memo;
   std::lock_guard<std::mutex> lock(mu);
@@ -1374,25 +1375,25 @@ static int64_t v8_band_rows(int64_t rows, int64_t strips) {
   const int64_t restart = 96;   // fill of five ring groups + the window sums, in rows of steady-state work
   int64_t best = V8_BLK;
   double best_t = 1e300;
-  for (int64_t br = V8_BLK; br <= 16 * V8_BLK; br += V8_BLK) {
+  for (int64_t br = 4 * V8_NB; br <= 4096 && br < rows + V8_NB; br += V8_NB) {
     const int64_t bands = (rows + br - 1) / br;
     if (bands > 65535) continue;
     const int64_t last = rows - (bands - 1) * br;
-    // list scheduling on 148 SMs: the next CTA (launch order) goes to the SM that frees up first
+    const int64_t c1 = br + restart, c2 = last + restart;
+    // list scheduling on 148 SMs in launch order: the strips * (bands - 1) equal CTAs fill the SMs evenly ...
+    const int64_t n_full = strips * (bands - 1);
+    const int64_t q = n_full / 148, r = n_full % 148;
     std::priority_queue<int64_t, std::vector<int64_t>, std::greater<int64_t>> sm;
-    for (int i = 0; i < 148; ++i) sm.push(0);
-    int64_t mk = 0;
-    for (int64_t b = 0; b < bands; ++b) {
-      const int64_t cost = (b + 1 == bands ? last : br) + restart;
-      for (int64_t c = 0; c < strips; ++c) {
-        const int64_t t = sm.top() + cost;
-        sm.pop();
-        sm.push(t);
-        mk = t > mk ? t : mk;
-      }
+    for (int i = 0; i < 148; ++i) sm.push((q + (i < r ? 1 : 0)) * c1);
+    int64_t mk = (q + (r ? 1 : 0)) * c1;
+    // ... and the CTAs of the last (shorter) band go to whichever SM frees up first
+    for (int64_t c = 0; c < strips; ++c) {
+      const int64_t t = sm.top() + c2;
+      sm.pop();
+      sm.push(t);
+      mk = t > mk ? t : mk;
     }
     if ((double)mk < best_t) { best_t = (double)mk; best = br; }
-    if (bands == 1) break;
   }
   memo[{rows, strips}] = best;
   return best;
@@ -1454,9 +1455,15 @@ static int launch_fused_v8(FusedParams& fp, int* flags, size_t flag_bytes, cudaS
   int64_t Xa = C0 > V8_RH ? C0 : V8_RH;
   Xa = (Xa + 3) / 4 * 4;
   int64_t xmax = C1 < W - V8_RH ? C1 : W - V8_RH;
-  const int64_t n8 = xmax > Xa ? (xmax - Xa) / V8_TW : 0;
-  const int64_t Xb = Xa + n8 * V8_TW;
+  int64_t n8 = xmax > Xa ? (xmax - Xa) / V8_TW : 0;
+  int64_t Xb = Xa + n8 * V8_TW;
   if (n8 < 1 || Yb - Ya < 4 * V8_NB) return 0;
+  int64_t xlast = Xb - V8_TW;
+  if (Xb < xmax && (xmax - V8_TW) % 4 == 0) {   // one more strip, shifted left to end at xmax (the overlap is computed
+    xlast = xmax - V8_TW;                        // twice, same values): no narrow rectangle left for the general kernel
+    ++n8;
+    Xb = xmax;
+  }
   const int64_t nblk = (Yb - Ya + V8_BLK - 1) / V8_BLK;
   if ((size_t)nblk * (size_t)n8 * sizeof(int) > flag_bytes) return 0;
 
@@ -1465,7 +1472,7 @@ static int launch_fused_v8(FusedParams& fp, int* flags, size_t flag_bytes, cudaS
   auto done = [&](int rc) { prof_end(slot, s); *rc_out = rc; return 1; };
   if (cudaMemsetAsync(flags, 0, (size_t)nblk * (size_t)n8 * sizeof(int), s) != cudaSuccess)
     return done(fail(FSG_E_CUDA, "fsg_topousm_fast: clearing the block flags failed"));
-  fp.v8_col0 = (int)Xa; fp.v8_row0 = Ya; fp.v8_row1 = Yb; fp.v8_flags = flags;
+  fp.v8_col0 = (int)Xa; fp.v8_xlast = (int)xlast; fp.v8_row0 = Ya; fp.v8_row1 = Yb; fp.v8_flags = flags;
   fp.col0 = 0; fp.col_end = 0; fp.tile_flags = nullptr; fp.strip0 = 0;
   // raster borders (and rows / columns outside the v8 grid): on the side stream, ahead of the interior launch
   SideLane* lane = fused_switches().no_side ? nullptr : side_lane();

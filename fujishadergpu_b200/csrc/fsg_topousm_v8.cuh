@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(V8_THREADS, 1) fused_kernel_v8(FusedParams p) 
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int x0 = p.v8_col0 + (int)blockIdx.x * V8_TW;
+  const int x0r = p.v8_col0 + (int)blockIdx.x * V8_TW;
+  const int x0 = x0r < p.v8_xlast ? x0r : p.v8_xlast;
   const int cs0 = x0 - V8_RH;
   const int64_t yb0 = p.v8_row0 + (int64_t)blockIdx.y * p.band_rows;
   const int64_t yb1 = (yb0 + p.band_rows < p.v8_row1) ? yb0 + p.band_rows : p.v8_row1;
