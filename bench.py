@@ -271,7 +271,7 @@ def run_gpu_arm(a) -> None:
         checksum += int(out[r:r + 8192].view(torch.int32).sum(dtype=torch.int64).item())
     checksum &= (1 << 64) - 1
     launches = k.launch_count()
-    prof = k.profile_read()
+    prof = k.profile_read(max_records=4096)
     k.profile_enable(False)
     clocks = sampler.stop()
     ms_step = total_ms / a.steps

@@ -5,7 +5,7 @@ from .. import kernels as _k
 from .. import _device as _dev
 from ._base import DaskAlgorithm
 from ._global_stats import apply_display_stretch_dask, robust_unsigned_stretch_stat_func  # noqa: F401 (re-export)
-from ._nan_utils import (_combine_multiscale_dask, _radius_to_downsample_factor, _resolve_spatial_radii_weights,
+from ._nan_utils import (overlap_whole, _combine_multiscale_dask, _radius_to_downsample_factor, _resolve_spatial_radii_weights,
                          large_radius_threshold, multiscale_response_fields)
 
 
@@ -65,7 +65,7 @@ class AmbientOcclusionAlgorithm(DaskAlgorithm):
             result = gpu_arr.map_overlap(compute_ambient_occlusion_block, depth=int(radius + 1), boundary="reflect",
                                          dtype="float32", radius=radius, **kw)
         else:
-            result = compute_ambient_occlusion_block(gpu_arr, radius=radius, **kw)
+            result = overlap_whole(gpu_arr, compute_ambient_occlusion_block, int(radius + 1), radius=radius, **kw)
         return apply_display_stretch_dask(result, params.get("global_stats"))
 
     def get_default_params(self) -> dict:

@@ -5,7 +5,7 @@ from __future__ import annotations
 from .. import kernels as _k
 from .. import _device as _dev
 from ._base import Constants, DaskAlgorithm
-from ._nan_utils import (_resolve_spatial_radii_weights, _smooth_for_radius, large_radius_threshold,
+from ._nan_utils import (overlap_whole, _resolve_spatial_radii_weights, _smooth_for_radius, large_radius_threshold,
                          multiscale_response_fields)
 
 
@@ -94,7 +94,7 @@ class HillshadeAlgorithm(DaskAlgorithm):
             return _combine_multiscale_dask(results, weights=None, agg="mean")
         if hasattr(gpu_arr, "map_overlap"):  # a dask array: same halo contract as the reference (:133)
             return gpu_arr.map_overlap(compute_hillshade_block, depth=1, boundary="reflect", dtype="float32", **kw)
-        return compute_hillshade_block(gpu_arr, **kw)
+        return overlap_whole(gpu_arr, compute_hillshade_block, 1, **kw)   # one block == the raster, same halo contract
 
     def get_default_params(self) -> dict:
         return {"azimuth": Constants.DEFAULT_AZIMUTH, "altitude": Constants.DEFAULT_ALTITUDE, "z_factor": 1.0,

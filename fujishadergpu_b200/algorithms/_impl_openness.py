@@ -5,7 +5,7 @@ from .. import kernels as _k
 from .. import _device as _dev
 from ._base import DaskAlgorithm
 from ._global_stats import apply_display_stretch_dask, robust_unsigned_stretch_stat_func  # noqa: F401 (re-export)
-from ._nan_utils import (_combine_multiscale_dask, _downsample_nan_aware, _radius_to_downsample_factor,
+from ._nan_utils import (overlap_whole, _combine_multiscale_dask, _downsample_nan_aware, _radius_to_downsample_factor,
                          _resolve_spatial_radii_weights, _upsample_to_shape, large_radius_threshold,
                          multiscale_response_fields)
 
@@ -64,7 +64,8 @@ class OpennessAlgorithm(DaskAlgorithm):
             result = gpu_arr.map_overlap(compute_openness_vectorized, depth=md + 1, boundary="reflect",
                                          dtype="float32", max_distance=md, **kw)
         else:
-            result = compute_openness_vectorized(gpu_arr, max_distance=params.get("max_distance", 50), **kw)
+            md = params.get("max_distance", 50)
+            result = overlap_whole(gpu_arr, compute_openness_vectorized, int(md) + 1, max_distance=md, **kw)
         return apply_display_stretch_dask(result, params.get("global_stats"))
 
     def get_default_params(self) -> dict:

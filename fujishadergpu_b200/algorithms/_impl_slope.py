@@ -5,7 +5,7 @@ from .. import kernels as _k
 from .. import _device as _dev
 from ._base import DaskAlgorithm
 from ._impl_hillshade import spatial_responses
-from ._nan_utils import _combine_multiscale_dask, _resolve_spatial_radii_weights, _smooth_for_radius
+from ._nan_utils import overlap_whole, _combine_multiscale_dask, _resolve_spatial_radii_weights, _smooth_for_radius
 
 
 def compute_slope_block(block, *, unit="degree", pixel_size=1.0, pixel_scale_x=None, pixel_scale_y=None):
@@ -38,7 +38,7 @@ class SlopeAlgorithm(DaskAlgorithm):
             return _combine_multiscale_dask(responses, weights=weights, agg=params.get("agg", "mean"))
         if hasattr(gpu_arr, "map_overlap"):
             return gpu_arr.map_overlap(compute_slope_block, depth=1, boundary="reflect", dtype="float32", **kw)
-        return compute_slope_block(gpu_arr, **kw)
+        return overlap_whole(gpu_arr, compute_slope_block, 1, **kw)
 
     def get_default_params(self) -> dict:
         return {"unit": "degree", "pixel_size": 1.0, "mode": "local", "radii": None, "weights": None}

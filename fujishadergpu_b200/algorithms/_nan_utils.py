@@ -165,6 +165,18 @@ def _symmetric_pad(t, depth: int):
     return t.index_select(0, ri).index_select(1, ci).contiguous()
 
 
+def overlap_whole(block, block_fn, depth: int, **kw):
+    """`block.map_overlap(block_fn, depth, boundary='reflect')` when the whole raster is ONE block (a device array
+    handed to Algorithm.process): mirror-pad (edge inclusive) by the depth, evaluate, crop -- so the ring of `depth`
+    pixels along the raster edge sees the mirrored neighbours the reference's Dask path gives it, not the block
+    function's own edge rule."""
+    t = _dev.as_f32_2d(block)
+    H, W = int(t.shape[0]), int(t.shape[1])
+    pad = max(1, min(int(depth), max(1, min(H, W) - 1)))
+    r = _dev.as_f32_2d(block_fn(_symmetric_pad(t, pad), **kw))
+    return _dev.like_input(r[pad:pad + H, pad:pad + W].contiguous(), block)
+
+
 def coarse_large_radius_response(block, *, block_fn, radius_kw: str, radius: float, factor: int, depth_for_radius,
                                  pixel_size: float = 1.0, pixel_scale_x=None, pixel_scale_y=None,
                                  coarse_cache: Optional[dict] = None, coarse_dem=None, coarse_decimation=None,
@@ -234,8 +246,10 @@ def multiscale_response_fields(block, scales, *, block_fn, depth_for_scale, radi
                 pixel_scale_x=pixel_scale_x, pixel_scale_y=pixel_scale_y, coarse_cache=cache, coarse_dem=coarse_dem,
                 coarse_decimation=coarse_decimation, **block_kwargs))
         else:
-            out.append(block_fn(block, pixel_size=pixel_size, pixel_scale_x=pixel_scale_x, pixel_scale_y=pixel_scale_y,
-                                **{radius_kw: sv}, **block_kwargs))
+            # reference :516-522: map_overlap(block_fn, depth=max(1, min(d, smallest chunk - 1)), boundary='reflect') --
+            # with one block == the whole raster that is: mirror-pad (edge inclusive) by the depth, evaluate, crop
+            out.append(overlap_whole(block, block_fn, d, pixel_size=pixel_size, pixel_scale_x=pixel_scale_x,
+                                     pixel_scale_y=pixel_scale_y, **{radius_kw: sv}, **block_kwargs))
     return out
 
 
@@ -289,4 +303,5 @@ __all__ = [
     "_bilinear_sample_coarse", "handle_nan_with_uniform", "restore_nan", "handle_nan_with_gaussian", "_smooth_for_radius", "large_radius_threshold",
     "_combine_multiscale_dask", "coarsen_factor_for_shape", "coarse_large_radius_response",
     "multiscale_response_fields",
+    "overlap_whole",
 ]

@@ -461,10 +461,10 @@ def topousm_fast_sharded_with_stats(band: torch.Tensor, H: int, rank: int, world
 _PREP_STREAMS: dict = {}
 
 
-def _side_stream(device, name):
+def _side_stream(device, name, priority: int = 0):
     key = (device.index, name)
     if key not in _PREP_STREAMS:
-        _PREP_STREAMS[key] = torch.cuda.Stream(device=device)
+        _PREP_STREAMS[key] = torch.cuda.Stream(device=device, priority=priority)
     return _PREP_STREAMS[key]
 
 
@@ -954,7 +954,7 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
         csum += out[r:r + 8192].view(torch.int32).sum(dtype=torch.int64)
     dist.all_reduce(csum, op=dist.ReduceOp.SUM)
     checksum = int(csum.item()) & ((1 << 64) - 1)
-    prof = k.profile_read()
+    prof = k.profile_read(max_records=4096)
     k.profile_enable(False)
     clocks = sampler.stop() if sampler is not None else None
     dist.barrier()

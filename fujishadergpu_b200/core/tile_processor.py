@@ -164,6 +164,15 @@ class HostTilePipeline:
                 raise ValueError(f"{self.algorithm}: integer output needs an explicit value range")
             self.qp = quantize_params(rng[0], rng[1], self.output_dtype)
         self.workspace = None
+        if self.algorithm != "topousm_fast":
+            # the other algorithms run their LOCAL block kernel here (one call, no multiscale combine, no display
+            # stretch): say so instead of silently ignoring the request -- cli.run / Algorithm.process do the rest
+            if str(self.params.get("mode", "local")).lower() == "spatial":
+                raise ValueError(f"HostTilePipeline: {self.algorithm} runs in local mode only; use "
+                                 "algorithms.ALGORITHMS[...].process (cli.run) for --mode spatial")
+            for key in ("radii", "weights", "agg"):
+                if self.params.get(key) not in (None, [], ()):
+                    raise ValueError(f"HostTilePipeline: '{key}' is a spatial-mode parameter and is not applied here")
         if self.algorithm == "topousm_fast":
             need = _k.topousm_fast_workspace_bytes(self.shape, self.params["radii"], self.params.get("pixel_size", 1.0))
             self.workspace = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
@@ -190,6 +199,10 @@ class HostTilePipeline:
                     "openness": ("openness_type", "num_directions", "max_distance"),
                     "ambient_occlusion": ("num_samples", "radius", "intensity")}[algo]
             kw = {k: p[k] for k in keys + ("pixel_size", "pixel_scale_x", "pixel_scale_y") if k in p}
+            if algo in ("openness", "ambient_occlusion"):   # the reference's [p1, p99] display stretch (global stats)
+                inject_global_stats(self.dev_in, algo, p)
+                if p.get("global_stats") is not None:
+                    kw["stretch"] = p["global_stats"]
             self.dev_out = fn(self.dev_in, output_dtype=self.output_dtype, qp=self.qp, **kw)
         for r in range(0, H, self.chunk_rows):
             host_out[r:r + self.chunk_rows].copy_(self.dev_out[r:r + self.chunk_rows], non_blocking=True)

@@ -186,8 +186,9 @@ def _geo_entries(ifd: _Ifd, transform, epsg) -> None:
         ifd.add(TAG_PIXELSCALE, T_DOUBLE, [abs(dx), abs(dy), 0.0])
         ifd.add(TAG_TIEPOINT, T_DOUBLE, [0.0, 0.0, 0.0, x0, y0, 0.0])
     if epsg is not None:
+        from .raster_info import is_geographic_epsg
         code = int(epsg)
-        geographic = 4000 <= code < 5000
+        geographic = is_geographic_epsg(code)      # the SAME rule that chose degree -> metre scaling on the way in
         keys = [1, 1, 0, 3,
                 1024, 0, 1, 2 if geographic else 1,       # GTModelTypeGeoKey
                 1025, 0, 1, 1,                            # GTRasterTypeGeoKey: PixelIsArea

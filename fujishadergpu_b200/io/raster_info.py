@@ -28,6 +28,8 @@ def is_geographic_epsg(epsg: Optional[int]) -> bool:
     if epsg is None:
         return False
     code = int(epsg)
+    if code in (4087, 4088, 4936, 4978):       # projected (World Equidistant Cylindrical) / geocentric codes of that range
+        return False
     return 4000 <= code < 5000 or code in (6668, 6318, 7844)    # JGD2011, NAD83(2011), GDA2020
 
 

@@ -946,6 +946,15 @@ def stats_window_geometry(algorithm: str, params: dict, max_tile: int = 4096):
     return margin, max(min(2048, max(1, int(max_tile))), 4 * margin)
 
 
+def with_overlap(fn, dem: np.ndarray, depth: int, **kw) -> np.ndarray:
+    """`dem.map_overlap(fn, depth, boundary='reflect')` with one chunk == the whole raster (the spatial-mode small
+    radii, algorithms/_nan_utils.py:516-522): edge-inclusive mirror padding by the depth, the block function, crop."""
+    h, w = dem.shape
+    d = max(1, min(int(depth), max(1, min(h, w) - 1)))
+    out = fn(np.pad(dem, d, mode="symmetric"), **kw)
+    return np.ascontiguousarray(out[..., d:d + h, d:d + w])
+
+
 def halo_depth(algorithm: str, params: dict) -> int:
     """map_overlap depth per algorithm: _impl_topousm_fast.py:203, _impl_hillshade.py:133,
     _impl_slope.py:71, _impl_curvature.py:92, _impl_openness.py:204-206."""

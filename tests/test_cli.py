@@ -90,7 +90,8 @@ def test_cli_end_to_end_against_oracle(tmp_path):
     out = str(tmp_path / "hs.tif")
     assert main([src, out, "--algorithm", "hillshade", "--mode", "local", "--output-dtype", "uint8"]) == 0
     got, meta = read_geotiff(out)
-    want = orc.encode_array(orc.hillshade_block(dem, pixel_size=2.0, pixel_scale_x=2.0, pixel_scale_y=-2.0),
+    # (Algorithm.process on the whole raster = map_overlap(depth=1, boundary='reflect') with one block)
+    want = orc.encode_array(orc.with_overlap(orc.hillshade_block, dem, 1, pixel_size=2.0, pixel_scale_x=2.0, pixel_scale_y=-2.0),
                             orc.encode_params(0.0, 1.0, "uint8"), "uint8")
     assert np.array_equal(got == 0, want == 0) and np.abs(got.astype(int) - want.astype(int)).max() <= 1
     assert meta["epsg"] == 6677 and meta["transform"] == (500000.0, 2.0, 0.0, 4100000.0, 0.0, -2.0) and meta["nodata"] == 0.0

@@ -264,3 +264,25 @@ def test_sharded_cog_writer_equals_single_writer(tmp_path, world):
         th.join(timeout=300)
     assert not errs, errs
     assert open(out, "rb").read() == open(ref, "rb").read()
+
+
+@pytest.mark.parametrize("epsg,geographic", [(4326, True), (6668, True), (6318, True), (7844, True), (6677, False),
+                                             (32654, False), (4087, False), (4978, False)])
+def test_geokeys_follow_the_shared_geographic_rule(tmp_path, epsg, geographic):
+    """The writer tags GTModelType / Geographic- vs ProjectedCSType with the same rule that picked the degree ->
+    metre scaling on the way in (io/raster_info.is_geographic_epsg): JGD2011 (6668) is geographic."""
+    from fujishadergpu_b200.io.cog_writer import write_tiff_pyramid
+    from fujishadergpu_b200.io.raster_info import is_geographic_epsg
+    from fujishadergpu_b200.io import geotiff_reader as gr
+    assert is_geographic_epsg(epsg) is geographic
+    p = str(tmp_path / "g.tif")
+    write_tiff_pyramid(p, [np.zeros((64, 64), dtype=np.uint8)], nodata=0, transform=(139.0, 1e-4, 0.0, 36.0, 0.0, -1e-4),
+                       epsg=epsg)
+    with open(p, "rb") as fh:
+        ifds, _big = gr._read_ifds(fh)
+    keys = list(ifds[0][34735])
+    entries = {keys[i]: keys[i + 3] for i in range(4, len(keys), 4)}
+    assert entries[1024] == (2 if geographic else 1)
+    assert entries[2048 if geographic else 3072] == epsg and (3072 if geographic else 2048) not in entries
+    _a, meta = gr.read_geotiff(p)
+    assert meta["epsg"] == epsg

@@ -85,9 +85,11 @@ def test_spatial_mode_algorithm_classes_vs_oracle():
     w = orc.pow2_weights(3)
     # slope / curvature: _combine_multiscale_dask (weights cleaned in Python floats)
     clean = [float(x) / float(sum(w)) for x in w]
+    depth = {"slope": lambda r: max(2, int(r * 2 + 1)), "curvature": lambda r: max(3, int(r * 2 + 2))}
     for name, fn, extra in (("slope", orc.slope_spatial_block, dict(unit="degree")),
                             ("curvature", orc.curvature_spatial_block, dict(curvature_type="mean"))):
-        resp = [fn(dem, radius=float(r), **extra, **kw) for r in radii]
+        # small radii: map_overlap(depth, boundary='reflect') on the whole raster (reference _nan_utils.py:516-522)
+        resp = [orc.with_overlap(fn, dem, depth[name](float(r)), radius=float(r), **extra, **kw) for r in radii]
         want = resp[0] * np.float32(clean[0])
         for i in range(1, 3):
             want = want + resp[i] * np.float32(clean[i])
@@ -96,7 +98,12 @@ def test_spatial_mode_algorithm_classes_vs_oracle():
             # the per-radius responses are held to the reference in the golden test (tanh-saturation aware);
             # here the COMBINER is checked exactly, on the device responses themselves
             from fujishadergpu_b200.algorithms._impl_curvature import compute_curvature_spatial_block
-            dresp = [_np(compute_curvature_spatial_block(d, radius=float(r), **extra, **kw)) for r in radii]
+            from fujishadergpu_b200.algorithms._nan_utils import _symmetric_pad
+            dresp = []
+            for r in radii:
+                dp = depth[name](float(r))
+                full = _np(compute_curvature_spatial_block(_symmetric_pad(d, dp), radius=float(r), **extra, **kw))
+                dresp.append(full[dp:dp + dem.shape[0], dp:dp + dem.shape[1]])
             exact = dresp[0] * np.float32(clean[0])
             for i in range(1, 3):
                 exact = exact + dresp[i] * np.float32(clean[i])
@@ -104,7 +111,7 @@ def test_spatial_mode_algorithm_classes_vs_oracle():
         else:
             assert_close_f32(got, want, what=name)
     # hillshade: f32-normalised weights, auto radii/weights when none are given
-    resp = [orc.hillshade_spatial_block(dem, radius=float(r), **kw) for r in radii]
+    resp = [orc.with_overlap(orc.hillshade_spatial_block, dem, max(2, int(r * 2 + 1)), radius=float(r), **kw) for r in radii]
     want = orc.combine_responses(resp, weights=w, agg="mean")
     got = _np(ALGORITHMS["hillshade"].process(d, mode="spatial", radii=radii, weights=None, **kw))
     assert_close_f32(got, want, what="hillshade spatial")
@@ -122,14 +129,14 @@ def test_spatial_mode_large_radius_coarse_path_vs_oracle():
     assert F == 2
     # hillshade: f32-normalised weights
     big = orc.large_radius_response(dem, 300.0, F, orc.hillshade_spatial_block, lambda rc: max(2, int(rc * 2 + 1)), **kw)
-    small = orc.hillshade_spatial_block(dem, radius=8.0, **kw)
+    small = orc.with_overlap(orc.hillshade_spatial_block, dem, 17, radius=8.0, **kw)
     want = orc.combine_responses([small, big], weights=w, agg="mean")
     got = _np(ALGORITHMS["hillshade"].process(d, mode="spatial", radii=radii, weights=w, **kw))
     assert_close_f32(got, want, rtol=1e-5, atol=2e-6, what="hillshade spatial, large radius")
     # slope: python-float weights
     big = orc.large_radius_response(dem, 300.0, F, orc.slope_spatial_block, lambda rc: max(2, int(rc * 2 + 1)),
                                     unit="degree", **kw)
-    small = orc.slope_spatial_block(dem, radius=8.0, unit="degree", **kw)
+    small = orc.with_overlap(orc.slope_spatial_block, dem, 17, radius=8.0, unit="degree", **kw)
     want = small * np.float32(0.5) + big * np.float32(0.5)
     got = _np(ALGORITHMS["slope"].process(d, mode="spatial", radii=radii, weights=w, unit="degree", **kw))
     assert_close_f32(got, want, rtol=1e-5, atol=2e-5, what="slope spatial, large radius")
@@ -416,12 +423,14 @@ def test_ambient_occlusion_classes_stretch_and_encoding():
     d = _cuda(dem)
     kw = dict(num_samples=16, radius=12.0, intensity=1.0, pixel_size=1.0, pixel_scale_x=1.0, pixel_scale_y=-1.0)
     want = orc.ambient_occlusion_block(dem, **kw)
-    assert_close_f32(_np(ALGORITHMS["ambient_occlusion"].process(d, **kw)), want, what="ao local")
+    # Algorithm.process on a device array = map_overlap(depth=radius + 1, boundary='reflect') with one block
+    want_ov = orc.with_overlap(orc.ambient_occlusion_block, dem, int(kw.get("radius", 10.0) + 1), **kw)
+    assert_close_f32(_np(ALGORITHMS["ambient_occlusion"].process(d, **kw)), want_ov, what="ao local")
     stats = orc.p1_p99_stretch_stats(want)
     want_st = orc.display_stretch(want, stats)
     assert_close_f32(_np(TileAO().process(d, global_stats=stats, **kw)), want_st, rtol=2e-5, atol=2e-6, what="ao tile stretch")
-    assert_close_f32(_np(ALGORITHMS["ambient_occlusion"].process(d, global_stats=stats, **kw)), want_st, rtol=2e-5,
-                     atol=2e-6, what="ao dask-class stretch")
+    assert_close_f32(_np(ALGORITHMS["ambient_occlusion"].process(d, global_stats=stats, **kw)),
+                     orc.display_stretch(want_ov, stats), rtol=2e-5, atol=2e-6, what="ao dask-class stretch")
     qp = quantize_params(*resolve_output_range("ambient_occlusion"), "uint8")
     got8 = _np(k.ambient_occlusion(d, output_dtype="uint8", qp=qp, **kw)).astype(np.int32)
     want8 = orc.encode_array(want, qp, "uint8").astype(np.int32)
@@ -429,7 +438,7 @@ def test_ambient_occlusion_classes_stretch_and_encoding():
     assert np.abs(got8 - want8).max() <= 1
     # spatial mode: two radii mixed with the automatic 2^n weights
     radii = [6, 40]
-    resp = [orc.ambient_occlusion_spatial_block(dem, **{**kw, "radius": float(r)}) for r in radii]
+    resp = [orc.with_overlap(orc.ambient_occlusion_spatial_block, dem, int(r) + 1, **{**kw, "radius": float(r)}) for r in radii]
     want_sp = orc.combine_responses(resp, weights=orc.pow2_weights(2), agg="mean")
     got_sp = _np(ALGORITHMS["ambient_occlusion"].process(d, mode="spatial", radii=radii, weights=None, **kw))
     assert_close_f32(got_sp, want_sp, what="ao spatial")
@@ -440,7 +449,8 @@ def test_openness_spatial_multi_radius_vs_oracle():
     dem = orc.synth_dem(300, 420, seed=43, nodata=True)
     kw = dict(openness_type="positive", num_directions=8, pixel_size=1.0)
     radii, w = [8, 40, 120], [0.5, 0.3, 0.2]
-    resp = [orc.openness_spatial_block(dem, max_distance=float(int(max(2, round(float(r))))), **kw) for r in radii]
+    resp = [orc.with_overlap(orc.openness_spatial_block, dem, int(max(2, round(float(r)))) + 1,
+                             max_distance=float(int(max(2, round(float(r))))), **kw) for r in radii]
     want = orc.combine_responses(resp, weights=w, agg="mean")
     got = _np(ALGORITHMS["openness"].process(_cuda(dem), mode="spatial", radii=radii, weights=w, **kw))
     assert_close_f32(got, want, what="openness spatial 3 radii")
