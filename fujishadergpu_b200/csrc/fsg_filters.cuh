@@ -23,8 +23,11 @@ struct Grid {
 
 // pass A (axis 0) for global output rows [oy0, oy0+oh); tv/tw: f32 planes oh x w (ld = w).
 int launch_box_axis0(const Grid& g, int size, float* tv, float* tw, int64_t oy0, int64_t oh, cudaStream_t s);
+// need_scratch (void_fill_need_bytes(h, w) bytes, whole-grid void fill only, may be NULL): the pass is evaluated only
+// on the (row, 256-column tile) pairs within `radius` columns of a NaN cell -- all the fill's axis-1 pass reads.
+size_t void_fill_need_bytes(int64_t h, int64_t w);
 int launch_gauss_axis0(const Grid& g, const double* taps_dev, int radius, float* tv, float* tw, const int* run_flag,
-                       int64_t oy0, int64_t oh, cudaStream_t s);
+                       int64_t oy0, int64_t oh, cudaStream_t s, unsigned char* need_scratch = nullptr);
 
 // pass B (axis 1) + combine.  mode 0: mean = tw>0 ? tv/tw : 0 -> out
 //                            mode 1 (void fill, _nan_utils.py:655-667): where isnan(orig) & (sw > 0.5):

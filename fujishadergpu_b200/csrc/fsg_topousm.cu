@@ -62,6 +62,7 @@ struct HostPlan {
   size_t off_tv, off_tw;   // scratch planes (max over users)
   size_t off_taps;         // f64 taps scratch
   size_t off_flags;        // ints: [0..3] level has void cell, [4..7] level still has NaN after fill
+  size_t off_need;         // bytes: (row, tile) maps of the enclosed-void fill (void_fill_need_bytes of the largest level)
   size_t off_v8flags, v8flag_bytes;   // NaN-block flags of the interior fast path (fused_kernel_v8)
   size_t total;
   int taps_cap;
@@ -153,6 +154,14 @@ static int make_plan(int64_t H, int64_t W, const int32_t* radii, int n, double p
   p->off_tw = off; off = align_up(off + scratch * 4, 256);
   p->off_taps = off; off = align_up(off + (size_t)taps_cap * 8, 256);
   p->off_flags = off; off = align_up(off + 64, 256);
+  {
+    size_t nb = 0;
+    for (int k = 0; k < p->n_levels; ++k) {
+      const size_t b = void_fill_need_bytes(p->levels[k].h, p->levels[k].w);
+      nb = b > nb ? b : nb;
+    }
+    p->off_need = off; off = align_up(off + nb, 256);
+  }
   p->v8flag_bytes = (size_t)((H + 255) / 256 + 1) * (size_t)(W / 192 + 2) * sizeof(int);
   p->off_v8flags = off; off = align_up(off + p->v8flag_bytes, 256);
   p->taps_cap = taps_cap;
@@ -1633,7 +1642,7 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
       float* grid_k = (float*)(base + l.off);
       Grid g{grid_k, l.h, l.w, l.w};
       if ((rc = launch_gauss_taps(sigma, radius, taps, s))) return rc;
-      if ((rc = launch_gauss_axis0(g, taps, radius, tv, tw, flags + k, 0, l.h, s))) return rc;
+      if ((rc = launch_gauss_axis0(g, taps, radius, tv, tw, flags + k, 0, l.h, s, base + plan.off_need))) return rc;
       if ((rc = launch_gauss_axis1(tv, tw, l.h, l.w, taps, radius, COMBINE_VOIDFILL, grid_k, flags + k, flags + 4 + k, s)))
         return rc;
     }
