@@ -340,6 +340,13 @@ struct GsRow {
   float v[GS_VEC + 2];   // columns c-1 .. c+4
 };
 
+// L2 prefetch of the 16 bytes a thread will load from row gy (no register, no scoreboard): the rows in flight in
+// registers hide the L2 latency, these hide the DRAM latency behind them.
+constexpr int GS_PF = 8;   // rows ahead of the register pipeline
+__device__ __forceinline__ void gs_prefetch(const GradParams& p, int64_t gy, int64_t c) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dem + (gy - p.buf_row0) * p.ld_in + c));
+}
+
 __device__ __forceinline__ void gs_issue(const GradParams& p, int64_t gy, int64_t c, GsRow& r) {
   const float* row = p.dem + (gy - p.buf_row0) * p.ld_in;
   if (c + GS_VEC <= p.W) {
@@ -381,6 +388,9 @@ __global__ void __launch_bounds__(GS_THREADS, 3) grad_stream_kernel(const __grid
 #pragma unroll
     for (int q = 0; q < AHEAD; ++q)
       if (y0 + q <= last_needed) gs_issue(p, y0 + q, c, r[1 + q]);
+#pragma unroll
+    for (int q = AHEAD; q < AHEAD + GS_PF; ++q)
+      if (y0 + q <= last_needed) gs_prefetch(p, y0 + q, c);
     const bool vec_out = (p.ld_out % 4 == 0) && (c + GS_VEC <= p.W);
     const bool scale = p.zscale != 1.0f;
     nanprobe += ((r[0].v[1] + r[0].v[2]) + (r[0].v[3] + r[0].v[4]));
@@ -394,6 +404,7 @@ __global__ void __launch_bounds__(GS_THREADS, 3) grad_stream_kernel(const __grid
           GsRow& cur = r[(j + 1) % NS];
           GsRow& next = r[(j + 2) % NS];
           if (y + AHEAD <= last_needed) gs_issue(p, y + AHEAD, c, r[(j + 1 + AHEAD) % NS]);
+          if (y + AHEAD + GS_PF <= last_needed) gs_prefetch(p, y + AHEAD + GS_PF, c);
           float res[GS_VEC];
 #pragma unroll
           for (int k = 0; k < GS_VEC; ++k) {
@@ -519,6 +530,11 @@ __global__ void __launch_bounds__(GS_THREADS, 2) curv_stream_kernel(const __grid
 #pragma unroll 1
     for (int64_t y = y0; y < y1; ++y) {
       cs_issue(p, y + 5, c, q3);
+      {   // L2 prefetch GS_PF rows ahead of the register pipeline (clamped like the loads)
+        int64_t by = y + 5 + GS_PF - p.buf_row0;
+        by = by < 0 ? 0 : (by > p.buf_rows - 1 ? p.buf_rows - 1 : by);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dem + by * p.ld_in + c));
+      }
       float res[GS_VEC];
 #pragma unroll
       for (int k = 0; k < GS_VEC; ++k) {
