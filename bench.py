@@ -317,6 +317,8 @@ def run_gpu_arm(a) -> None:
     # their 256-row blocks leave the interior fast path for the general kernel) -- reported, not the headline
     nodata_ms = None
     try:
+        if a.no_nodata_variant:
+            raise RuntimeError("skipped (--no-nodata-variant)")
         k.synth_dem((H, W), seed=20261017 + 2, device=dev, nodata=True, out=dem)
         for _ in range(2):
             k.topousm_fast(dem, radii=RADII, weights=weights, pixel_size=1.0, norm_scale=float(st[0]), workspace=ws, out=out)
@@ -399,6 +401,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-nodata-variant", action="store_true", help="skip the NoData main-pass timing (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup

@@ -318,7 +318,8 @@ __global__ void gauss_taps_kernel(double sigma, int radius, double* w) {
 // the axis-0 pass (2 * radius + 1 taps in f64 per cell: 2049 on the level-4 grid of a 65536^2 raster) is evaluated only
 // on the (row, 256-column tile) pairs within reach of a void cell.  3 % NoData: 834 -> 130 ms for the main pass.
 __global__ void __launch_bounds__(256) void_tiles_kernel(const float* __restrict__ grid, int64_t h, int64_t w, int nt,
-                                                         const int* run_flag, unsigned char* __restrict__ vt) {
+                                                         const int* run_flag, unsigned char* __restrict__ vt,
+                                                         int* __restrict__ vlist, int* __restrict__ vcount) {
   if (run_flag && *run_flag == 0) return;
   const int lane = threadIdx.x & 31;
   const int64_t item0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -333,34 +334,57 @@ __global__ void __launch_bounds__(256) void_tiles_kernel(const float* __restrict
       if (x < w) { const float v = row[x]; any |= !(v == v); }
     }
     any = __any_sync(0xffffffffu, any);
-    if (lane == 0) vt[item] = any ? 1 : 0;
+    if (lane == 0) {
+      vt[item] = any ? 1 : 0;
+      if (any) vlist[atomicAdd(vcount, 1)] = (int)item;
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) need_tiles_kernel(const unsigned char* __restrict__ vt, int64_t h, int nt, int reach,
-                                                         const int* run_flag, unsigned char* __restrict__ need) {
+                                                         const int* run_flag, int* __restrict__ nlist,
+                                                         int* __restrict__ ncount) {
   if (run_flag && *run_flag == 0) return;
-  for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < h * nt; item += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t y = item / nt;
-    const int t = (int)(item - y * nt);
-    int lo = t - reach, hi = t + reach;
-    lo = lo < 0 ? 0 : lo;
-    hi = hi > nt - 1 ? nt - 1 : hi;
-    unsigned char any = 0;
-    for (int k = lo; k <= hi; ++k) any |= vt[y * nt + k];
-    need[item] = any;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = h * nt;
+  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total;
+       base += (int64_t)gridDim.x * blockDim.x) {   // (whole warps: the append below is aggregated per warp)
+    const int64_t item = base + lane;
+    bool any = false;
+    if (item < total) {
+      const int64_t y = item / nt;
+      const int t = (int)(item - y * nt);
+      int lo = t - reach, hi = t + reach;
+      lo = lo < 0 ? 0 : lo;
+      hi = hi > nt - 1 ? nt - 1 : hi;
+      for (int k = lo; k <= hi; ++k) any |= vt[y * nt + k] != 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, any);
+    if (m) {   // consecutive needed items stay consecutive in the list (rows / tiles next to each other share loads)
+      int pos = 0;
+      if (lane == 0) pos = atomicAdd(ncount, __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (any) nlist[pos + __popc(m & ((1u << lane) - 1u))] = (int)item;
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) gauss_axis0_kernel(Grid g, const double* __restrict__ taps, int radius,
                                                           float* __restrict__ tv, float* __restrict__ tw,
                                                           const int* run_flag, int64_t oy0, int64_t oh,
-                                                          const unsigned char* __restrict__ need, int nt) {
+                                                          const int* __restrict__ list, const int* __restrict__ list_n,
+                                                          int nt) {
   if (run_flag && *run_flag == 0) return;
-  int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= g.w) return;
-  for (int64_t yl = blockIdx.y; yl < oh; yl += gridDim.y) {   // few CTAs: the flag check is the common case
-  if (need && need[yl * nt + blockIdx.x] == 0) continue;       // (blockDim.x == VT_W: one CTA column per tile)
+  // with an item list: a 1-D grid walks the (row, tile) items that are needed (a launch the flag cancels costs ~1 200
+  // empty CTAs); else rows strided per column tile
+  const bool lin = list != nullptr;
+  const int64_t first = lin ? blockIdx.x : blockIdx.y, step = lin ? gridDim.x : gridDim.y;
+  const int64_t count = lin ? *list_n : oh;
+  for (int64_t idx = first; idx < count; idx += step) {
+  const int64_t it = lin ? list[idx] : idx;
+  const int64_t yl = lin ? it / nt : it;
+  const int64_t x = (lin ? it - yl * nt : (int64_t)blockIdx.x) * blockDim.x + threadIdx.x;   // (blockDim.x == VT_W)
+  if (x >= g.w) continue;
   const int64_t y = oy0 + yl;
   double sv, sw;
   if (y - radius >= 0 && y + radius < g.h) {
@@ -424,11 +448,17 @@ __global__ void __launch_bounds__(256) gauss_axis0_kernel(Grid g, const double* 
 __global__ void __launch_bounds__(256) gauss_axis1_kernel(const float* __restrict__ tv, const float* __restrict__ tw,
                                                           int64_t h, int64_t w, const double* __restrict__ taps,
                                                           int radius, int combine, float* out, const int* run_flag,
-                                                          int* still_nan) {
+                                                          int* still_nan, const int* __restrict__ list,
+                                                          const int* __restrict__ list_n, int nt) {
   if (run_flag && *run_flag == 0) return;
-  int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= w) return;
-  for (int64_t y = blockIdx.y; y < h; y += gridDim.y) {
+  const bool lin = list != nullptr;   // the (row, tile) items that hold a void cell, 1-D grid (see gauss_axis0_kernel)
+  const int64_t first = lin ? blockIdx.x : blockIdx.y, step = lin ? gridDim.x : gridDim.y;
+  const int64_t count = lin ? *list_n : h;
+  for (int64_t idx = first; idx < count; idx += step) {
+  const int64_t it = lin ? list[idx] : idx;
+  const int64_t y = lin ? it / nt : it;
+  const int64_t x = (lin ? it - y * nt : (int64_t)blockIdx.x) * blockDim.x + threadIdx.x;
+  if (x >= w) continue;
   if (combine == COMBINE_VOIDFILL) {
     float cur = out[y * w + x];
     if (cur == cur) continue;  // only void cells are candidates
@@ -546,7 +576,27 @@ int launch_gauss_taps(double sigma, int radius, double* taps_dev, cudaStream_t s
   return FSG_OK;
 }
 
-size_t void_fill_need_bytes(int64_t h, int64_t w) { return 2 * (size_t)h * (size_t)((w + VT_W - 1) / VT_W); }
+// scratch of the whole-grid void fill: tile map (h * nt bytes, padded), two item lists (h * nt ints each), two counters
+struct VoidScratch {
+  unsigned char* vt;
+  int* vlist;
+  int* nlist;
+  int* counts;   // [0] void items, [1] needed items
+};
+static VoidScratch void_scratch(unsigned char* p, int64_t h, int64_t nt) {
+  const size_t items = (size_t)h * (size_t)nt;
+  const size_t a = (items + 255) / 256 * 256;
+  VoidScratch v;
+  v.vt = p;
+  v.vlist = reinterpret_cast<int*>(p + a);
+  v.nlist = v.vlist + items;
+  v.counts = v.nlist + items;
+  return v;
+}
+size_t void_fill_need_bytes(int64_t h, int64_t w) {
+  const size_t items = (size_t)h * (size_t)((w + VT_W - 1) / VT_W);
+  return (items + 255) / 256 * 256 + 2 * items * 4 + 256;
+}
 
 int launch_gauss_axis0(const Grid& g, const double* taps_dev, int radius, float* tv, float* tw, const int* run_flag,
                        int64_t oy0, int64_t oh, cudaStream_t s, unsigned char* need_scratch) {
@@ -555,34 +605,43 @@ int launch_gauss_axis0(const Grid& g, const double* taps_dev, int radius, float*
   int64_t gy = (148 * 16 + gx - 1) / gx;   // ~16 CTAs per SM in total, rows are strided over
   if (gy > oh) gy = oh;
   dim3 grid((unsigned)gx, (unsigned)gy);
-  const unsigned char* need = nullptr;
   const int nt = (int)gx;
-  if (need_scratch && oy0 == 0 && oh == g.h && g.row_off == 0 && g.ld == g.w) {   // whole-grid void fill
-    unsigned char* vt = need_scratch;
-    unsigned char* nd = need_scratch + (size_t)g.h * nt;
-    void_tiles_kernel<<<148 * 4, 256, 0, s>>>(g.src, g.h, g.w, nt, run_flag, vt);
+  const int* list = nullptr;
+  const int* list_n = nullptr;
+  if (need_scratch && oy0 == 0 && oh == g.h && g.row_off == 0 && g.ld == g.w && (int64_t)g.h * nt < 2147483647LL) {
+    // whole-grid void fill: lists of the (row, tile) items that hold a void cell / lie within reach of one
+    VoidScratch v = void_scratch(need_scratch, g.h, nt);
+    FSG_CUDA_OK(cudaMemsetAsync(v.counts, 0, 2 * sizeof(int), s));
+    void_tiles_kernel<<<148 * 4, 256, 0, s>>>(g.src, g.h, g.w, nt, run_flag, v.vt, v.vlist, v.counts);
     FSG_LAUNCH_OK();
-    need_tiles_kernel<<<148 * 2, 256, 0, s>>>(vt, g.h, nt, radius / VT_W + 1, run_flag, nd);
+    need_tiles_kernel<<<148 * 2, 256, 0, s>>>(v.vt, g.h, nt, radius / VT_W + 1, run_flag, v.nlist, v.counts + 1);
     FSG_LAUNCH_OK();
-    need = nd;
+    list = v.nlist;
+    list_n = v.counts + 1;
+    grid = dim3(148 * 8);
   }
-  if (need) {   // the work sits in a few column tiles: many short row strides per tile instead of 37 long ones
-    gy = oh < 2048 ? oh : 2048;
-    grid = dim3((unsigned)gx, (unsigned)gy);
-  }
-  gauss_axis0_kernel<<<grid, 256, 0, s>>>(g, taps_dev, radius, tv, tw, run_flag, oy0, oh, need, nt);
+  gauss_axis0_kernel<<<grid, 256, 0, s>>>(g, taps_dev, radius, tv, tw, run_flag, oy0, oh, list, list_n, nt);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }
 
 int launch_gauss_axis1(const float* tv, const float* tw, int64_t h, int64_t w, const double* taps_dev, int radius,
-                       int combine, float* out, const int* run_flag, int* still_nan, cudaStream_t s) {
+                       int combine, float* out, const int* run_flag, int* still_nan, cudaStream_t s,
+                       const unsigned char* void_tiles) {
   const int64_t gx = (w + 255) / 256;
   int64_t gy = (148 * 16 + gx - 1) / gx;
-  if (combine == COMBINE_VOIDFILL) gy = 2048;   // only void cells do work, and they cluster in a few column tiles
   if (gy > h) gy = h;
   dim3 grid((unsigned)gx, (unsigned)gy);
-  gauss_axis1_kernel<<<grid, 256, 0, s>>>(tv, tw, h, w, taps_dev, radius, combine, out, run_flag, still_nan);
+  const int* list = nullptr;
+  const int* list_n = nullptr;
+  if (void_tiles && combine == COMBINE_VOIDFILL) {   // the items launch_gauss_axis0 listed (same h, w)
+    VoidScratch v = void_scratch(const_cast<unsigned char*>(void_tiles), h, gx);
+    list = v.vlist;
+    list_n = v.counts;
+    grid = dim3(148 * 8);
+  }
+  gauss_axis1_kernel<<<grid, 256, 0, s>>>(tv, tw, h, w, taps_dev, radius, combine, out, run_flag, still_nan, list, list_n,
+                                          (int)gx);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }

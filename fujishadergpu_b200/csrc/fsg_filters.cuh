@@ -34,8 +34,11 @@ int launch_gauss_axis0(const Grid& g, const double* taps_dev, int radius, float*
 //                                    orig = sv / max(sw, 1e-6) (in place); sets *still_nan if NaN remains
 enum { COMBINE_MEAN = 0, COMBINE_VOIDFILL = 1 };
 int launch_box_axis1(const float* tv, const float* tw, int64_t h, int64_t w, int size, float* out, cudaStream_t s);
+// void_tiles (COMBINE_VOIDFILL only, may be NULL): the first h * ceil(w / 256) bytes of the need scratch
+// launch_gauss_axis0 filled (1 = the tile of that row holds a void cell)
 int launch_gauss_axis1(const float* tv, const float* tw, int64_t h, int64_t w, const double* taps_dev, int radius,
-                       int combine, float* out, const int* run_flag, int* still_nan, cudaStream_t s);
+                       int combine, float* out, const int* run_flag, int* still_nan, cudaStream_t s,
+                       const unsigned char* void_tiles = nullptr);
 
 // both box passes in one kernel (intermediate planes of a 16-row batch in shared memory), sizes 3..257: returns 1
 // when launched (*rc = status), 0 when the size is out of range -- same values as axis0 + axis1 bit for bit

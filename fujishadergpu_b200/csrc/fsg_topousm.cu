@@ -1643,7 +1643,8 @@ static int run_topousm(const float* dem, void* out, int64_t H, int64_t W, int64_
       Grid g{grid_k, l.h, l.w, l.w};
       if ((rc = launch_gauss_taps(sigma, radius, taps, s))) return rc;
       if ((rc = launch_gauss_axis0(g, taps, radius, tv, tw, flags + k, 0, l.h, s, base + plan.off_need))) return rc;
-      if ((rc = launch_gauss_axis1(tv, tw, l.h, l.w, taps, radius, COMBINE_VOIDFILL, grid_k, flags + k, flags + 4 + k, s)))
+      if ((rc = launch_gauss_axis1(tv, tw, l.h, l.w, taps, radius, COMBINE_VOIDFILL, grid_k, flags + k, flags + 4 + k, s,
+                                   base + plan.off_need)))
         return rc;
     }
   }
