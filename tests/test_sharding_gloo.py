@@ -192,8 +192,9 @@ def test_band_bounds_are_aligned_and_cover():
 
 
 def test_window_owner_assignment_is_balanced_and_local():
-    """Statistics windows go to the rank that already holds most of their rows; no rank gets more than
-    ceil(n / world) windows (the critical path of the pre-pass), every rank computes the same assignment."""
+    """Statistics windows: the assignment that lets the slowest rank finish first and moves the fewest rows (cost model
+    of assign_window_owners); no rank gets more than ceil(n / world) windows, never more traffic than round-robin,
+    every rank computes the same assignment."""
     from fujishadergpu_b200.algorithms._norm_stats import stratified_windows
     H = W = 65536
     wins = stratified_windows(W, H, 0, H, 0, W, grid=3, tile=8256)
