@@ -30,6 +30,11 @@ struct SelState {
   unsigned int key_next;      // min key > key_k
   double q;
   double out[4];              // a[k], a[k+1], gamma, n
+  // compaction after level 0 (fsg_select_compact): the keys of the selected level-0 bucket, local to this rank
+  unsigned long long cmp_n;       // keys in the compact buffer
+  unsigned long long cmp_below;   // local keys below the bucket
+  unsigned int cmp_above_min;     // smallest local key above the bucket (0xffffffff: none)
+  unsigned int cmp_overflow;      // the buffer was too small (cannot happen with capacity = sample count)
 };
 
 __device__ __forceinline__ bool sample_key(float v, int take_abs, int finite_only, unsigned int* key) {
@@ -301,6 +306,7 @@ __global__ void sel_begin_kernel(SelState* st, unsigned long long* x) {
   if (threadIdx.x == 0) {
     memset(st, 0, sizeof(SelState));
     st->key_next = 0xffffffffu;
+    st->cmp_above_min = 0xffffffffu;
   }
 }
 
@@ -426,6 +432,96 @@ __global__ void sel_finish_kernel(const SelState* st, const unsigned long long* 
   result[1] = (double)ak1;
   result[2] = st->out[2];
   result[3] = (double)st->n;
+}
+
+// ---- levels 1, 2 and the a[k+1] pass on the compacted level-0 bucket -------------------------------------------
+// After the level-0 pick only the keys of one of 2048 buckets can still matter (a few per cent of the sample for
+// |topousm|): one more scan copies them out (warp-aggregated append) and counts what lies below / finds the smallest
+// key above, and the remaining three stages read the compact keys instead of the sample: two scans instead of four.
+__global__ void __launch_bounds__(256) sel_compact_kernel(Chunks c, int take_abs, int finite_only, SelState* st,
+                                                          unsigned int* __restrict__ keys, unsigned long long cap) {
+  if (st->n == 0) return;
+  const unsigned int prefix = st->prefix, mask = st->mask;
+  const int lane = threadIdx.x & 31;
+  unsigned long long below = 0;
+  unsigned int above = 0xffffffffu;
+  scan_chunks(c, [&](float v, bool in) {
+    unsigned int key = 0;
+    const bool ok = in && sample_key(v, take_abs, finite_only, &key);
+    const bool hit = ok && (key & mask) == prefix;
+    if (ok && !hit) {
+      if (key < prefix) ++below;
+      else if (key < above) above = key;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+      unsigned long long pos = 0;
+      if (lane == 0) pos = atomicAdd(&st->cmp_n, (unsigned long long)__popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (hit) {
+        const unsigned long long at = pos + __popc(m & ((1u << lane) - 1u));
+        if (at < cap) keys[at] = key;
+        else st->cmp_overflow = 1u;
+      }
+    }
+  });
+  for (int o = 16; o; o >>= 1) {
+    below += __shfl_down_sync(0xffffffffu, below, o);
+    const unsigned int other = __shfl_down_sync(0xffffffffu, above, o);
+    above = other < above ? other : above;
+  }
+  if (lane == 0) {
+    if (below) atomicAdd(&st->cmp_below, below);
+    if (above != 0xffffffffu) atomicMin(&st->cmp_above_min, above);
+  }
+}
+
+__global__ void __launch_bounds__(256) sel_hist_keys_kernel(const unsigned int* __restrict__ keys, int level,
+                                                            const SelState* st, unsigned long long* x) {
+  __shared__ unsigned int sh[2048];
+  for (int i = threadIdx.x; i < 2048; i += 256) sh[i] = 0;
+  __syncthreads();
+  if (st->n == 0) return;
+  const unsigned int prefix = st->prefix, mask = st->mask;
+  const int shift = level == 1 ? 10 : 0;
+  const unsigned int bins_mask = level == 2 ? 1023u : 2047u;
+  const unsigned long long n = st->cmp_n;
+  const unsigned long long per = (unsigned long long)gridDim.x * 256ull;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * 256ull; base < n; base += per) {   // (whole warps)
+    const unsigned long long i = base + threadIdx.x;
+    const unsigned int key = i < n ? keys[i] : 0u;
+    hist_add(sh, (key >> shift) & bins_mask, i < n && (key & mask) == prefix);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += 256)
+    if (sh[i]) atomicAdd(&x[i], (unsigned long long)sh[i]);
+}
+
+__global__ void __launch_bounds__(256) sel_next_keys_kernel(const unsigned int* __restrict__ keys, const SelState* st,
+                                                            unsigned long long* x) {
+  if (st->n == 0) return;
+  const unsigned int kk = st->key_k;
+  const unsigned long long n = st->cmp_n;
+  unsigned long long le = 0;
+  unsigned int mn = 0xffffffffu;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * 256ull + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256ull) {
+    const unsigned int key = keys[i];
+    if (key <= kk) ++le;
+    else if (key < mn) mn = key;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // what lies outside the bucket (counted once per rank)
+    le += st->cmp_below;
+    mn = st->cmp_above_min < mn ? st->cmp_above_min : mn;
+  }
+  for (int o = 16; o; o >>= 1) {
+    le += __shfl_down_sync(0xffffffffu, le, o);
+    const unsigned int other = __shfl_down_sync(0xffffffffu, mn, o);
+    mn = other < mn ? other : mn;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (le) atomicAdd(&x[SEL_X_LE], le);
+    atomicMin(&x[SEL_X_NEXT], (unsigned long long)mn);
+  }
 }
 
 // ---- exchange over peer memory (NVLink / NVSwitch) instead of all-reduce calls --------------------------------
@@ -729,6 +825,43 @@ int fsg_select_next(const float* const* chunks_host, const int64_t* rows_host, c
   if (blocks > 148 * 8) blocks = 148 * 8;
   sel_next_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(c, take_abs, finite_only, sel_state(workspace),
                                                             (unsigned long long*)workspace);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_select_compact(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                       const int64_t* ld_host, int n_chunks, int take_abs, int finite_only, void* workspace,
+                       uint32_t* keys_dev, int64_t capacity, void* stream) {
+  using namespace fsg;
+  if (n_chunks < 0 || n_chunks > MAX_CHUNKS || !workspace || capacity < 0) return fail(FSG_E_INVALID, "fsg_select_compact: bad argument");
+  if (n_chunks == 0) return FSG_OK;
+  Chunks c{};
+  int64_t tot = 0;
+  if (fill_chunks(c, chunks_host, rows_host, cols_host, ld_host, n_chunks, &tot)) return fail(FSG_E_INVALID, "fsg_select_compact: bad chunk");
+  if (tot == 0) return FSG_OK;
+  if (!keys_dev || capacity < tot) return fail(FSG_E_WORKSPACE, "fsg_select_compact: the key buffer must hold one key per sample");
+  int blocks = (int)((tot + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sel_compact_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(c, take_abs, finite_only, sel_state(workspace), keys_dev,
+                                                               (unsigned long long)capacity);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_select_hist_keys(const uint32_t* keys_dev, int level, void* workspace, void* stream) {
+  using namespace fsg;
+  if (!workspace || level < 1 || level > 2) return fail(FSG_E_INVALID, "fsg_select_hist_keys: bad argument");
+  if (!keys_dev) return FSG_OK;
+  sel_hist_keys_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(keys_dev, level, sel_state(workspace), (unsigned long long*)workspace);
+  FSG_LAUNCH_OK();
+  return FSG_OK;
+}
+
+int fsg_select_next_keys(const uint32_t* keys_dev, void* workspace, void* stream) {
+  using namespace fsg;
+  if (!workspace) return fail(FSG_E_INVALID, "fsg_select_next_keys: bad argument");
+  if (!keys_dev) return FSG_OK;
+  sel_next_keys_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(keys_dev, sel_state(workspace), (unsigned long long*)workspace);
   FSG_LAUNCH_OK();
   return FSG_OK;
 }

@@ -395,7 +395,7 @@ def count_samples(chunks: Sequence, *, finite_only: bool = True):
 
 def percentile(chunks: Sequence, q: float, *, take_abs=False, finite_only=False) -> float:
     """np.percentile(sample, q) for an f32 sample (method 'linear'); NaN when the sample is empty.
-    One pass structure: device-staged radix select (4 scans of the sample, one host synchronisation)."""
+    One pass structure: device-staged radix select (2 scans of the sample, one host synchronisation)."""
     views = _pooled_views(chunks)
     if not views:
         return float("nan")
@@ -610,7 +610,8 @@ def key_to_float(key: int, take_abs: bool) -> float:
 
 
 def staged_percentile(chunks, q: float, *, take_abs: bool, finite_only: bool, device, all_reduce=None,
-                      scale_out: Optional[torch.Tensor] = None, min_valid: float = 1e-9, peer_exchange=None):
+                      scale_out: Optional[torch.Tensor] = None, min_valid: float = 1e-9, peer_exchange=None,
+                      compact: bool = True):
     """np.percentile(sample, q) (method 'linear', f32 sample) of the union of every rank's chunks with the
     selection state kept on the device: the host only enqueues the radix-select stages and, between them,
     `all_reduce(tensor, op)` (op in {"sum", "min"}) of the exchange area -- no host round trip until the
@@ -644,11 +645,25 @@ def staged_percentile(chunks, q: float, *, take_abs: bool, finite_only: bool, de
                 all_reduce(ws[2049:2050], "sum")
                 all_reduce(ws[2050:2051], "min")
 
+    # level 0 scans the sample; the keys of the selected bucket are copied out once and levels 1, 2 and the a[k+1] pass
+    # read those (two scans instead of four)
+    n_local = sum(int(v.shape[0]) * int(v.shape[1]) for v in views)
+    keys = torch.empty(max(n_local, 1), dtype=torch.int32, device=device) if (compact and n_local) else None
+    kptr = C.c_void_p(keys.data_ptr()) if keys is not None else C.c_void_p(0)
     for level in range(3):
-        check(lib.fsg_select_hist(ptrs, rows, cols, lds, len(views), level, ta, fo, _ptr(ws), stream), "fsg_select_hist")
+        if level == 0 or not compact:
+            check(lib.fsg_select_hist(ptrs, rows, cols, lds, len(views), level, ta, fo, _ptr(ws), stream), "fsg_select_hist")
+        else:
+            check(lib.fsg_select_hist_keys(kptr, level, _ptr(ws), stream), "fsg_select_hist_keys")
         exchange(level)
         check(lib.fsg_select_pick(level, float(q32), _ptr(ws), stream), "fsg_select_pick")
-    check(lib.fsg_select_next(ptrs, rows, cols, lds, len(views), ta, fo, _ptr(ws), stream), "fsg_select_next")
+        if level == 0 and compact:
+            check(lib.fsg_select_compact(ptrs, rows, cols, lds, len(views), ta, fo, _ptr(ws), kptr, n_local, stream),
+                  "fsg_select_compact")
+    if compact:
+        check(lib.fsg_select_next_keys(kptr, _ptr(ws), stream), "fsg_select_next_keys")
+    else:
+        check(lib.fsg_select_next(ptrs, rows, cols, lds, len(views), ta, fo, _ptr(ws), stream), "fsg_select_next")
     exchange(3)
     if px is not None:
         px.barrier()   # the slots may be rewritten by the next call once every rank has read them

@@ -286,6 +286,15 @@ int fsg_select_pick(int level, float q32, void* workspace, void* stream);
 int fsg_select_next(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
                     const int64_t* ld_host, int n_chunks, int take_abs, int finite_only, void* workspace, void* stream);
 int fsg_select_finish(void* workspace, int take_abs, double* result_dev, void* stream);
+/* Two scans of the sample instead of four: after fsg_select_pick(level 0) fsg_select_compact copies the keys of the
+ * selected level-0 bucket into `keys_dev` (capacity >= the sample count, uint32) and counts what lies outside it;
+ * fsg_select_hist_keys (levels 1, 2) and fsg_select_next_keys then replace fsg_select_hist / fsg_select_next.  The
+ * exchange area and its reductions between the stages are unchanged. */
+int fsg_select_compact(const float* const* chunks_host, const int64_t* rows_host, const int64_t* cols_host,
+                       const int64_t* ld_host, int n_chunks, int take_abs, int finite_only, void* workspace,
+                       uint32_t* keys_dev, int64_t capacity, void* stream);
+int fsg_select_hist_keys(const uint32_t* keys_dev, int level, void* workspace, void* stream);
+int fsg_select_next_keys(const uint32_t* keys_dev, void* workspace, void* stream);
 /* The same exchange without collective calls, over peer memory (NVLink / NVSwitch): every rank owns
  * fsg_select_peer_slot_words() int64 words of symmetric memory mapped by all ranks of the node.  After a stage
  * (0..2: fsg_select_hist of that level, 3: fsg_select_next) a rank publishes its part of the exchange area into its

@@ -356,6 +356,9 @@ def test_staged_percentile_matches_numpy_and_two_pass():
                 old = k.percentile_two_pass([t], q, take_abs=take_abs, finite_only=finite_only)
                 assert (got == want) or (got != got and want != want), (a.size, q, take_abs, got, want)
                 assert (got == old) or (got != got and old != old), (a.size, q, take_abs, got, old)
+                # four scans of the sample (no compaction of the level-0 bucket): same value
+                full = k.staged_percentile([t], q, take_abs=take_abs, finite_only=finite_only, device=t.device, compact=False)
+                assert (got == full) or (got != got and full != full), (a.size, q, take_abs, got, full)
     allnan = _cuda(np.full((4, 9), np.nan, np.float32))
     assert k.percentile([allnan], 99.0, take_abs=True) != k.percentile([allnan], 99.0, take_abs=True)   # NaN
 
