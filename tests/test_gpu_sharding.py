@@ -122,7 +122,10 @@ def _nccl_worker(rank, world, port, path, out_dir):
     assert torch.equal(torch.nan_to_num(out, nan=-7777.0), torch.nan_to_num(out3, nan=-7777.0))
     # bands in symmetric memory: the window gather reads the other ranks' bands directly over NVLink (PeerBands)
     pext, pview = sh.haloed_band(H, dem.shape[1], world, rank, radii, device=band.device, peer_group=dist.group.WORLD)
-    assert sh.PeerBands.of(pext) is not None, "symmetric memory is expected to work on an NVLink node"
+    # (a node without symmetric-memory support falls back to send / receive inside haloed_band: same call, same result;
+    #  the marker file tells the parent which path ran)
+    if sh.PeerBands.of(pext) is not None and rank == 0:
+        open(os.path.join(out_dir, "peer_path_ran"), "w").close()
     pview.copy_(band)
     for _ in range(2):   # twice: the closing barrier of a step lets the next one refill / reread the bands
         out4, scale4 = sh.topousm_fast_sharded_with_stats(pview, H, rank, world, radii=radii, weights=w, dist=dist, dem_ext=pext)
@@ -149,6 +152,9 @@ def test_nccl_pipeline_equals_single_gpu():
         mp.spawn(_nccl_worker, args=(world, 29650, path, td), nprocs=world, join=True)
         got = np.concatenate([np.load(os.path.join(td, f"out_{r}.npy")) for r in range(world)], axis=0)
         scale = float(np.load(os.path.join(td, "scale.npy"))[0])
+        if not os.path.exists(os.path.join(td, "peer_path_ran")):
+            import warnings
+            warnings.warn("symmetric memory unavailable on this node: the peer-memory gather / exchange was not exercised")
     d = torch.from_numpy(dem).cuda()
     radii, w = [2, 8, 32, 128, 512, 2048], orc.pow2_weights(6)
     st = compute_norm_stats_device(d, "topousm_fast", {"radii": radii, "weights": w, "pixel_size": 1.0})
