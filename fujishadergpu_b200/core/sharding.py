@@ -870,6 +870,35 @@ def sharded_topousm_scale(band: torch.Tensor, H: int, rank: int, world: int, *, 
 # ------------------------------------------------------------------------------------------------
 # bench driver for N > 1 (called from bench.py under torchrun)
 # ------------------------------------------------------------------------------------------------
+def bind_host_to_gpu(device) -> dict:
+    """Pin this process to the CPUs NVML reports as local to `device` (same NUMA node / PCIe root) BEFORE the pinned
+    staging buffers are allocated, so that their pages are local and the upload / download DMA does not cross the
+    socket interconnect (one process per GPU: eight ranks share the host's memory system).  Best effort: returns what
+    was done, never raises."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device)
+        bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {i for i in range(ncpu) if (int(mask[i // 64]) >> (i % 64)) & 1}
+        allowed = set(os.sched_getaffinity(0))
+        cpus = sorted(local & allowed)
+        info.update(local_cpus=len(local), allowed_cpus=len(allowed), used_cpus=len(cpus))
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+    except Exception as e:   # NVML missing, cpuset restrictions, ...: stay where we are
+        info["error"] = repr(e)
+    return info
+
+
 def _breakdown(prof, steps):
     names = {1: "fused_main", 2: "pyramid", 3: "coarse_means", 6: "fused_stats_windows"}
     out = {}
@@ -978,6 +1007,7 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
     # e2e: pinned host band -> device -> uint8 band back to pinned host, every step
     from ..io.output_encoding import quantize_params, resolve_output_range
     qp = quantize_params(*resolve_output_range("topousm_fast"), "uint8")
+    binding = None if os.environ.get("FSG_NO_NUMA_BIND") else bind_host_to_gpu(dev)
     hin = torch.empty((r1 - r0, W), dtype=torch.float32, pin_memory=True)
     hin.copy_(band)
     hout = torch.empty((r1 - r0, W), dtype=torch.uint8, pin_memory=True)
@@ -1027,7 +1057,8 @@ def bench_sharded(a, dist, dev, metric, unit, radii, weights, clock_sampler=None
                        "out_checksum": f"{checksum:016x}"},
             "roofline": roofline, "cpu_baseline": None, "clocks": clocks,
             "e2e": {"value": px / float(dt.item()) / 1e6, "unit": unit, "h2d_bytes_per_step": px * 4,
-                    "d2h_bytes_per_step": px, "ms_per_step": float(dt.item()) * 1e3, "output_dtype": "uint8"},
+                    "d2h_bytes_per_step": px, "ms_per_step": float(dt.item()) * 1e3, "output_dtype": "uint8",
+                    "host_binding_rank0": binding},
             "gpu_launches": int(launches.item()),
         }
         print(json.dumps(line))
