@@ -95,6 +95,7 @@ _SIGNATURES = {
     "fsg_select_pick": (_I, [_I, C.c_float, _P, _P]),
     "fsg_select_next": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, _I, _I, _P, _P]),
     "fsg_select_finish": (_I, [_P, _I, _P, _P]),
+    "fsg_debug_v8_band_rows": (C.c_int64, [_L, _L]),
     "fsg_select_compact": (_I, [C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _I, _I, _I, _P, _P, _L, _P]),
     "fsg_select_hist_keys": (_I, [_P, _I, _P, _P]),
     "fsg_select_next_keys": (_I, [_P, _P, _P]),

@@ -2010,6 +2010,8 @@ int fsg_topousm_fused_band(const float* dem, int64_t dem_row0, int64_t dem_rows,
                              norm_scale, nullptr, enc, nullptr, 0, (cudaStream_t)stream);
 }
 
+int64_t fsg_debug_v8_band_rows(int64_t rows, int64_t strips) { return fsg::v8_band_rows(rows, strips); }
+
 #ifdef FSG_V8_TIMERS
 int fsg_debug_v8_timers(unsigned long long* out48) {
   return cudaMemcpyFromSymbol(out48, fsg::v8_timers, sizeof(unsigned long long) * 48) == cudaSuccess ? 0 : -1;

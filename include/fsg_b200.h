@@ -173,6 +173,8 @@ int fsg_topousm_fused_band_ws(const float* dem, int64_t dem_row0, int64_t dem_ro
 int fsg_grid_void_fill(float* grid, int64_t gh, int64_t gw, void* workspace, size_t workspace_bytes, void* stream);
 /* Re-reads the FSG_* debug environment switches (they are otherwise read once per process). */
 void fsg_debug_reload_switches(void);
+/* host-only: rows per CTA the interior fast path chooses for `rows` x `strips` (its makespan model; for tests) */
+int64_t fsg_debug_v8_band_rows(int64_t rows, int64_t strips);
 
 /* ---- overview large-radius part (algorithms/_impl_topousm_fast.py:158-186,
  *      algorithms/_nan_utils.py:255-281): out = f32(w_large)*block - bilinear(field) */

@@ -219,3 +219,41 @@ def test_tile_backend_plugin_lookup_and_nodata_replacement():
     assert np.array_equal(np.isnan(out), [[False, True], [True, True]]) and out[0, 0] == 1.0
     assert _replace_nodata_with_nan(a, None) is a
     assert np.array_equal(np.isnan(_replace_nodata_with_nan(a, float("nan"))), np.isnan(a))
+
+
+def test_v8_band_rows_minimises_its_makespan_model():
+    """fsg_debug_v8_band_rows (host-only): rows per CTA of the interior fast path = the candidate (multiples of the
+    16-row batch, 64..4096) with the smallest list-scheduling makespan on 148 SMs, a CTA costing rows + 96."""
+    import heapq
+    from fujishadergpu_b200 import _lib
+    lib = _lib.load()
+
+    def makespan(rows, strips, br):
+        bands = -(-rows // br)
+        last = rows - (bands - 1) * br
+        c1, c2 = br + 96, last + 96
+        n_full = strips * (bands - 1)
+        q, r = divmod(n_full, 148)
+        sm = [(q + (1 if i < r else 0)) * c1 for i in range(148)]
+        heapq.heapify(sm)
+        mk = (q + (1 if r else 0)) * c1
+        for _ in range(strips):
+            t = heapq.heappop(sm) + c2
+            heapq.heappush(sm, t)
+            mk = max(mk, t)
+        return mk
+
+    for rows, strips in ((65472, 341), (8128, 341), (4128, 22), (32704, 171), (16320, 85), (1000, 5), (64, 1), (4096, 1)):
+        br = int(lib.fsg_debug_v8_band_rows(rows, strips))
+        assert br % 16 == 0 and 64 <= br <= 4096
+        cands = [c for c in range(64, 4097, 16) if c < rows + 16]
+        best = min(makespan(rows, strips, c) for c in cands)
+        assert makespan(rows, strips, br) == best, (rows, strips, br)
+
+
+def test_bind_host_to_gpu_is_best_effort():
+    """The NUMA binding helper of the N > 1 bench never raises (no GPU / no NVML here: it reports why)."""
+    pytest.importorskip("torch")
+    from fujishadergpu_b200.core.sharding import bind_host_to_gpu
+    info = bind_host_to_gpu("cuda:0")
+    assert isinstance(info, dict) and "bound" in info
